@@ -1,0 +1,137 @@
+/*
+ * kgpu.h -- C ABI of libkgpu: the B200-native topology-aware GPU placement scorer
+ * that replaces the scoring path of microsoft/KubeGPU's gpuschedulerplugin.
+ *
+ * This is the drop-in boundary.  A Go host binds these entry
+ * points through cgo (`#include "kgpu.h"`); in this
+ * repository they are exercised through ctypes (kubegpu_b200/_lib.py) and through
+ * the C++ host mirror of the reference's DeviceScheduler interface
+ * (kubegpu_b200/csrc/host/).  Plain pointers and sizes only -- no C++/torch types.
+ *
+ * What each group replaces in the reference (/root/reference, commit 73e59ce):
+ *   kgpu_upload_nodes / kgpu_update_node / kgpu_remove_node
+ *       <- NvidiaGPUScheduler.AddNode / RemoveNode   gpuschedulerplugin/gpu_scheduler.go:21-32
+ *          (node cache: AddResourcesToNodeTreeCache   gpuschedulerplugin/gpu.go:192-230);
+ *          the matrix is the one nvml.GetDevices builds nvidiagpuplugin/gpu/nvml/nvml.go:37-49
+ *   kgpu_score_batch[_device]
+ *       <- NvidiaGPUScheduler.PodFitsDevice (score)   gpuschedulerplugin/gpu_scheduler.go:34-44
+ *          -> TranslatePodGPUResources                gpuschedulerplugin/gpu.go:94-127
+ *          -> findBestTreeInCache + assignGPUs        gpuschedulerplugin/gpu.go:232-271
+ *          batched over every (pod, node) pair instead of one cgo call per pair
+ *   kgpu_reduce_shards_device
+ *       <- (no reference counterpart; the reference is single-process) the final
+ *          per-pod pick over the all-gathered shard results, SURVEY.md 8(e)
+ *   kgpu_set_weights
+ *       <- the link-level grouping tables {6,5,4} / {6,5,4,3,2,1}
+ *          nvidiagpuplugin/gpu/nvidia/nvidia_gpu_manager.go:178-180
+ *   kgpu_last_error
+ *       <- Go `error` returns (gpu_scheduler.go:46-55, gpu.go:125-126)
+ *
+ * Data layouts (all little-endian, host or device as stated per function):
+ *   topo       int32[N][64]   row-major 8x8 link-level matrix per node; only the
+ *                             upper triangle (i<j) is read; values 0..15
+ *                             (0 unknown, 1..6 NVML P2P level, 7..12 NVLink links).
+ *   free_mask  int32[N]       bit i = GPU i present and free (low 8 bits).
+ *   pods       int32[P][4]    {k, pod_id, flags, reserved}; k GPUs wanted, 0..8.
+ *                             pod_id/flags/reserved are carried, not interpreted.
+ *   keys       uint64[P]      (cost << 40) | (node_id << 8) | gpu_mask, or
+ *                             KGPU_NO_FIT.  cost = sum over GPU pairs i<j in the
+ *                             mask of W[topo[i][j]]; the key is the minimum over
+ *                             all nodes and all k-subsets of free GPUs, so ties go
+ *                             to the lower node_id, then the lower mask.
+ *
+ * Threading: every call on one handle is serialised by an internal mutex.
+ * Errors: functions return KGPU_OK (0) or a negative KGPU_ERR_*; the message is
+ * kept per handle (kgpu_last_error(h)) and per thread (kgpu_last_error(NULL)).
+ * "No node fits" is a result (KGPU_NO_FIT), never an error.  Nothing here falls
+ * back to the CPU: without a usable CUDA device every call fails.
+ */
+#ifndef KGPU_H_
+#define KGPU_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KGPU_OK 0
+#define KGPU_ERR_INVALID (-1) /* bad argument / value out of domain          */
+#define KGPU_ERR_CUDA (-2)    /* CUDA runtime error (message has the detail) */
+#define KGPU_ERR_NOMEM (-3)   /* host or device allocation failed            */
+#define KGPU_ERR_COMM (-4)    /* NCCL / peer-access failure (multi-device)   */
+#define KGPU_ERR_STATE (-5)   /* call not valid in the handle's state        */
+
+#define KGPU_NO_FIT UINT64_MAX
+#define KGPU_MAX_GPUS_PER_NODE 8
+#define KGPU_NUM_LEVELS 16
+#define KGPU_MAX_WEIGHT 4095
+
+/* Kernel variants of K1 `score_pairs` (all bit-identical in result). */
+#define KGPU_VARIANT_AUTO 0          /* = LANE_PER_NODE                                      */
+#define KGPU_VARIANT_WARP_PER_PAIR 1 /* north_star mapping: warp per (pod,node), lane per subset */
+#define KGPU_VARIANT_LANE_PER_NODE 2 /* lane per node, pair costs in registers, full per-pair enumeration */
+#define KGPU_VARIANT_MEMO_BY_K 3     /* per-node best[k] computed once, pods look it up (NOT the headline) */
+
+#define KGPU_KEY_COST(key) ((uint32_t)((key) >> 40))
+#define KGPU_KEY_NODE(key) ((uint32_t)(((key) >> 8) & 0xFFFFFFFFu))
+#define KGPU_KEY_MASK(key) ((uint32_t)((key)&0xFFu))
+
+typedef struct kgpu_ctx kgpu_t;
+
+/* "major.minor.patch" of the library. */
+const char *kgpu_version(void);
+
+/* Create a scorer on CUDA device(s) dev_ids[0..ndev).  ndev == 1: one handle per
+ * GPU (one process per GPU, or several handles in one process).  ndev > 1: the
+ * handle shards the node array over the devices and combines their results
+ * (single scheduler process driving all local GPUs). */
+int kgpu_create(const int *dev_ids, int ndev, kgpu_t **out);
+int kgpu_destroy(kgpu_t *h);
+
+/* Message of the last failing call on h (or on this thread if h == NULL). */
+const char *kgpu_last_error(kgpu_t *h);
+
+/* Link-level -> cost table, 16 entries, each 0..KGPU_MAX_WEIGHT.
+ * Default {64,32,16,8,4,2,1,0,...}: level 1 (cross-CPU) costs most, NVLink 0. */
+int kgpu_set_weights(kgpu_t *h, const int32_t w[KGPU_NUM_LEVELS]);
+int kgpu_get_weights(kgpu_t *h, int32_t w[KGPU_NUM_LEVELS]);
+
+int kgpu_set_variant(kgpu_t *h, int variant);
+
+/* Replace the node array (host pointers).  node_id_base is added to the local
+ * index to form the node_id field of the keys (global id of this shard's node 0). */
+int kgpu_upload_nodes(kgpu_t *h, const int32_t *topo, const int32_t *free_mask, int64_t n,
+                      int64_t node_id_base);
+/* Overwrite one node (AddNode on an existing name / usage update). */
+int kgpu_update_node(kgpu_t *h, int64_t idx, const int32_t topo[64], int32_t free_mask);
+int kgpu_set_free_mask(kgpu_t *h, int64_t idx, int32_t free_mask);
+/* RemoveNode: the slot stays, its GPUs become unschedulable (free_mask = 0). */
+int kgpu_remove_node(kgpu_t *h, int64_t idx);
+int64_t kgpu_num_nodes(kgpu_t *h);
+
+/* Score P pods against every node: host buffers in, host buffers out
+ * (H2D copy of pods + kernel(s) + D2H copy of keys, synchronous). */
+int kgpu_score_batch(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_keys);
+
+/* Same with device buffers on the handle's device (ndev == 1 handles only),
+ * enqueued on `stream` (a cudaStream_t, NULL = the handle's stream), no sync.
+ * d_pods must be 16-byte aligned. */
+int kgpu_score_batch_device(kgpu_t *h, const int32_t *d_pods, int64_t P, uint64_t *d_keys,
+                            void *stream);
+
+/* K2: d_out[p] = min over g < G of d_gathered[g*P + p] (after an all-gather of
+ * every shard's keys), enqueued on `stream`. */
+int kgpu_reduce_shards_device(kgpu_t *h, const uint64_t *d_gathered, int G, int64_t P,
+                              uint64_t *d_out, void *stream);
+
+/* Number of CUDA kernels this handle has launched so far (bench bookkeeping). */
+int64_t kgpu_kernel_launches(kgpu_t *h);
+/* Device duration (ms, CUDA events on the launching stream) of the K1 launch(es)
+ * of the most recent kgpu_score_batch call. */
+double kgpu_last_kernel_ms(kgpu_t *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGPU_H_ */

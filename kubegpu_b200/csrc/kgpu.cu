@@ -1,0 +1,457 @@
+// kgpu.cu -- C ABI of libkgpu (include/kgpu.h) over the sm_100a kernels in
+// score_pairs.cuh.  No CPU fallback: every entry point needs a CUDA device.
+#include "../../include/kgpu.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "multi_device.h"
+#include "score_pairs.cuh"
+
+namespace {
+
+thread_local std::string t_last_error;
+
+const int32_t kDefaultWeights[16] = {64, 32, 16, 8, 4, 2, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+
+}  // namespace
+
+// One device's shard of the node array plus its scratch buffers.
+struct kgpu_shard {
+    int dev = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int32_t *d_topo = nullptr;       // [n][64]
+    int32_t *d_free = nullptr;       // [n]
+    int64_t n = 0, cap = 0;
+    int64_t node_id_base = 0;
+    int32_t *d_pods = nullptr;       // [pcap][4]
+    unsigned long long *d_keys = nullptr;    // [pcap]
+    unsigned long long *d_gather = nullptr;  // [ndev][pcap] (multi-device only)
+    unsigned long long *d_bestk = nullptr;   // [9] memo variant
+    int64_t pcap = 0;
+};
+
+struct kgpu_ctx {
+    std::mutex mu;
+    std::string err;
+    std::vector<kgpu_shard> shards;
+    int32_t W[16];
+    int variant = KGPU_VARIANT_LANE_PER_NODE;
+    int64_t n_total = 0;
+    int64_t launches = 0;
+    double last_kernel_ms = 0.0;
+    bool subsets_uploaded = false;
+    kgpu::MultiDevice *multi = nullptr;   // NCCL communicator set, ndev > 1 only
+};
+
+namespace {
+
+int fail(kgpu_ctx *h, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_last_error = buf;
+    if (h) h->err = buf;
+    return code;
+}
+
+#define KGPU_CUDA(h, expr)                                                                          \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail((h), e__ == cudaErrorMemoryAllocation ? KGPU_ERR_NOMEM : KGPU_ERR_CUDA,      \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+int upload_subset_tables(kgpu_ctx *h) {
+    uint8_t subs[9][70];
+    uint8_t nsub[9];
+    memset(subs, 0, sizeof subs);
+    for (int k = 0; k <= 8; k++) {
+        int c = 0;
+        for (unsigned S = 0; S < 256; S++)
+            if (__builtin_popcount(S) == k) subs[k][c++] = (uint8_t)S;
+        nsub[k] = (uint8_t)c;
+    }
+    for (auto &s : h->shards) {
+        KGPU_CUDA(h, cudaSetDevice(s.dev));
+        KGPU_CUDA(h, cudaMemcpyToSymbol(kgpu::c_subsets, subs, sizeof subs));
+        KGPU_CUDA(h, cudaMemcpyToSymbol(kgpu::c_nsub, nsub, sizeof nsub));
+    }
+    h->subsets_uploaded = true;
+    return KGPU_OK;
+}
+
+int ensure_pod_capacity(kgpu_ctx *h, kgpu_shard &s, int64_t P) {
+    if (P <= s.pcap) return KGPU_OK;
+    int64_t cap = std::max<int64_t>(1024, P + P / 4);
+    KGPU_CUDA(h, cudaSetDevice(s.dev));
+    if (s.d_pods) cudaFree(s.d_pods);
+    if (s.d_keys) cudaFree(s.d_keys);
+    if (s.d_gather) cudaFree(s.d_gather);
+    s.d_pods = nullptr; s.d_keys = nullptr; s.d_gather = nullptr; s.pcap = 0;
+    KGPU_CUDA(h, cudaMalloc(&s.d_pods, (size_t)cap * 16));
+    KGPU_CUDA(h, cudaMalloc(&s.d_keys, (size_t)cap * 8));
+    if (h->shards.size() > 1) KGPU_CUDA(h, cudaMalloc(&s.d_gather, (size_t)cap * 8 * h->shards.size()));
+    s.pcap = cap;
+    return KGPU_OK;
+}
+
+// Enqueue K1 for P pods on shard s: d_keys[p] = best placement over this shard's nodes.
+int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, unsigned long long *d_keys,
+                 cudaStream_t st) {
+    if (P <= 0) return KGPU_OK;
+    if ((reinterpret_cast<uintptr_t>(d_pods) & 15u) != 0)
+        return fail(h, KGPU_ERR_INVALID, "pods pointer must be 16-byte aligned");
+    KGPU_CUDA(h, cudaSetDevice(s.dev));
+    kgpu::Weights W;
+    memcpy(W.w, h->W, sizeof W.w);
+    const int4 *topo4 = reinterpret_cast<const int4 *>(s.d_topo);
+    const int4 *pods4 = reinterpret_cast<const int4 *>(d_pods);
+
+    if (h->variant == KGPU_VARIANT_MEMO_BY_K) {
+        KGPU_CUDA(h, cudaMemsetAsync(s.d_bestk, 0xFF, 9 * 8, st));
+        if (s.n > 0) {
+            int blocks = (int)std::min<int64_t>((s.n + kgpu::LPN_THREADS - 1) / kgpu::LPN_THREADS, (int64_t)s.sm_count * 4);
+            kgpu::memo_best_by_k<<<blocks, kgpu::LPN_THREADS, 0, st>>>(topo4, s.d_free, s.n, s.node_id_base, W, s.d_bestk);
+            h->launches++;
+        }
+        kgpu::memo_gather<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(pods4, P, s.d_bestk, d_keys);
+        h->launches++;
+        KGPU_CUDA(h, cudaGetLastError());
+        return KGPU_OK;
+    }
+
+    KGPU_CUDA(h, cudaMemsetAsync(d_keys, 0xFF, (size_t)P * 8, st));
+    if (s.n == 0) return KGPU_OK;
+
+    const bool wpp = h->variant == KGPU_VARIANT_WARP_PER_PAIR;
+    const int tile = wpp ? kgpu::WPP_TILE : kgpu::LPN_THREADS;
+    const int64_t tiles = (s.n + tile - 1) / tile;
+    // Pod splits: enough blocks for ~8 waves of resident CTAs, but each block keeps
+    // >= 128 pods so staging its node tile stays amortised.
+    const int64_t resident = (int64_t)s.sm_count * (wpp ? 8 : 4);
+    int64_t splits = std::max<int64_t>(1, (8 * resident + tiles - 1) / tiles);
+    splits = std::min<int64_t>(splits, std::max<int64_t>(1, P / 128));
+    splits = std::min<int64_t>(splits, 65535);
+    int64_t per = (P + splits - 1) / splits;
+    per = (per + 31) / 32 * 32;
+    splits = (P + per - 1) / per;
+    if (tiles > 0x7FFFFFFFLL || per > 0x7FFFFFFFLL) return fail(h, KGPU_ERR_INVALID, "batch too large for one launch");
+    dim3 grid((unsigned)tiles, (unsigned)splits);
+    if (wpp)
+        kgpu::score_pairs_warp_per_pair<<<grid, kgpu::WPP_THREADS, 0, st>>>(topo4, s.d_free, s.n, s.node_id_base, pods4, P,
+                                                                            (int)per, W, d_keys);
+    else
+        kgpu::score_pairs_lane_per_node<<<grid, kgpu::LPN_THREADS, 0, st>>>(topo4, s.d_free, s.n, s.node_id_base, pods4, P,
+                                                                            (int)per, W, d_keys);
+    h->launches++;
+    KGPU_CUDA(h, cudaGetLastError());
+    return KGPU_OK;
+}
+
+int validate_topo(kgpu_ctx *h, const int32_t *topo, int64_t n) {
+    for (int64_t i = 0; i < n * 64; i++)
+        if ((uint32_t)topo[i] > 15u)
+            return fail(h, KGPU_ERR_INVALID, "topo[%lld][%d] = %d outside the link-level domain 0..15",
+                        (long long)(i / 64), (int)(i % 64), topo[i]);
+    return KGPU_OK;
+}
+
+// Which shard holds local node index idx (contiguous split)?
+kgpu_shard *shard_of(kgpu_ctx *h, int64_t idx, int64_t *local) {
+    int64_t off = 0;
+    for (auto &s : h->shards) {
+        if (idx < off + s.n) { *local = idx - off; return &s; }
+        off += s.n;
+    }
+    return nullptr;
+}
+
+void free_shard(kgpu_shard &s) {
+    if (s.dev < 0) return;
+    cudaSetDevice(s.dev);
+    if (s.d_topo) cudaFree(s.d_topo);
+    if (s.d_free) cudaFree(s.d_free);
+    if (s.d_pods) cudaFree(s.d_pods);
+    if (s.d_keys) cudaFree(s.d_keys);
+    if (s.d_gather) cudaFree(s.d_gather);
+    if (s.d_bestk) cudaFree(s.d_bestk);
+    if (s.ev0) cudaEventDestroy(s.ev0);
+    if (s.ev1) cudaEventDestroy(s.ev1);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    s = kgpu_shard();
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *kgpu_version(void) { return "0.1.0"; }
+
+const char *kgpu_last_error(kgpu_t *h) {
+    if (h) {
+        std::lock_guard<std::mutex> g(h->mu);
+        t_last_error = h->err;   // return storage that outlives the lock
+    }
+    return t_last_error.c_str();
+}
+
+int kgpu_create(const int *dev_ids, int ndev, kgpu_t **out) {
+    if (!out) return fail(nullptr, KGPU_ERR_INVALID, "kgpu_create: out is NULL");
+    *out = nullptr;
+    if (!dev_ids || ndev < 1 || ndev > 64) return fail(nullptr, KGPU_ERR_INVALID, "kgpu_create: need 1..64 device ids");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, KGPU_ERR_CUDA, "kgpu_create: no usable CUDA device (%s); libkgpu has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    kgpu_ctx *h = new (std::nothrow) kgpu_ctx();
+    if (!h) return fail(nullptr, KGPU_ERR_NOMEM, "kgpu_create: out of host memory");
+    memcpy(h->W, kDefaultWeights, sizeof h->W);
+    h->shards.resize((size_t)ndev);
+    int rc = KGPU_OK;
+    for (int i = 0; i < ndev && rc == KGPU_OK; i++) {
+        kgpu_shard &s = h->shards[(size_t)i];
+        if (dev_ids[i] < 0 || dev_ids[i] >= count) {
+            rc = fail(nullptr, KGPU_ERR_INVALID, "kgpu_create: device id %d out of range (have %d)", dev_ids[i], count);
+            break;
+        }
+        s.dev = dev_ids[i];
+        auto step = [&](cudaError_t ce, const char *what) {
+            if (ce != cudaSuccess && rc == KGPU_OK)
+                rc = fail(nullptr, KGPU_ERR_CUDA, "kgpu_create: %s on device %d: %s", what, s.dev, cudaGetErrorString(ce));
+        };
+        step(cudaSetDevice(s.dev), "cudaSetDevice");
+        step(cudaDeviceGetAttribute(&s.sm_count, cudaDevAttrMultiProcessorCount, s.dev), "query SM count");
+        step(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        step(cudaEventCreate(&s.ev0), "cudaEventCreate");
+        step(cudaEventCreate(&s.ev1), "cudaEventCreate");
+        step(cudaMalloc(&s.d_bestk, 9 * 8), "cudaMalloc");
+    }
+    if (rc == KGPU_OK && ndev > 1) {
+        std::vector<int> devs(dev_ids, dev_ids + ndev);
+        std::string why;
+        h->multi = kgpu::MultiDevice::create(devs, &why);
+        if (!h->multi) rc = fail(nullptr, KGPU_ERR_COMM, "kgpu_create: %s", why.c_str());
+    }
+    if (rc == KGPU_OK) rc = upload_subset_tables(h);
+    if (rc != KGPU_OK) {
+        std::string keep = t_last_error;
+        for (auto &s : h->shards) free_shard(s);
+        delete h->multi;
+        delete h;
+        t_last_error = keep;
+        return rc;
+    }
+    *out = h;
+    return KGPU_OK;
+}
+
+int kgpu_destroy(kgpu_t *h) {
+    if (!h) return KGPU_OK;
+    for (auto &s : h->shards) {
+        if (s.dev >= 0) { cudaSetDevice(s.dev); cudaStreamSynchronize(s.stream); }
+    }
+    delete h->multi;
+    for (auto &s : h->shards) free_shard(s);
+    delete h;
+    return KGPU_OK;
+}
+
+int kgpu_set_weights(kgpu_t *h, const int32_t w[KGPU_NUM_LEVELS]) {
+    if (!h || !w) return fail(h, KGPU_ERR_INVALID, "kgpu_set_weights: NULL argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    for (int i = 0; i < 16; i++)
+        if (w[i] < 0 || w[i] > KGPU_MAX_WEIGHT)
+            return fail(h, KGPU_ERR_INVALID, "kgpu_set_weights: w[%d] = %d outside 0..%d", i, w[i], KGPU_MAX_WEIGHT);
+    memcpy(h->W, w, sizeof h->W);
+    return KGPU_OK;
+}
+
+int kgpu_get_weights(kgpu_t *h, int32_t w[KGPU_NUM_LEVELS]) {
+    if (!h || !w) return fail(h, KGPU_ERR_INVALID, "kgpu_get_weights: NULL argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    memcpy(w, h->W, sizeof h->W);
+    return KGPU_OK;
+}
+
+int kgpu_set_variant(kgpu_t *h, int variant) {
+    if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_set_variant: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (variant == KGPU_VARIANT_AUTO) variant = KGPU_VARIANT_LANE_PER_NODE;
+    if (variant < KGPU_VARIANT_WARP_PER_PAIR || variant > KGPU_VARIANT_MEMO_BY_K)
+        return fail(h, KGPU_ERR_INVALID, "kgpu_set_variant: unknown variant %d", variant);
+    h->variant = variant;
+    return KGPU_OK;
+}
+
+int kgpu_upload_nodes(kgpu_t *h, const int32_t *topo, const int32_t *free_mask, int64_t n, int64_t node_id_base) {
+    if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_upload_nodes: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (n < 0 || (n > 0 && (!topo || !free_mask))) return fail(h, KGPU_ERR_INVALID, "kgpu_upload_nodes: bad arguments");
+    if (node_id_base < 0 || node_id_base + n > 0xFFFFFFFFLL)
+        return fail(h, KGPU_ERR_INVALID, "kgpu_upload_nodes: node ids must fit in 32 bits");
+    int rc = validate_topo(h, topo, n);
+    if (rc != KGPU_OK) return rc;
+    const int64_t G = (int64_t)h->shards.size();
+    const int64_t per = (n + G - 1) / G;     // contiguous ranges: shard g holds [g*per, ...)
+    int64_t off = 0;
+    for (auto &s : h->shards) {
+        const int64_t cnt = std::max<int64_t>(0, std::min<int64_t>(per, n - off));
+        KGPU_CUDA(h, cudaSetDevice(s.dev));
+        if (cnt > s.cap) {
+            if (s.d_topo) cudaFree(s.d_topo);
+            if (s.d_free) cudaFree(s.d_free);
+            s.d_topo = nullptr; s.d_free = nullptr; s.cap = 0;
+            KGPU_CUDA(h, cudaMalloc(&s.d_topo, (size_t)cnt * 256));
+            KGPU_CUDA(h, cudaMalloc(&s.d_free, (size_t)cnt * 4));
+            s.cap = cnt;
+        }
+        if (cnt > 0) {
+            KGPU_CUDA(h, cudaMemcpyAsync(s.d_topo, topo + off * 64, (size_t)cnt * 256, cudaMemcpyHostToDevice, s.stream));
+            KGPU_CUDA(h, cudaMemcpyAsync(s.d_free, free_mask + off, (size_t)cnt * 4, cudaMemcpyHostToDevice, s.stream));
+        }
+        s.n = cnt;
+        s.node_id_base = node_id_base + off;
+        off += cnt;
+    }
+    for (auto &s : h->shards) {
+        KGPU_CUDA(h, cudaSetDevice(s.dev));
+        KGPU_CUDA(h, cudaStreamSynchronize(s.stream));
+    }
+    h->n_total = n;
+    return KGPU_OK;
+}
+
+int kgpu_update_node(kgpu_t *h, int64_t idx, const int32_t topo[64], int32_t free_mask) {
+    if (!h || !topo) return fail(h, KGPU_ERR_INVALID, "kgpu_update_node: NULL argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (idx < 0 || idx >= h->n_total) return fail(h, KGPU_ERR_INVALID, "kgpu_update_node: index %lld out of range", (long long)idx);
+    int rc = validate_topo(h, topo, 1);
+    if (rc != KGPU_OK) return rc;
+    int64_t local = 0;
+    kgpu_shard *s = shard_of(h, idx, &local);
+    KGPU_CUDA(h, cudaSetDevice(s->dev));
+    KGPU_CUDA(h, cudaMemcpyAsync(s->d_topo + local * 64, topo, 256, cudaMemcpyHostToDevice, s->stream));
+    KGPU_CUDA(h, cudaMemcpyAsync(s->d_free + local, &free_mask, 4, cudaMemcpyHostToDevice, s->stream));
+    KGPU_CUDA(h, cudaStreamSynchronize(s->stream));
+    return KGPU_OK;
+}
+
+int kgpu_set_free_mask(kgpu_t *h, int64_t idx, int32_t free_mask) {
+    if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_set_free_mask: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (idx < 0 || idx >= h->n_total) return fail(h, KGPU_ERR_INVALID, "kgpu_set_free_mask: index %lld out of range", (long long)idx);
+    int64_t local = 0;
+    kgpu_shard *s = shard_of(h, idx, &local);
+    KGPU_CUDA(h, cudaSetDevice(s->dev));
+    KGPU_CUDA(h, cudaMemcpyAsync(s->d_free + local, &free_mask, 4, cudaMemcpyHostToDevice, s->stream));
+    KGPU_CUDA(h, cudaStreamSynchronize(s->stream));
+    return KGPU_OK;
+}
+
+int kgpu_remove_node(kgpu_t *h, int64_t idx) { return kgpu_set_free_mask(h, idx, 0); }
+
+int64_t kgpu_num_nodes(kgpu_t *h) {
+    if (!h) return 0;
+    std::lock_guard<std::mutex> g(h->mu);
+    return h->n_total;
+}
+
+int kgpu_score_batch(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_keys) {
+    if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_score_batch: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (P < 0 || (P > 0 && (!pods || !out_keys))) return fail(h, KGPU_ERR_INVALID, "kgpu_score_batch: bad arguments");
+    if (P == 0) return KGPU_OK;
+    const size_t G = h->shards.size();
+    for (auto &s : h->shards) {
+        int rc = ensure_pod_capacity(h, s, P);
+        if (rc != KGPU_OK) return rc;
+    }
+    // every device: pods H2D, K1 over its node shard (devices run concurrently)
+    for (auto &s : h->shards) {
+        KGPU_CUDA(h, cudaSetDevice(s.dev));
+        KGPU_CUDA(h, cudaMemcpyAsync(s.d_pods, pods, (size_t)P * 16, cudaMemcpyHostToDevice, s.stream));
+        KGPU_CUDA(h, cudaEventRecord(s.ev0, s.stream));
+        int rc = launch_score(h, s, s.d_pods, P, s.d_keys, s.stream);
+        if (rc != KGPU_OK) return rc;
+        KGPU_CUDA(h, cudaEventRecord(s.ev1, s.stream));
+    }
+    kgpu_shard &s0 = h->shards[0];
+    if (G > 1) {
+        // one all-gather of every shard's per-pod best over NVLink, then K2 on device 0
+        std::vector<const void *> send(G);
+        std::vector<void *> recv(G);
+        std::vector<cudaStream_t> streams(G);
+        for (size_t i = 0; i < G; i++) { send[i] = h->shards[i].d_keys; recv[i] = h->shards[i].d_gather; streams[i] = h->shards[i].stream; }
+        std::string why;
+        if (!h->multi->all_gather_u64(send, recv, (size_t)P, streams, &why))
+            return fail(h, KGPU_ERR_COMM, "kgpu_score_batch: %s", why.c_str());
+        KGPU_CUDA(h, cudaSetDevice(s0.dev));
+        kgpu::reduce_shards<<<(unsigned)((P + 255) / 256), 256, 0, s0.stream>>>(s0.d_gather, (int)G, P, s0.d_keys);
+        h->launches++;
+        KGPU_CUDA(h, cudaGetLastError());
+    }
+    KGPU_CUDA(h, cudaSetDevice(s0.dev));
+    KGPU_CUDA(h, cudaMemcpyAsync(out_keys, s0.d_keys, (size_t)P * 8, cudaMemcpyDeviceToHost, s0.stream));
+    double worst = 0.0;
+    for (auto &s : h->shards) {
+        KGPU_CUDA(h, cudaSetDevice(s.dev));
+        KGPU_CUDA(h, cudaStreamSynchronize(s.stream));
+        float ms = 0.f;
+        KGPU_CUDA(h, cudaEventElapsedTime(&ms, s.ev0, s.ev1));
+        worst = std::max(worst, (double)ms);
+    }
+    h->last_kernel_ms = worst;
+    return KGPU_OK;
+}
+
+int kgpu_score_batch_device(kgpu_t *h, const int32_t *d_pods, int64_t P, uint64_t *d_keys, void *stream) {
+    if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_score_batch_device: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (h->shards.size() != 1) return fail(h, KGPU_ERR_STATE, "kgpu_score_batch_device: needs a single-device handle");
+    if (P < 0 || (P > 0 && (!d_pods || !d_keys))) return fail(h, KGPU_ERR_INVALID, "kgpu_score_batch_device: bad arguments");
+    kgpu_shard &s = h->shards[0];
+    return launch_score(h, s, d_pods, P, reinterpret_cast<unsigned long long *>(d_keys),
+                        stream ? (cudaStream_t)stream : s.stream);
+}
+
+int kgpu_reduce_shards_device(kgpu_t *h, const uint64_t *d_gathered, int G, int64_t P, uint64_t *d_out, void *stream) {
+    if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_reduce_shards_device: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (G < 1 || P < 0 || (P > 0 && (!d_gathered || !d_out))) return fail(h, KGPU_ERR_INVALID, "kgpu_reduce_shards_device: bad arguments");
+    if (P == 0) return KGPU_OK;
+    kgpu_shard &s = h->shards[0];
+    KGPU_CUDA(h, cudaSetDevice(s.dev));
+    kgpu::reduce_shards<<<(unsigned)((P + 255) / 256), 256, 0, stream ? (cudaStream_t)stream : s.stream>>>(
+        reinterpret_cast<const unsigned long long *>(d_gathered), G, P, reinterpret_cast<unsigned long long *>(d_out));
+    h->launches++;
+    KGPU_CUDA(h, cudaGetLastError());
+    return KGPU_OK;
+}
+
+int64_t kgpu_kernel_launches(kgpu_t *h) {
+    if (!h) return 0;
+    std::lock_guard<std::mutex> g(h->mu);
+    return h->launches;
+}
+
+double kgpu_last_kernel_ms(kgpu_t *h) {
+    if (!h) return 0.0;
+    std::lock_guard<std::mutex> g(h->mu);
+    return h->last_kernel_ms;
+}
+
+}  // extern "C"

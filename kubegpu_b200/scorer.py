@@ -1,0 +1,140 @@
+"""Handle wrapper over the C ABI: what bench.py and the GPU tests drive.
+
+Mirrors the call sequence a Go ``DeviceScheduler`` host makes through cgo
+(INTEGRATION.md): create -> upload_nodes (AddNode for the whole cluster) ->
+score_batch per scheduling cycle -> update_node / remove_node as the cluster changes.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+
+class KgpuError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("libkgpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _i32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Scorer:
+    """One libkgpu handle (``kgpu_t``) on one or more CUDA devices."""
+
+    def __init__(self, devices: Sequence[int] = (0,)):
+        self._L = _lib.load()
+        self._h = ctypes.c_void_p()
+        devs = (ctypes.c_int * len(devices))(*devices)
+        rc = self._L.kgpu_create(devs, len(devices), ctypes.byref(self._h))
+        if rc != _lib.OK:
+            self._h = ctypes.c_void_p()
+            raise KgpuError(rc, (self._L.kgpu_last_error(None) or b"").decode())
+        self.devices = tuple(devices)
+
+    # -- plumbing ---------------------------------------------------------------
+    def _check(self, rc: int) -> None:
+        if rc != _lib.OK:
+            raise KgpuError(rc, (self._L.kgpu_last_error(self._h) or b"").decode())
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.kgpu_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- configuration ----------------------------------------------------------
+    def set_weights(self, w) -> None:
+        w = _i32(w)
+        if w.size != 16:
+            raise ValueError("weights must have 16 entries")
+        self._check(self._L.kgpu_set_weights(self._h, w.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+
+    def get_weights(self) -> np.ndarray:
+        w = np.zeros(16, dtype=np.int32)
+        self._check(self._L.kgpu_get_weights(self._h, w.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        return w
+
+    def set_variant(self, variant: int) -> None:
+        self._check(self._L.kgpu_set_variant(self._h, int(variant)))
+
+    # -- node array (AddNode / RemoveNode side) -----------------------------------
+    def upload_nodes(self, topo, free_mask, node_id_base: int = 0) -> None:
+        topo, free_mask = _i32(topo), _i32(free_mask)
+        n = free_mask.shape[0]
+        if topo.size != 64 * n:
+            raise ValueError("topo must be [N,64] for N = len(free_mask)")
+        p32 = ctypes.POINTER(ctypes.c_int32)
+        self._check(self._L.kgpu_upload_nodes(self._h, topo.ctypes.data_as(p32), free_mask.ctypes.data_as(p32),
+                                              n, int(node_id_base)))
+
+    def update_node(self, idx: int, topo, free_mask: int) -> None:
+        topo = _i32(topo)
+        if topo.size != 64:
+            raise ValueError("topo must have 64 entries")
+        self._check(self._L.kgpu_update_node(self._h, int(idx), topo.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                             int(free_mask)))
+
+    def set_free_mask(self, idx: int, free_mask: int) -> None:
+        self._check(self._L.kgpu_set_free_mask(self._h, int(idx), int(free_mask)))
+
+    def remove_node(self, idx: int) -> None:
+        self._check(self._L.kgpu_remove_node(self._h, int(idx)))
+
+    @property
+    def num_nodes(self) -> int:
+        return int(self._L.kgpu_num_nodes(self._h))
+
+    # -- scoring ------------------------------------------------------------------
+    def score_batch(self, pods, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Host buffers in, host buffers out (the end-to-end call)."""
+        pods = _i32(pods)
+        P = pods.size // 4
+        if out is None:
+            out = np.empty(P, dtype=np.uint64)
+        self._check(self._L.kgpu_score_batch(self._h, pods.ctypes.data, P, out.ctypes.data))
+        return out
+
+    def score_batch_ptr(self, pods_addr: int, P: int, out_addr: int) -> None:
+        """Same call on raw host addresses (e.g. pinned torch tensors' data_ptr())."""
+        self._check(self._L.kgpu_score_batch(self._h, pods_addr, int(P), out_addr))
+
+    def score_batch_device(self, d_pods_addr: int, P: int, d_keys_addr: int, stream: int = 0) -> None:
+        """Device buffers, enqueued on `stream` (cudaStream_t as int, 0 = handle stream)."""
+        self._check(self._L.kgpu_score_batch_device(self._h, d_pods_addr, int(P), d_keys_addr, stream or None))
+
+    def reduce_shards_device(self, d_gathered_addr: int, G: int, P: int, d_out_addr: int, stream: int = 0) -> None:
+        self._check(self._L.kgpu_reduce_shards_device(self._h, d_gathered_addr, int(G), int(P), d_out_addr,
+                                                      stream or None))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._L.kgpu_kernel_launches(self._h))
+
+    @property
+    def last_kernel_ms(self) -> float:
+        return float(self._L.kgpu_last_kernel_ms(self._h))
+
+
+def unpack_key(key: int):
+    """(cost, node_id, gpu_mask) or None for KGPU_NO_FIT."""
+    key = int(key)
+    if key == _lib.NO_FIT:
+        return None
+    return key >> 40, (key >> 8) & 0xFFFFFFFF, key & 0xFF

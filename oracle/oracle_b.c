@@ -1,0 +1,197 @@
+/*
+ * oracle_b.c -- Oracle B: CPU twin of the subset-enumeration placement scorer.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under kubegpu_b200/ (the product) may
+ * include, link, import or execute this file.  Only tests/, bench.py's
+ * cpu_baseline / --impl reference legs and __graft_entry__.smoke() use it, and
+ * there only as the checker / the reported CPU baseline.
+ *
+ * Parity status: the subset scorer named by BASELINE.json:north_star does not
+ * exist as code in the reference (SURVEY.md "Read this first"); this file is
+ * the definition fixed in SURVEY.md 8(c) "Oracle B".  It is tied to the
+ * reference in two ways, both tested in tests/test_oracle_agree.py:
+ *   - its inputs (the 8x8 link-level matrix, value domain 0..6 = NVML P2P
+ *     levels, 0 = unknown/diagonal) follow
+ *     nvidiagpuplugin/gpu/nvml/nvml.go:37-49,69-78 and
+ *     nvidiagpuplugin/gpu/nvidia/nvidia_gpu_manager.go:159-180;
+ *   - on matrices generated from a 2-level group shape its min cost equals the
+ *     pairwise cost of the reference's greedy fill (gpuschedulerplugin/gpu.go:
+ *     247-271, restated in oracle/oracle_a.py) on the documented agree-set.
+ * "Bit-exact" for the CUDA path means bit-exact against THIS file.
+ *
+ * Definition (all integer):
+ *   node n:  M = int32[8][8] link levels (only the upper triangle i<j is read,
+ *            each value masked to 0..15), free = free_mask & 0xFF.
+ *   pod:     k = pods[4*p+0]  (k==0: empty set, cost 0; k<0 or k>8: no fit).
+ *   cost(S)  = sum_{i<j in S} W[M[i][j]]          W = int32[16], 0..4095
+ *   nodekey  = min over S (popcount(S)==k, S subset of free) of (cost<<8 | S)
+ *   podkey   = min over nodes of (cost<<40 | node_id<<8 | S)   (uint64)
+ *   no feasible (node,S) anywhere -> UINT64_MAX.
+ *   Subsets are enumerated in increasing integer order (Gosper's hack).
+ */
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define KGPU_NO_FIT UINT64_MAX
+#define NODE_NO_FIT UINT32_MAX
+
+/* ---- plain restatement: the checker ------------------------------------ */
+
+uint32_t kgpu_oracle_subset_cost(const int32_t *M, unsigned S, const int32_t *W)
+{
+    uint32_t cost = 0;
+    for (int i = 0; i < 8; i++) {
+        if (!((S >> i) & 1u)) continue;
+        for (int j = i + 1; j < 8; j++)
+            if ((S >> j) & 1u) cost += (uint32_t)W[M[i * 8 + j] & 15];
+    }
+    return cost;
+}
+
+uint32_t kgpu_oracle_node_key(const int32_t *M, int32_t free_mask, int k, const int32_t *W)
+{
+    unsigned fm = (unsigned)free_mask & 0xFFu;
+    if (k < 0 || k > 8) return NODE_NO_FIT;
+    if (k == 0) return 0u;
+    uint32_t best = NODE_NO_FIT;
+    unsigned S = (1u << k) - 1u;
+    while (S < 256u) {
+        if ((S & ~fm) == 0u) {
+            uint32_t key = (kgpu_oracle_subset_cost(M, S, W) << 8) | S;
+            if (key < best) best = key;
+        }
+        unsigned c = S & (0u - S);          /* Gosper: next k-subset */
+        unsigned r = S + c;
+        S = (((r ^ S) >> 2) / c) | r;
+    }
+    return best;
+}
+
+static inline uint64_t pod_key(uint32_t nk, uint64_t node_id)
+{
+    return ((uint64_t)(nk >> 8) << 40) | (node_id << 8) | (uint64_t)(nk & 0xFFu);
+}
+
+/* out_keys[p] = best placement of pod p over nodes [0,N) whose global ids are
+ * node_id_base + index.  Single thread, no precomputation. */
+void kgpu_oracle_score_batch(const int32_t *topo, const int32_t *free_mask, int64_t N,
+                             int64_t node_id_base, const int32_t *pods, int64_t P,
+                             const int32_t *W, uint64_t *out_keys)
+{
+    for (int64_t p = 0; p < P; p++) {
+        int k = pods[4 * p];
+        uint64_t best = KGPU_NO_FIT;
+        for (int64_t n = 0; n < N; n++) {
+            uint32_t nk = kgpu_oracle_node_key(topo + 64 * n, free_mask[n], k, W);
+            if (nk == NODE_NO_FIT) continue;
+            uint64_t key = pod_key(nk, (uint64_t)(node_id_base + n));
+            if (key < best) best = key;
+        }
+        out_keys[p] = best;
+    }
+}
+
+/* ---- tuned CPU variant: the reported CPU baseline ---------------------- */
+/* Same results (tests assert equality with the plain version).  Per node a
+ * 256-entry subset-cost table is built once (cost[S] = cost[S minus lowest
+ * bit] + row sum), then every pod of the thread's range enumerates its k-subsets
+ * through the table.  Threads split the pod range, so no merge is needed. */
+
+static const uint8_t *subsets_of_size(int k, int *count)
+{
+    static uint8_t tbl[9][70];
+    static int cnt[9];
+    static int ready = 0;
+    if (!ready) {
+        for (int kk = 0; kk <= 8; kk++) {
+            cnt[kk] = 0;
+            for (unsigned S = 0; S < 256; S++)
+                if (__builtin_popcount(S) == kk) tbl[kk][cnt[kk]++] = (uint8_t)S;
+        }
+        ready = 1;
+    }
+    *count = cnt[k];
+    return tbl[k];
+}
+
+static void build_cost_table(const int32_t *M, const int32_t *W, uint32_t *cost)
+{
+    cost[0] = 0;
+    for (unsigned S = 1; S < 256; S++) {
+        int i = __builtin_ctz(S);
+        unsigned rest = S & (S - 1);
+        uint32_t c = cost[rest];
+        for (unsigned t = rest; t; t &= t - 1)
+            c += (uint32_t)W[M[i * 8 + __builtin_ctz(t)] & 15];
+        cost[S] = c;
+    }
+}
+
+struct fast_job {
+    const int32_t *topo, *free_mask, *pods, *W;
+    int64_t N, node_id_base, p0, p1;
+    uint64_t *out;
+};
+
+static void *fast_worker(void *arg)
+{
+    struct fast_job *j = (struct fast_job *)arg;
+    uint32_t cost[256];
+    for (int64_t p = j->p0; p < j->p1; p++) j->out[p] = KGPU_NO_FIT;
+    for (int64_t n = 0; n < j->N; n++) {
+        unsigned fm = (unsigned)j->free_mask[n] & 0xFFu;
+        uint64_t nid = (uint64_t)(j->node_id_base + n);
+        build_cost_table(j->topo + 64 * n, j->W, cost);
+        for (int64_t p = j->p0; p < j->p1; p++) {
+            int k = j->pods[4 * p];
+            if (k < 0 || k > 8) continue;
+            int cnt;
+            const uint8_t *subs = subsets_of_size(k, &cnt);
+            uint32_t best = NODE_NO_FIT;
+            for (int s = 0; s < cnt; s++) {
+                unsigned S = subs[s];
+                if (S & ~fm) continue;
+                uint32_t key = (cost[S] << 8) | S;
+                if (key < best) best = key;
+            }
+            if (best == NODE_NO_FIT) continue;
+            uint64_t key = pod_key(best, nid);
+            if (key < j->out[p]) j->out[p] = key;
+        }
+    }
+    return NULL;
+}
+
+void kgpu_oracle_score_batch_fast(const int32_t *topo, const int32_t *free_mask, int64_t N,
+                                  int64_t node_id_base, const int32_t *pods, int64_t P,
+                                  const int32_t *W, uint64_t *out_keys, int nthreads)
+{
+    int dummy;
+    (void)subsets_of_size(0, &dummy); /* build the table before threads start */
+    if (nthreads < 1) nthreads = 1;
+    if ((int64_t)nthreads > P) nthreads = P > 0 ? (int)P : 1;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
+    struct fast_job *jobs = (struct fast_job *)malloc(sizeof(struct fast_job) * (size_t)nthreads);
+    for (int t = 0; t < nthreads; t++) {
+        jobs[t] = (struct fast_job){topo, free_mask, pods, W, N, node_id_base,
+                                    P * t / nthreads, P * (t + 1) / nthreads, out_keys};
+        if (t > 0) pthread_create(&th[t], NULL, fast_worker, &jobs[t]);
+    }
+    fast_worker(&jobs[0]);
+    for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
+    free(th);
+    free(jobs);
+}
+
+/* K2 twin: column-min over G gathered key arrays. */
+void kgpu_oracle_reduce_shards(const uint64_t *gathered, int G, int64_t P, uint64_t *out)
+{
+    for (int64_t p = 0; p < P; p++) {
+        uint64_t best = KGPU_NO_FIT;
+        for (int g = 0; g < G; g++)
+            if (gathered[(int64_t)g * P + p] < best) best = gathered[(int64_t)g * P + p];
+        out[p] = best;
+    }
+}

@@ -1,0 +1,170 @@
+"""GPU parity (run with `-m gpu` on the B200 box): every K1 variant, through the C ABI,
+bit-exact against Oracle B on the same seeded inputs, against the committed golden
+vectors, and -- at BASELINE's full sizes -- through size-independent properties."""
+import os
+
+import numpy as np
+import pytest
+
+from kubegpu_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = [_lib.VARIANT_LANE_PER_NODE, _lib.VARIANT_WARP_PER_PAIR, _lib.VARIANT_MEMO_BY_K]
+
+
+@pytest.fixture(scope="module")
+def scorer():
+    from kubegpu_b200.scorer import Scorer
+    s = Scorer((0,))
+    yield s
+    s.close()
+
+
+def _score(scorer, variant, topo, free, pods, base=0, W=None):
+    scorer.set_variant(variant)
+    if W is not None:
+        scorer.set_weights(W)
+    scorer.upload_nodes(topo, free, node_id_base=base)
+    out = scorer.score_batch(pods)
+    if W is not None:
+        scorer.set_weights([64, 32, 16, 8, 4, 2, 1] + [0] * 9)
+    return out
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_committed_golden_vectors(scorer, golden_dir, variant):
+    z = np.load(os.path.join(golden_dir, "oracle_b_vectors.npz"))
+    for tag in ("c1", "c2", "c3", "c4"):
+        keys = _score(scorer, variant, z[tag + "_topo"].astype(np.int32), z[tag + "_free"], z[tag + "_pods"])
+        assert (keys == z[tag + "_keys"]).all(), tag
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("gen,kw", [
+    (synth.gen_c2, dict(N=20_000, P=257)),
+    (synth.gen_c3, dict(N=12_345, P=300)),
+    (synth.gen_c4, dict(N=33_000, P=200)),
+])
+def test_parity_vs_oracle_seeded(scorer, oracle_b, variant, gen, kw):
+    topo, free, pods = gen(**kw)
+    want = oracle_b.score_batch(topo, free, pods, node_id_base=1000, fast=True, nthreads=8)
+    got = _score(scorer, variant, topo, free, pods, base=1000)
+    assert (got == want).all()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_edge_cases(scorer, oracle_b, variant):
+    rng = np.random.default_rng(5)
+    # ragged sizes around the tile (128/64 nodes) and chunk (512 pods) boundaries, all k incl. invalid
+    for N, P in [(1, 1), (127, 3), (128, 31), (129, 33), (640, 513), (1, 1100)]:
+        topo = rng.integers(0, 16, size=(N, 64)).astype(np.int32)
+        free = rng.integers(0, 256, size=N).astype(np.int32)
+        pods = synth.make_pods(rng.integers(-2, 11, size=P).astype(np.int32))
+        W = rng.integers(0, 4096, size=16).astype(np.int32)
+        want = oracle_b.score_batch(topo, free, pods, W, node_id_base=2**32 - 1 - N)
+        got = _score(scorer, variant, topo, free, pods, base=2**32 - 1 - N, W=W)
+        assert (got == want).all(), (N, P)
+    # nothing free anywhere / empty node list / empty pod list
+    topo, free, pods = synth.gen_c2(N=300, P=40)
+    assert (_score(scorer, variant, topo, np.zeros_like(free), pods) == np.uint64(_lib.NO_FIT)).all()
+    assert (_score(scorer, variant, topo[:0], free[:0], pods) == np.uint64(_lib.NO_FIT)).all()
+    assert _score(scorer, variant, topo, free, pods[:0]).shape == (0,)
+    # maximum weights: cost field at its largest, no overflow into the penalty range
+    wmax = np.full(16, 4095, dtype=np.int32)
+    full = np.full(200, 0xFF, dtype=np.int32)
+    got = _score(scorer, variant, topo[:200], full, synth.make_pods(np.arange(0, 9, dtype=np.int32)), W=wmax)
+    want = oracle_b.score_batch(topo[:200], full, synth.make_pods(np.arange(0, 9, dtype=np.int32)), wmax)
+    assert (got == want).all() and int(got[8]) >> 40 == 28 * 4095
+
+
+def test_update_and_remove_node(scorer, oracle_b):
+    scorer.set_variant(_lib.VARIANT_LANE_PER_NODE)
+    topo, free, pods = synth.gen_c2(N=2000, P=64)
+    topo, free = topo.copy(), free.copy()
+    scorer.upload_nodes(topo, free)
+    base = scorer.score_batch(pods)
+    assert (base == oracle_b.score_batch(topo, free, pods)).all()
+    # make node 1500 perfect (all NVLink, all free): every pod must move there
+    topo[1500] = 9
+    free[1500] = 0xFF
+    scorer.update_node(1500, topo[1500], 0xFF)
+    got = scorer.score_batch(pods)
+    assert (got == oracle_b.score_batch(topo, free, pods)).all()
+    assert all(((int(k) >> 8) & 0xFFFFFFFF) in (1500, ((int(b) >> 8) & 0xFFFFFFFF)) for k, b in zip(got, base))
+    scorer.remove_node(1500)
+    free[1500] = 0
+    assert (scorer.score_batch(pods) == oracle_b.score_batch(topo, free, pods)).all()
+    scorer.set_free_mask(7, 0x0F)
+    free[7] = 0x0F
+    assert (scorer.score_batch(pods) == oracle_b.score_batch(topo, free, pods)).all()
+    assert scorer.num_nodes == 2000
+
+
+def test_error_paths(scorer):
+    from kubegpu_b200.scorer import KgpuError
+    topo, free, pods = synth.gen_c2(N=10, P=4)
+    bad = topo.copy()
+    bad[3, 5] = 16
+    with pytest.raises(KgpuError) as e:
+        scorer.upload_nodes(bad, free)
+    assert e.value.code == _lib.ERR_INVALID and "topo[3][5]" in str(e.value)
+    with pytest.raises(KgpuError):
+        scorer.set_weights([4096] + [0] * 15)
+    with pytest.raises(KgpuError):
+        scorer.set_variant(9)
+    scorer.upload_nodes(topo, free)
+    with pytest.raises(KgpuError):
+        scorer.update_node(10, topo[0], 0xFF)
+    with pytest.raises(KgpuError):
+        scorer.upload_nodes(topo, free, node_id_base=2**32)
+
+
+def test_variants_agree_at_full_c2_size(scorer, oracle_b):
+    """BASELINE config 2 (100k nodes x 10k pods): the oracle is too slow for all of it, so
+    check (a) the three variants agree bit for bit, (b) an oracle-checked pod sample,
+    (c) per-k collapse: pods with equal k get equal keys (snapshot scoring), and
+    (d) every reported (node, mask) re-scores to the reported cost."""
+    topo, free, pods = synth.gen_c2()
+    outs = {v: _score(scorer, v, topo, free, pods) for v in VARIANTS}
+    assert (outs[VARIANTS[0]] == outs[VARIANTS[1]]).all() and (outs[VARIANTS[0]] == outs[VARIANTS[2]]).all()
+    keys = outs[VARIANTS[0]]
+    sample = np.arange(0, 10_000, 625)
+    want = oracle_b.score_batch(topo, free, pods[sample], fast=True, nthreads=8)
+    assert (keys[sample] == want).all()
+    for k in (1, 2, 4, 8):
+        assert len(set(keys[pods[:, 0] == k].tolist())) == 1
+    for key, k in zip(keys[:64], pods[:64, 0]):
+        cost, node, mask = int(key) >> 40, (int(key) >> 8) & 0xFFFFFFFF, int(key) & 0xFF
+        assert bin(mask).count("1") == k and (mask & ~int(free[node])) == 0
+        assert oracle_b.lib().kgpu_oracle_subset_cost(
+            topo[node].ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_int32)), mask,
+            oracle_b.DEFAULT_WEIGHTS.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_int32))) == cost
+
+
+def test_heterogeneous_256k_bit_exact(scorer, oracle_b):
+    """BASELINE config 4: 256k heterogeneous nodes, every key compared with Oracle B."""
+    topo, free, pods = synth.gen_c4(N=262_144, P=64)
+    want = oracle_b.score_batch(topo, free, pods, fast=True, nthreads=8)
+    for v in VARIANTS[:2]:
+        assert (_score(scorer, v, topo, free, pods) == want).all()
+
+
+def test_device_buffer_entry_point_and_k2(scorer, oracle_b):
+    import torch
+    scorer.set_variant(_lib.VARIANT_LANE_PER_NODE)
+    topo, free, pods = synth.gen_c3(N=5000, P=333)
+    G, per = 4, 1250
+    d_pods = torch.from_numpy(pods).cuda()
+    gathered = torch.empty((G, 333), dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for g in range(G):
+        scorer.upload_nodes(topo[g * per:(g + 1) * per], free[g * per:(g + 1) * per], node_id_base=g * per)
+        scorer.score_batch_device(d_pods.data_ptr(), 333, gathered[g].data_ptr(), st)
+        torch.cuda.synchronize()
+    out = torch.empty(333, dtype=torch.int64, device="cuda")
+    scorer.reduce_shards_device(gathered.data_ptr(), G, 333, out.data_ptr(), st)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().view(np.uint64)
+    assert (got == oracle_b.score_batch(topo, free, pods, fast=True, nthreads=4)).all()
+    assert scorer.kernel_launches > 0
