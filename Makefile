@@ -3,7 +3,8 @@
 # runs exactly this.
 NVCC ?= nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
-NVCCFLAGS ?= -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wextra -Xptxas -v
+EXTRA ?=
+NVCCFLAGS ?= $(EXTRA) -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wextra -Xptxas -v
 CSRC := kubegpu_b200/csrc
 LIB := kubegpu_b200/lib/libkgpu.so
 

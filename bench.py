@@ -133,18 +133,24 @@ def cpu_baseline(topo, free, pods, target_s: float = 12.0):
     workload against ALL nodes.  Returns the cpu_baseline object."""
     from oracle import oracle_b
     cores = os.cpu_count() or 1
-    probe = pods[:cores]
-    t0 = time.perf_counter()
-    oracle_b.score_batch(topo, free, probe, fast=True, nthreads=cores)
-    t_probe = max(time.perf_counter() - t0, 1e-6)
-    S = int(min(len(pods), max(cores, (target_s / t_probe) * len(probe))))
-    S = max(cores, S // cores * cores)
-    t0 = time.perf_counter()
-    oracle_b.score_batch(topo, free, pods[:S], fast=True, nthreads=cores)
-    dt = time.perf_counter() - t0
+    S, dt = _sized_cpu_run(oracle_b, topo, free, pods, cores, target_s)
     return {"value": S / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "first %d of %d pods x all %d nodes, oracle/oracle_b.c tuned variant, %d threads, %.1f s"
                       % (S, len(pods), len(free), cores, dt)}
+
+
+def _sized_cpu_run(oracle_b, topo, free, pods, cores, target_s):
+    """Grow the pod sample until one run takes >= target_s/2 (per-thread table building is a
+    fixed cost, so a linear guess from a tiny probe undershoots).  Returns (S, seconds)."""
+    S = min(len(pods), 2 * cores)
+    while True:
+        t0 = time.perf_counter()
+        oracle_b.score_batch(topo, free, pods[:S], fast=True, nthreads=cores)
+        dt = max(time.perf_counter() - t0, 1e-6)
+        if dt >= target_s / 2 or S >= len(pods):
+            return S, dt
+        S = int(min(len(pods), max(S + cores, S * min(8.0, target_s / dt))))
+        S = min(len(pods), (S + cores - 1) // cores * cores)
 
 
 def run_reference(args):
@@ -157,13 +163,9 @@ def run_reference(args):
     topo, free, pods = synth.gen_c2(N_NODES, N_PODS)
     cores = os.cpu_count() or 1
     oracle_b.lib()
-    # size each step's pod sample so that warmup+steps finish in a few minutes (~6 s per step)
-    t0 = time.perf_counter()
-    oracle_b.score_batch(topo, free, pods[:cores], fast=True, nthreads=cores)
-    t_probe = max(time.perf_counter() - t0, 1e-6)
+    # size each step's pod sample so that warmup+steps finish in a few minutes (<= ~6 s per step)
     budget = min(6.0, 150.0 / max(1, args.steps + args.warmup))
-    S = int(min(N_PODS, max(cores, budget / t_probe * cores)))
-    S = max(cores, S // cores * cores)
+    S, _ = _sized_cpu_run(oracle_b, topo, free, pods, cores, budget)
     for _ in range(args.warmup):
         oracle_b.score_batch(topo, free, pods[:S], fast=True, nthreads=cores)
     t0 = time.perf_counter()
@@ -234,7 +236,8 @@ def main():
     h_pods = torch.from_numpy(pods).pin_memory()
     h_keys = torch.empty(N_PODS, dtype=torch.int64).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)          # everything (K1, NCCL, K2, copies) is enqueued here
+    torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
 
     def step_device():

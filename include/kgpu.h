@@ -115,10 +115,17 @@ int64_t kgpu_num_nodes(kgpu_t *h);
 int kgpu_score_batch(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_keys);
 
 /* Same with device buffers on the handle's device (ndev == 1 handles only),
- * enqueued on `stream` (a cudaStream_t, NULL = the handle's stream), no sync.
+ * enqueued on `stream` (a cudaStream_t; NULL = the CUDA default stream, as in every CUDA
+ * API), no sync.  The node array must not be changed until the work has completed.
  * d_pods must be 16-byte aligned. */
 int kgpu_score_batch_device(kgpu_t *h, const int32_t *d_pods, int64_t P, uint64_t *d_keys,
                             void *stream);
+
+/* Per-pair query (one PodFitsDevice(node, pod) call, or a list of them): for each i,
+ * out_node_keys[i] = (cost << 8) | gpu_mask of the cheapest k[i]-subset of the free GPUs
+ * of node node_idx[i] (local index as uploaded), or UINT32_MAX if it does not fit.
+ * Host buffers, synchronous. */
+int kgpu_score_pairs(kgpu_t *h, const int64_t *node_idx, const int32_t *k, int64_t n, uint32_t *out_node_keys);
 
 /* K2: d_out[p] = min over g < G of d_gathered[g*P + p] (after an all-gather of
  * every shard's keys), enqueued on `stream`. */

@@ -19,6 +19,10 @@ namespace {
 
 thread_local std::string t_last_error;
 
+// F2/F2N multipliers handed to the kernels as arguments so that ptxas cannot fold them
+// (subset_dp_gen.cuh: pins those adds to the FMA pipe).
+const kgpu::PipeConsts PC = {1u, 0xFFFFFFFFu};
+
 const int32_t kDefaultWeights[16] = {64, 32, 16, 8, 4, 2, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
 }  // namespace
@@ -124,7 +128,7 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
         KGPU_CUDA(h, cudaMemsetAsync(s.d_bestk, 0xFF, 9 * 8, st));
         if (s.n > 0) {
             int blocks = (int)std::min<int64_t>((s.n + kgpu::LPN_THREADS - 1) / kgpu::LPN_THREADS, (int64_t)s.sm_count * 4);
-            kgpu::memo_best_by_k<<<blocks, kgpu::LPN_THREADS, 0, st>>>(topo4, s.d_free, s.n, s.node_id_base, W, s.d_bestk);
+            kgpu::memo_best_by_k<<<blocks, kgpu::LPN_THREADS, 0, st>>>(topo4, s.d_free, s.n, s.node_id_base, W, PC, s.d_bestk);
             h->launches++;
         }
         kgpu::memo_gather<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(pods4, P, s.d_bestk, d_keys);
@@ -141,7 +145,7 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
     const int64_t tiles = (s.n + tile - 1) / tile;
     // Pod splits: enough blocks for ~8 waves of resident CTAs, but each block keeps
     // >= 128 pods so staging its node tile stays amortised.
-    const int64_t resident = (int64_t)s.sm_count * (wpp ? 8 : 4);
+    const int64_t resident = (int64_t)s.sm_count * (wpp ? 8 : KGPU_LPN_MINBLOCKS);
     int64_t splits = std::max<int64_t>(1, (8 * resident + tiles - 1) / tiles);
     splits = std::min<int64_t>(splits, std::max<int64_t>(1, P / 128));
     splits = std::min<int64_t>(splits, 65535);
@@ -152,10 +156,10 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
     dim3 grid((unsigned)tiles, (unsigned)splits);
     if (wpp)
         kgpu::score_pairs_warp_per_pair<<<grid, kgpu::WPP_THREADS, 0, st>>>(topo4, s.d_free, s.n, s.node_id_base, pods4, P,
-                                                                            (int)per, W, d_keys);
+                                                                            (int)per, W, PC, d_keys);
     else
         kgpu::score_pairs_lane_per_node<<<grid, kgpu::LPN_THREADS, 0, st>>>(topo4, s.d_free, s.n, s.node_id_base, pods4, P,
-                                                                            (int)per, W, d_keys);
+                                                                            (int)per, W, PC, d_keys);
     h->launches++;
     KGPU_CUDA(h, cudaGetLastError());
     return KGPU_OK;
@@ -418,14 +422,55 @@ int kgpu_score_batch(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_ke
     return KGPU_OK;
 }
 
+int kgpu_score_pairs(kgpu_t *h, const int64_t *node_idx, const int32_t *k, int64_t n, uint32_t *out_node_keys) {
+    if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_score_pairs: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (n < 0 || (n > 0 && (!node_idx || !k || !out_node_keys))) return fail(h, KGPU_ERR_INVALID, "kgpu_score_pairs: bad arguments");
+    for (int64_t i = 0; i < n; i++)
+        if (node_idx[i] < 0 || node_idx[i] >= h->n_total)
+            return fail(h, KGPU_ERR_INVALID, "kgpu_score_pairs: node index %lld out of range", (long long)node_idx[i]);
+    kgpu::Weights W;
+    memcpy(W.w, h->W, sizeof W.w);
+    // route each pair to the shard that holds its node
+    int64_t off = 0;
+    for (auto &s : h->shards) {
+        std::vector<long long> idx;
+        std::vector<int32_t> kk;
+        std::vector<int64_t> pos;
+        for (int64_t i = 0; i < n; i++)
+            if (node_idx[i] >= off && node_idx[i] < off + s.n) { idx.push_back(node_idx[i] - off); kk.push_back(k[i]); pos.push_back(i); }
+        off += s.n;
+        if (idx.empty()) continue;
+        const size_t m = idx.size();
+        KGPU_CUDA(h, cudaSetDevice(s.dev));
+        long long *d_idx = nullptr; int32_t *d_k = nullptr; uint32_t *d_out = nullptr;
+        KGPU_CUDA(h, cudaMallocAsync(&d_idx, m * 8, s.stream));
+        KGPU_CUDA(h, cudaMallocAsync(&d_k, m * 4, s.stream));
+        KGPU_CUDA(h, cudaMallocAsync(&d_out, m * 4, s.stream));
+        KGPU_CUDA(h, cudaMemcpyAsync(d_idx, idx.data(), m * 8, cudaMemcpyHostToDevice, s.stream));
+        KGPU_CUDA(h, cudaMemcpyAsync(d_k, kk.data(), m * 4, cudaMemcpyHostToDevice, s.stream));
+        kgpu::score_pair_list<<<(unsigned)((m + 127) / 128), 128, 0, s.stream>>>(
+            reinterpret_cast<const int4 *>(s.d_topo), s.d_free, s.n, d_idx, d_k, (int64_t)m, W, PC, d_out);
+        h->launches++;
+        KGPU_CUDA(h, cudaGetLastError());
+        std::vector<uint32_t> res(m);
+        KGPU_CUDA(h, cudaMemcpyAsync(res.data(), d_out, m * 4, cudaMemcpyDeviceToHost, s.stream));
+        KGPU_CUDA(h, cudaFreeAsync(d_idx, s.stream));
+        KGPU_CUDA(h, cudaFreeAsync(d_k, s.stream));
+        KGPU_CUDA(h, cudaFreeAsync(d_out, s.stream));
+        KGPU_CUDA(h, cudaStreamSynchronize(s.stream));
+        for (size_t j = 0; j < m; j++) out_node_keys[pos[j]] = res[j];
+    }
+    return KGPU_OK;
+}
+
 int kgpu_score_batch_device(kgpu_t *h, const int32_t *d_pods, int64_t P, uint64_t *d_keys, void *stream) {
     if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_score_batch_device: NULL handle");
     std::lock_guard<std::mutex> g(h->mu);
     if (h->shards.size() != 1) return fail(h, KGPU_ERR_STATE, "kgpu_score_batch_device: needs a single-device handle");
     if (P < 0 || (P > 0 && (!d_pods || !d_keys))) return fail(h, KGPU_ERR_INVALID, "kgpu_score_batch_device: bad arguments");
     kgpu_shard &s = h->shards[0];
-    return launch_score(h, s, d_pods, P, reinterpret_cast<unsigned long long *>(d_keys),
-                        stream ? (cudaStream_t)stream : s.stream);
+    return launch_score(h, s, d_pods, P, reinterpret_cast<unsigned long long *>(d_keys), (cudaStream_t)stream);
 }
 
 int kgpu_reduce_shards_device(kgpu_t *h, const uint64_t *d_gathered, int G, int64_t P, uint64_t *d_out, void *stream) {
@@ -435,7 +480,7 @@ int kgpu_reduce_shards_device(kgpu_t *h, const uint64_t *d_gathered, int G, int6
     if (P == 0) return KGPU_OK;
     kgpu_shard &s = h->shards[0];
     KGPU_CUDA(h, cudaSetDevice(s.dev));
-    kgpu::reduce_shards<<<(unsigned)((P + 255) / 256), 256, 0, stream ? (cudaStream_t)stream : s.stream>>>(
+    kgpu::reduce_shards<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const unsigned long long *>(d_gathered), G, P, reinterpret_cast<unsigned long long *>(d_out));
     h->launches++;
     KGPU_CUDA(h, cudaGetLastError());

@@ -111,12 +111,22 @@ class Scorer:
         self._check(self._L.kgpu_score_batch(self._h, pods.ctypes.data, P, out.ctypes.data))
         return out
 
+    def score_pairs(self, node_idx, ks) -> np.ndarray:
+        """Per-pair query: (cost << 8 | mask) of node node_idx[i] for k = ks[i], or 0xFFFFFFFF."""
+        node_idx = np.ascontiguousarray(node_idx, dtype=np.int64)
+        ks = _i32(ks)
+        out = np.empty(node_idx.shape[0], dtype=np.uint32)
+        self._check(self._L.kgpu_score_pairs(self._h, node_idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                             ks.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), node_idx.shape[0],
+                                             out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))))
+        return out
+
     def score_batch_ptr(self, pods_addr: int, P: int, out_addr: int) -> None:
         """Same call on raw host addresses (e.g. pinned torch tensors' data_ptr())."""
         self._check(self._L.kgpu_score_batch(self._h, pods_addr, int(P), out_addr))
 
     def score_batch_device(self, d_pods_addr: int, P: int, d_keys_addr: int, stream: int = 0) -> None:
-        """Device buffers, enqueued on `stream` (cudaStream_t as int, 0 = handle stream)."""
+        """Device buffers, enqueued on `stream` (cudaStream_t as int, 0 = the CUDA default stream)."""
         self._check(self._L.kgpu_score_batch_device(self._h, d_pods_addr, int(P), d_keys_addr, stream or None))
 
     def reduce_shards_device(self, d_gathered_addr: int, G: int, P: int, d_out_addr: int, stream: int = 0) -> None:
