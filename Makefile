@@ -8,7 +8,19 @@ NVCCFLAGS ?= $(EXTRA) -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-W
 CSRC := kubegpu_b200/csrc
 LIB := kubegpu_b200/lib/libkgpu.so
 
-all: $(LIB) oracle
+HOSTLIB := kubegpu_b200/lib/libkgpu_host.so
+CLI := kubegpu_b200/lib/kgpu_sched_cli
+CXX ?= g++
+CXXFLAGS ?= -O2 -std=c++17 -fPIC -Wall -Wextra
+
+all: $(LIB) $(HOSTLIB) $(CLI) oracle
+
+# C++ mirror of the reference's DeviceScheduler plugin (host layer above the C ABI)
+$(HOSTLIB): $(CSRC)/host/device_scheduler.cc $(CSRC)/host/device_scheduler.h include/kgpu.h $(LIB)
+	$(CXX) $(CXXFLAGS) -shared -o $@ $(CSRC)/host/device_scheduler.cc -Lkubegpu_b200/lib -lkgpu -Wl,-rpath,'$$ORIGIN'
+
+$(CLI): $(CSRC)/host/sched_cli.cc $(HOSTLIB)
+	$(CXX) $(CXXFLAGS) -o $@ $(CSRC)/host/sched_cli.cc -Lkubegpu_b200/lib -lkgpu_host -lkgpu -Wl,-rpath,'$$ORIGIN'
 
 $(LIB): $(CSRC)/kgpu.cu $(CSRC)/score_pairs.cuh $(CSRC)/subset_dp_gen.cuh $(CSRC)/multi_device.cc $(CSRC)/multi_device.h include/kgpu.h
 	@mkdir -p kubegpu_b200/lib

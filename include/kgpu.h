@@ -71,7 +71,8 @@ extern "C" {
 #define KGPU_VARIANT_AUTO 0          /* = LANE_PER_NODE                                      */
 #define KGPU_VARIANT_WARP_PER_PAIR 1 /* north_star mapping: warp per (pod,node), lane per subset */
 #define KGPU_VARIANT_LANE_PER_NODE 2 /* lane per node, pair costs in registers, full per-pair enumeration */
-#define KGPU_VARIANT_MEMO_BY_K 3     /* per-node best[k] computed once, pods look it up (NOT the headline) */
+#define KGPU_VARIANT_MEMO_BY_K 3     /* global best[k] computed once, pods look it up (NOT the headline) */
+#define KGPU_VARIANT_TILE_MEMO 4     /* lane per node, per-k minima hoisted out of the pod loop (NOT the headline) */
 
 #define KGPU_KEY_COST(key) ((uint32_t)((key) >> 40))
 #define KGPU_KEY_NODE(key) ((uint32_t)(((key) >> 8) & 0xFFFFFFFFu))

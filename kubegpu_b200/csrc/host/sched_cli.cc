@@ -19,6 +19,7 @@
 //   best K                                      findBestTreeInCache(K)
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <iostream>
 #include <sstream>
 

@@ -157,9 +157,12 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
     if (wpp)
         kgpu::score_pairs_warp_per_pair<<<grid, kgpu::WPP_THREADS, 0, st>>>(topo4, s.d_free, s.n, s.node_id_base, pods4, P,
                                                                             (int)per, W, PC, d_keys);
+    else if (h->variant == KGPU_VARIANT_TILE_MEMO)
+        kgpu::score_pairs_lane_per_node<false><<<grid, kgpu::LPN_THREADS, 0, st>>>(topo4, s.d_free, s.n, s.node_id_base, pods4,
+                                                                                   P, (int)per, W, PC, d_keys);
     else
-        kgpu::score_pairs_lane_per_node<<<grid, kgpu::LPN_THREADS, 0, st>>>(topo4, s.d_free, s.n, s.node_id_base, pods4, P,
-                                                                            (int)per, W, PC, d_keys);
+        kgpu::score_pairs_lane_per_node<true><<<grid, kgpu::LPN_THREADS, 0, st>>>(topo4, s.d_free, s.n, s.node_id_base, pods4,
+                                                                                  P, (int)per, W, PC, d_keys);
     h->launches++;
     KGPU_CUDA(h, cudaGetLastError());
     return KGPU_OK;
@@ -295,7 +298,7 @@ int kgpu_set_variant(kgpu_t *h, int variant) {
     if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_set_variant: NULL handle");
     std::lock_guard<std::mutex> g(h->mu);
     if (variant == KGPU_VARIANT_AUTO) variant = KGPU_VARIANT_LANE_PER_NODE;
-    if (variant < KGPU_VARIANT_WARP_PER_PAIR || variant > KGPU_VARIANT_MEMO_BY_K)
+    if (variant < KGPU_VARIANT_WARP_PER_PAIR || variant > KGPU_VARIANT_TILE_MEMO)
         return fail(h, KGPU_ERR_INVALID, "kgpu_set_variant: unknown variant %d", variant);
     h->variant = variant;
     return KGPU_OK;

@@ -1,0 +1,233 @@
+"""The C++ host mirror of the reference's DeviceScheduler plugin
+(kubegpu_b200/csrc/host/) driven through its line-protocol CLI and compared, transcript
+against transcript, with Oracle A (the Python restatement pinned by the reference's goldens).
+
+CPU part (`--no-device`): tree cache, request translation, knob/error behaviour.
+GPU part (marked gpu): ScoreBatch / PodFitsDevice score / PodAllocate / Take-Return against
+Oracle B on the matrices the group names imply."""
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle_a as oa
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "kubegpu_b200", "lib", "kgpu_sched_cli")
+P = oa.DEVICE_GROUP_PREFIX
+
+
+@pytest.fixture(scope="module")
+def cli():
+    if not os.path.exists(CLI):
+        subprocess.check_call(["make", "-s", "-C", ROOT, "kubegpu_b200/lib/kgpu_sched_cli"])
+    return CLI
+
+
+def run_cli(cli, script, device=False):
+    args = [cli] + ([] if device else ["--no-device"])
+    return subprocess.run(args, input=script, capture_output=True, text=True, check=True).stdout
+
+
+# ---- the same interpreter over Oracle A ----------------------------------------------------
+def _dump_pod(pod, out):
+    for kind, cs in (("run", pod.RunningContainers), ("init", pod.InitContainers)):
+        for name in sorted(cs):
+            c = cs[name]
+            out.append("  %s %s req=%d" % (kind, name, c.Requests.get(oa.RESOURCE_GPU, -1)))
+            for k in sorted(c.DevRequests):
+                out.append("    dev %s=%d" % (k, c.DevRequests[k]))
+            for k in sorted(c.AllocateFrom):
+                out.append("    from %s -> %s" % (k, c.AllocateFrom[k]))
+
+
+def run_oracle(script):
+    sched = oa.NvidiaGPUScheduler()
+    nodes, pods, out = {}, {}, []
+    for line in script.splitlines():
+        toks = line.split()
+        if not toks or toks[0].startswith("#"):
+            continue
+        out.append("> " + line)
+        cmd = toks[0]
+        if cmd == "addnode":
+            ni = oa.NodeInfo(KubeAlloc={oa.RESOURCE_GPU: int(toks[2])})
+            for t in toks[3:]:
+                k, v = t.rsplit("=", 1)
+                ni.Allocatable[k] = int(v)
+            nodes[toks[1]] = ni
+            sched.AddNode(toks[1], ni)
+            out += ["  alloc %s=%d" % (k, ni.Allocatable[k]) for k in sorted(ni.Allocatable)]
+        elif cmd == "rmnode":
+            sched.RemoveNode(toks[1])
+        elif cmd == "pod":
+            pod = oa.PodInfo(Name=toks[1])
+            cur, i = None, 2
+            while i < len(toks):
+                t = toks[i]
+                if t in ("run", "init"):
+                    cur = oa.ContainerInfo()
+                    (pod.RunningContainers if t == "run" else pod.InitContainers)[toks[i + 1]] = cur
+                    i += 1
+                elif t.startswith("topogen="):
+                    pod.Requests[oa.GPU_TOPOLOGY_GENERATION] = int(t[8:])
+                elif cur is not None and t.startswith("req="):
+                    cur.Requests[oa.RESOURCE_GPU] = int(t[4:])
+                elif cur is not None and t.startswith("kube="):
+                    cur.KubeRequests[oa.RESOURCE_GPU] = int(t[5:])
+                elif cur is not None and t.startswith("dev:"):
+                    k, v = t[4:].rsplit("=", 1)
+                    cur.DevRequests[k] = int(v)
+                i += 1
+            pods[toks[1]] = pod
+        elif cmd in ("fits", "allocate"):
+            if toks[1] not in nodes or toks[2] not in pods:
+                out.append("  unknown node or pod")
+                continue
+            if cmd == "fits":
+                fits, reasons, score = sched.PodFitsDevice(nodes[toks[1]], pods[toks[2]], False)
+                out.append("  fits=%d reasons=%d score=%.17g" % (1 if fits else 0, 0, score))
+            else:
+                out.append("  err=%s" % (sched.PodAllocate(nodes[toks[1]], pods[toks[2]]) or ""))
+            _dump_pod(pods[toks[2]], out)
+        elif cmd == "cache":
+            rows = []
+            for tree, info in sched.cache.node_cache:
+                rows.append(oa.format_tree_node(tree) + "score=%.17g nodes=%s" % (
+                    info.TreeScore, "".join(n + "," for n in sorted(info.ListOfNodes))))
+            out += sorted(rows)
+        elif cmd == "best":
+            t = sched.cache.find_best_tree_in_cache(int(toks[1]))
+            out.append(oa.format_tree_node(t).rstrip("\n") if t else "  none")
+        else:
+            out.append("  unknown command")
+    return "\n".join(out) + "\n"
+
+
+def node_line(name, shape, kube=None, ids=None):
+    res = oa.shape_to_resources(shape)
+    if ids:
+        res = {k.replace("/gpu/%d/" % i, "/gpu/%s/" % ids[i]): v for i, k in enumerate(sorted(res, key=lambda s: int(s.split("/gpu/")[1].split("/")[0])))
+               for v in [res[k]]}
+    n = sum(sum(g) for g in shape)
+    return "addnode %s %d %s" % (name, n if kube is None else kube, " ".join("%s=%d" % kv for kv in sorted(res.items())))
+
+
+GOLDEN_SCRIPT = "\n".join([
+    node_line("A", [[2, 2], [2, 2]]), node_line("B", [[2, 2], [4]]), node_line("C", [[2, 2], [2, 2]]),
+    "addnode D 0 ABCD=4", "cache", "rmnode A", "cache",
+    "pod p3 run A req=3 dev:%s/gpugrp1/B/gpugrp0/3/gpu/6/cards=1 dev:%s/gpugrp1/B/gpugrp0/3/gpu/7/cards=1" % (P, P),
+    "fits C p3", "rmnode B", "cache", "fits C p3", "best 3", "best 9",
+]) + "\n"
+
+
+def test_reference_TestTree_through_the_cpp_host(cli):
+    """gpuschedulerplugin/gpu_test.go:43-112 replayed through the C++ mirror."""
+    got = run_cli(cli, GOLDEN_SCRIPT)
+    assert got == run_oracle(GOLDEN_SCRIPT)
+    first, second = got.split("> fits C p3")[1:3]
+    assert "gpugrp1/0/gpugrp0/0/gpu/2/cards=1" in first            # golden 1: gpu 0,1,2 of the 4-group
+    assert "gpugrp1/0/gpugrp0/1/gpu/0/cards=1" in second and "gpu/2/" not in second.split("> best")[0]
+    assert "score=nan nodes=D," in got
+
+
+def test_knobs_errors_and_flat_translation(cli):
+    script = "\n".join([
+        node_line("N1", [[4], [2, 2]]),
+        "pod bad topogen=7 run a req=2", "fits N1 bad", "allocate N1 bad",
+        "pod flat topogen=0 run a req=2 run b req=1", "fits N1 flat", "allocate N1 flat",
+        "pod auto topogen=1 run a req=2 kube=5 init i req=6", "fits N1 auto",
+        "pod big run a req=9", "fits N1 big", "allocate N1 big",
+        "rmnode N1", "pod late run a req=2", "fits N1 late", "allocate N1 late",
+        "addnode F 3 %s/gpu/0/cards=1 %s/gpu/1/cards=1 %s/gpu/2/cards=1" % (P, P, P), "cache",
+        "pod onflat run a req=2", "fits F onflat",
+    ]) + "\n"
+    got = run_cli(cli, script)
+    assert got == run_oracle(script)
+    assert "err=Invalid topology generation request" in got
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_scripts_match_oracle(cli, seed):
+    rng = random.Random(seed)
+    shapes = [[[8]], [[4], [4]], [[2, 2], [2, 2]], [[4, 4]], [[4], [2, 2]], [[1]] * 4, [[3, 3, 2]], [[3], [3], [2]],
+              [[1, 1, 1, 1], [3]], [[2, 2, 1], [3]], [[1, 1, 1, 1, 1, 1], [2]], [[6], [1, 1]], [[5, 1], [2]]]
+    lines, names = [], []
+    for step in range(60):
+        r = rng.random()
+        if r < 0.35 or not names:
+            name = "n%d" % rng.randrange(12)
+            lines.append(node_line(name, rng.choice(shapes)))
+            if name not in names:
+                names.append(name)
+        elif r < 0.45:
+            lines.append("rmnode %s" % rng.choice(names))
+        elif r < 0.55:
+            lines.append("cache")
+        elif r < 0.65:
+            lines.append("best %d" % rng.randrange(0, 10))
+        else:
+            pod = "p%d" % step
+            conts = " ".join("%s c%d req=%d" % (rng.choice(["run", "run", "init"]), i, rng.randrange(0, 5))
+                             for i in range(rng.randrange(1, 4)))
+            knob = rng.choice(["", "", "topogen=1 ", "topogen=0 ", "topogen=3 "])
+            lines.append("pod %s %s%s" % (pod, knob, conts))
+            lines.append("%s %s %s" % (rng.choice(["fits", "allocate"]), rng.choice(names), pod))
+    script = "\n".join(lines) + "\n"
+    assert run_cli(cli, script) == run_oracle(script)
+
+
+# ---- GPU part --------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_score_batch_allocate_take_return_on_gpu(cli, oracle_b):
+    from kubegpu_b200 import synth
+    ids = ["GPU-%02d" % i for i in range(8)]
+    script = "\n".join([
+        node_line("A", [[2, 2], [2, 2]], ids=ids), node_line("B", [[4], [2, 2]], ids=ids), node_line("C", [[1]] * 4),
+        "pod p1 run a req=1", "pod p2 run a req=2", "pod p3 run a req=1 run b req=2", "pod p4 run a req=4",
+        "pod p8 run a req=8", "pod p9 run a req=9", "pod p5 run a req=5",
+        "scorebatch p1 p2 p3 p4 p8 p9 p5",
+        "fits A p4", "fits B p4", "fits C p4", "fits C p2",
+        "allocate B p3", "take p4", "scorebatch p4 p2", "take p4", "return p4", "scorebatch p4",
+    ]) + "\n"
+    got = run_cli(cli, script, device=True)
+    W = oracle_b.DEFAULT_WEIGHTS
+    tA, tB = synth.shape_matrix([[2, 2], [2, 2]]), synth.shape_matrix([[4], [2, 2]])
+    tC = np.zeros(64, np.int32)
+    tC.reshape(8, 8)[:4, :4] = 1 - np.eye(4, dtype=np.int32)          # four singletons: cross level 1
+    topo, free = np.stack([tA, tB, tC]), np.array([0xFF, 0xFF, 0x0F], np.int32)
+    names = ["A", "B", "C"]
+    keys = oracle_b.score_batch(topo, free, synth.make_pods(np.array([1, 2, 3, 4, 8, 9, 5], np.int32)), W)
+    block = got.split("> scorebatch p1 p2 p3 p4 p8 p9 p5\n")[1].split("> fits")[0].splitlines()
+    assert block[0] == "  err="
+    for line, pod, key in zip(block[1:], ["p1", "p2", "p3", "p4", "p8", "p9", "p5"], keys):
+        u = oracle_b.unpack_key(key)
+        want = ("  %s fits=0 cost=0 node= mask=0x00" % pod) if u is None else \
+            "  %s fits=1 cost=%d node=%s mask=0x%02x" % (pod, u[0], names[u[1]], u[2])
+        assert line == want
+    # per-pair score = 1/(1+cost of this node's best subset); C cannot host 4 GPUs -> k=4 fits the 4 singletons
+    def score_of(node, k):
+        nk = oracle_b.node_key(topo[node], int(free[node]), k)
+        return None if nk == oracle_b.NODE_NO_FIT else 1.0 / (1.0 + (nk >> 8))
+    for node, pod, k in (("A", "p4", 4), ("B", "p4", 4), ("C", "p4", 4), ("C", "p2", 2)):
+        line = got.split("> fits %s %s\n" % (node, pod))[1].splitlines()[0]
+        s = score_of(names.index(node), k)
+        assert line == ("  fits=0 reasons=0 score=0" if s is None else "  fits=1 reasons=0 score=%.17g" % s)
+    # PodAllocate after ScoreBatch: p3 (k=3) was placed on B's 4-group, slots 0,1,2 -> real GPU ids
+    alloc = got.split("> allocate B p3\n")[1].split("> take")[0]
+    assert "err=\n" in alloc
+    froms = [ln.strip() for ln in alloc.splitlines() if ln.strip().startswith("from")]
+    assert len(froms) == 3 and {f.split("/gpu/")[-1].split("/")[0] for f in froms} == {"GPU-00", "GPU-01", "GPU-02"}
+    assert all("-> %s/gpugrp1/" % P in f and f.endswith("/cards") for f in froms)
+    # Take: p4 took B's 4-group (mask 0x0f) -> rescoring p4 moves it off those GPUs, p2 avoids them too
+    after = got.split("> take p4\n")[1]
+    assert after.splitlines()[0] == "  err="
+    free2 = free.copy()
+    free2[1] = 0xF0
+    k2 = oracle_b.score_batch(topo, free2, synth.make_pods(np.array([4, 2], np.int32)), W)
+    lines = after.split("> scorebatch p4 p2\n")[1].splitlines()
+    for line, pod, key in zip(lines[1:3], ["p4", "p2"], k2):
+        u = oracle_b.unpack_key(key)
+        assert line == "  %s fits=1 cost=%d node=%s mask=0x%02x" % (pod, u[0], names[u[1]], u[2])
