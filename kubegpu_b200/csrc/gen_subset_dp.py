@@ -36,7 +36,7 @@ import os
 
 PAIRS = list(itertools.combinations(range(8), 2))
 NACC = int(os.environ.get("KGPU_GEN_NACC", "4"))          # independent min/max accumulators (ILP)
-STAGE_Y = os.environ.get("KGPU_GEN_STAGE_Y", "1") == "1"   # keep yXY in registers next to cXY
+STAGE_Y = os.environ.get("KGPU_GEN_STAGE_Y", "0") == "1"   # keep yXY in registers (makes K=2 hoistable: off)
 
 
 def c(i, j):
@@ -110,10 +110,11 @@ class Body:
 
 
 def gen_row_sums(b):
-    """r'_i = sum_j c_ij + bit_i (2 A3 + 2 F2 + 1), tm = total + 0xFF."""
+    """r_i = sum_j c_ij (4 F2 + 1 A3, every operand of the A3 goes through an F2 so nothing
+    here is invariant across pods), tm = total + 0xFF, q_i = r_i + bit_i."""
     for i in range(8):
         t = [c(i, j) for j in range(8) if j != i]
-        b.w("const uint32_t r%d = A3(A3(%s, %s, %s), F2(%s, %s), F2(%s, %s));" % (i, t[0], t[1], t[2], t[3], t[4], t[5], t[6]))
+        b.w("const uint32_t r%d = A3(F2(%s, %s), F2(%s, %s), F2(%s, F2(%s, %s)));" % (i, t[0], t[1], t[2], t[3], t[4], t[5], t[6]))
     b.w("const uint32_t tm = (A3(A3(r0, r1, r2), A3(r3, r4, r5), F2(r6, r7)) >> 1) + 0xFFu;")
     for i in range(8):
         b.w("const uint32_t q%d = r%d + 0x%02xu;" % (i, i, 1 << i))   # R'_i
@@ -166,6 +167,12 @@ def gen():
     for i in range(0, len(fields), 14):
         grp = fields[i:i + 14]
         w('    asm volatile("" : ' + ", ".join('"+r"(p.%s)' % f for f in grp) + ");")
+    w("}")
+    w("")
+
+    w("// K = 1: the 8 single-GPU subsets all cost 0; the key is the lowest free bit (times the per-pod one).")
+    w("__device__ __forceinline__ uint32_t best_k1(uint32_t free, const PipeConsts k) {")
+    w("    return free ? (free & (0u - free)) * k.one : 0xFFFFFFFFu;")
     w("}")
     w("")
 
@@ -254,11 +261,15 @@ def gen():
     terms = [c(a, bb) for a, bb in PAIRS]
     b = Body()
     b.lines = []
-    alu = ["A3(%s, %s, %s)" % tuple(terms[i:i + 3]) for i in range(0, 15, 3)]          # 15 terms, 5 IADD3
-    fma = terms[15]
-    for t in terms[16:]:                                                                # 13 terms, 12 IMAD
-        fma = "F2(%s, %s)" % (t, fma)
-    b.w("return A3(A3(%s, %s, %s), A3(%s, %s, %s), 0xFFu);" % (alu[0], alu[1], alu[2], alu[3], alu[4], fma))
+    # a tree of F2 (x*one + y with x itself a product of `one`): the sum is a polynomial in the
+    # per-pod multiplier, which no compiler factors back into hoistable invariant partial sums
+    level = terms[:]
+    while len(level) > 1:
+        nxt = ["F2(%s, %s)" % (level[i], level[i + 1]) for i in range(0, len(level) - 1, 2)]
+        if len(level) % 2:
+            nxt.append(level[-1])
+        level = nxt
+    b.w("return %s + 0xFFu;" % level[0])
     out += [sig % 8] + b.lines + ["}", ""]
 
     w("#undef A3")
