@@ -19,8 +19,8 @@ Prints ONE JSON line on rank 0.  Keys beyond the base contract:
                 from the committed ncu capture) is far below the algorithmic bytes and the
                 kernel is integer-issue bound.
   cpu_baseline  Oracle B (tuned C port, all host cores) on a bounded pod sample.
-  variants      the north_star warp-per-pair mapping and the memoise-by-k shortcut, for
-                context only (never the headline).
+  variants      the north_star warp-per-pair mapping and the two memoising shortcuts (per-tile
+                hoisting, global memoise-by-k), for context only (never the headline).
 `--impl reference` times the CPU port of the path instead (the reference itself is Go
 with un-vendored dependencies and cannot be built here: DESIGN.md "Oracle").
 """
@@ -311,6 +311,7 @@ def main():
     variants = {}
     if world == 1 and not args.no_variants:
         for name, var, reps in (("warp_per_pair_north_star_mapping", _lib.VARIANT_WARP_PER_PAIR, 3),
+                                ("tile_memo_not_headline", _lib.VARIANT_TILE_MEMO, 10),
                                 ("memo_by_k_not_headline", _lib.VARIANT_MEMO_BY_K, 10)):
             scorer.set_variant(var)
             step_device()

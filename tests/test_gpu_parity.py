@@ -10,7 +10,7 @@ from kubegpu_b200 import _lib, synth
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [_lib.VARIANT_LANE_PER_NODE, _lib.VARIANT_WARP_PER_PAIR, _lib.VARIANT_MEMO_BY_K]
+VARIANTS = [_lib.VARIANT_LANE_PER_NODE, _lib.VARIANT_WARP_PER_PAIR, _lib.VARIANT_MEMO_BY_K, _lib.VARIANT_TILE_MEMO]
 
 
 @pytest.fixture(scope="module")
@@ -127,7 +127,7 @@ def test_variants_agree_at_full_c2_size(scorer, oracle_b):
     (d) every reported (node, mask) re-scores to the reported cost."""
     topo, free, pods = synth.gen_c2()
     outs = {v: _score(scorer, v, topo, free, pods) for v in VARIANTS}
-    assert (outs[VARIANTS[0]] == outs[VARIANTS[1]]).all() and (outs[VARIANTS[0]] == outs[VARIANTS[2]]).all()
+    assert all((outs[VARIANTS[0]] == outs[v]).all() for v in VARIANTS[1:])
     keys = outs[VARIANTS[0]]
     sample = np.arange(0, 10_000, 625)
     want = oracle_b.score_batch(topo, free, pods[sample], fast=True, nthreads=8)
