@@ -132,11 +132,27 @@ def cpu_baseline(topo, free, pods, target_s: float = 12.0):
     """Oracle B (tuned port, all cores) on a bounded sample: the first S pods of the
     workload against ALL nodes.  Returns the cpu_baseline object."""
     from oracle import oracle_b
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     S, dt = _sized_cpu_run(oracle_b, topo, free, pods, cores, target_s)
     return {"value": S / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "first %d of %d pods x all %d nodes, oracle/oracle_b.c tuned variant, %d threads, %.1f s"
                       % (S, len(pods), len(free), cores, dt)}
+
+
+def usable_cores() -> int:
+    """Threads the CPU arm may really use: the scheduler affinity capped by the cgroup CPU quota
+    (the GPU boxes show 128 logical CPUs but a 24-CPU quota)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
 
 
 def _sized_cpu_run(oracle_b, topo, free, pods, cores, target_s):
@@ -161,7 +177,7 @@ def run_reference(args):
     from kubegpu_b200 import synth
     from oracle import oracle_b
     topo, free, pods = synth.gen_c2(N_NODES, N_PODS)
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     oracle_b.lib()
     # size each step's pod sample so that warmup+steps finish in a few minutes (<= ~6 s per step)
     budget = min(6.0, 150.0 / max(1, args.steps + args.warmup))
