@@ -35,7 +35,9 @@ import itertools
 import os
 
 PAIRS = list(itertools.combinations(range(8), 2))
-NACC = int(os.environ.get("KGPU_GEN_NACC", "4"))          # independent min/max accumulators (ILP)
+NACC = int(os.environ.get("KGPU_GEN_NACC", "2"))          # independent min/max accumulators (ILP)
+K4_FORMB_EVERY = int(os.environ.get("KGPU_GEN_K4_FORMB", "9"))   # every n-th K=4 subset as IMAD+VIADDMNMX (0 = never)
+K3_FORMB_EVERY = int(os.environ.get("KGPU_GEN_K3_FORMB", "0"))   # same for K=3
 STAGE_Y = os.environ.get("KGPU_GEN_STAGE_Y", "0") == "1"   # keep yXY in registers (makes K=2 hoistable: off)
 
 
@@ -191,7 +193,7 @@ def gen():
     n = 0
     for a, bb, d in itertools.combinations(range(8), 3):
         q = "F2(%s, %s)" % (c(a, d), c(bb, d))
-        if n % 3 == 2:      # form B: both adds on the FMA pipe, fused add+min on the ALU pipe
+        if K3_FORMB_EVERY and n % K3_FORMB_EVERY == K3_FORMB_EVERY - 1:      # form B: both adds on the FMA pipe, fused add+min on the ALU pipe
             b.addfold("F2(%s, %s)" % (y(a, bb), q), "0x%02xu" % (1 << d))
         else:               # form A: one IADD3, MIN3 per two keys
             b.fold("A3(%s, %s, 0x%02xu)" % (y(a, bb), q, 1 << d))
@@ -212,7 +214,7 @@ def gen():
         for d in range(bb + 1, 7):
             b.w("    const uint32_t t%d = F2(%s, q%d);" % (d, y(a, bb), d))
             for e in range(d + 1, 8):
-                if n % 9 == 8:
+                if K4_FORMB_EVERY and n % K4_FORMB_EVERY == K4_FORMB_EVERY - 1:
                     b.addfold("F2(t%d, q%d)" % (d, e), y(d, e))
                 else:
                     b.fold("A3(t%d, q%d, %s)" % (d, e, y(d, e)))

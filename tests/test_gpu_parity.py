@@ -168,3 +168,48 @@ def test_device_buffer_entry_point_and_k2(scorer, oracle_b):
     got = out.cpu().numpy().view(np.uint64)
     assert (got == oracle_b.score_batch(topo, free, pods, fast=True, nthreads=4)).all()
     assert scorer.kernel_launches > 0
+
+
+def test_one_million_nodes_c3_scale(scorer, oracle_b):
+    """BASELINE config 3's node count on one GPU (1M nodes = 256 MB of topology), k in 1..8:
+    an oracle-checked pod sample, per-k collapse, and agreement of the sharded flow (8 shards
+    scored one after the other + K2) with the unsharded launch."""
+    import torch
+    topo, free, pods = synth.gen_c3(N=1_000_000, P=2048)
+    scorer.set_variant(_lib.VARIANT_LANE_PER_NODE)
+    scorer.upload_nodes(topo, free)
+    keys = scorer.score_batch(pods)
+    sample = np.arange(0, 2048, 128)
+    assert (keys[sample] == oracle_b.score_batch(topo, free, pods[sample], fast=True, nthreads=8)).all()
+    for k in range(1, 9):
+        assert len(set(keys[pods[:, 0] == k].tolist())) == 1
+    G, per = 8, 125_000
+    d_pods = torch.from_numpy(pods).cuda()
+    gathered = torch.empty((G, 2048), dtype=torch.int64, device="cuda")
+    out = torch.empty(2048, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for g in range(G):
+        scorer.upload_nodes(topo[g * per:(g + 1) * per], free[g * per:(g + 1) * per], node_id_base=g * per)
+        scorer.score_batch_device(d_pods.data_ptr(), 2048, gathered[g].data_ptr(), st)
+        torch.cuda.synchronize()
+    scorer.reduce_shards_device(gathered.data_ptr(), G, 2048, out.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert (out.cpu().numpy().view(np.uint64) == keys).all()
+
+
+def test_ten_million_nodes_sweep_point(scorer, oracle_b):
+    """Largest point of BASELINE config 5's sweep: 10M nodes (2.56 GB of topology in HBM).
+    Few pods (the oracle has to follow); checks 64-bit indexing and node ids near 10^7."""
+    N = 10_000_000
+    topo, free, pods = synth.gen_c2(N=N, P=64, seed=synth.SEED_C5)
+    # make the very last node the unique best home for k=8 so the answer must come from the far end
+    topo[N - 1] = 9
+    free[N - 1] = 0xFF
+    scorer.set_variant(_lib.VARIANT_LANE_PER_NODE)
+    scorer.upload_nodes(topo, free)
+    keys = scorer.score_batch(pods)
+    sample = np.array([0, 1, 2, 3, 17, 40, 63])
+    assert (keys[sample] == oracle_b.score_batch(topo, free, pods[sample], fast=True, nthreads=8)).all()
+    k8 = keys[pods[:, 0] == 8]
+    assert len(k8) and all(((int(k) >> 8) & 0xFFFFFFFF) == N - 1 and (int(k) >> 40) == 0 for k in k8)
+    scorer.upload_nodes(topo[:1], free[:1])          # release the 2.5 GB before the next test
