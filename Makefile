@@ -16,8 +16,8 @@ CXXFLAGS ?= -O2 -std=c++17 -fPIC -Wall -Wextra
 all: $(LIB) $(HOSTLIB) $(CLI) oracle
 
 # C++ mirror of the reference's DeviceScheduler plugin (host layer above the C ABI)
-$(HOSTLIB): $(CSRC)/host/device_scheduler.cc $(CSRC)/host/device_scheduler.h include/kgpu.h $(LIB)
-	$(CXX) $(CXXFLAGS) -shared -o $@ $(CSRC)/host/device_scheduler.cc -Lkubegpu_b200/lib -lkgpu -Wl,-rpath,'$$ORIGIN'
+$(HOSTLIB): $(CSRC)/host/device_scheduler.cc $(CSRC)/host/gpus_info.cc $(CSRC)/host/device_scheduler.h $(CSRC)/host/gpus_info.h include/kgpu.h $(LIB)
+	$(CXX) $(CXXFLAGS) -shared -o $@ $(CSRC)/host/device_scheduler.cc $(CSRC)/host/gpus_info.cc -Lkubegpu_b200/lib -lkgpu -Wl,-rpath,'$$ORIGIN'
 
 $(CLI): $(CSRC)/host/sched_cli.cc $(HOSTLIB)
 	$(CXX) $(CXXFLAGS) -o $@ $(CSRC)/host/sched_cli.cc -Lkubegpu_b200/lib -lkgpu_host -lkgpu -Wl,-rpath,'$$ORIGIN'

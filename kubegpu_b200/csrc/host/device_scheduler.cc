@@ -7,6 +7,7 @@
 #include <regex>
 
 #include "../../../include/kgpu.h"
+#include "gpus_info.h"
 
 namespace kubedevice {
 namespace types {
@@ -457,6 +458,37 @@ std::string NvidiaGPUScheduler::SetNodeTopology(const std::string &nodeName, con
     it->second.explicitTopo = true;
     dirty_ = true;
     return "";
+}
+
+std::string NvidiaGPUScheduler::AddNodeFromGpusInfo(const std::string &nodeName, const std::string &gpusInfoJSON,
+                                                    bool useNVML, types::NodeInfo *nodeInfo) {
+    nvgputypes::GpusInfo info;
+    std::string err = nvgputypes::ParseGpusInfo(gpusInfoJSON, &info);
+    if (!err.empty()) return lastError_ = err;
+    if (info.Gpus.size() > KGPU_MAX_GPUS_PER_NODE) return lastError_ = "AddNodeFromGpusInfo: more than 8 GPUs on " + nodeName;
+    nvidia::DiscoverTopology(&info, useNVML);
+    *nodeInfo = types::NodeInfo();
+    nodeInfo->Name = nodeName;
+    nvidia::UpdateNodeInfo(info, nodeInfo);
+    AddNode(nodeName, nodeInfo);
+    // slot i of the node record = i-th advertised name in sorted order; map it back to the GPU
+    const NodeRecord *rec = node(nodeName);
+    const std::vector<int32_t> links = nvidia::LinkMatrix(info);
+    const size_t n = info.Gpus.size();
+    std::vector<size_t> gpuOfSlot;
+    for (const std::string &slotName : rec->gpuNames)
+        for (size_t g = 0; g < n; g++)
+            if (info.Gpus[g].Name == slotName) { gpuOfSlot.push_back(g); break; }
+    if (gpuOfSlot.size() != rec->gpuNames.size()) return lastError_ = "AddNodeFromGpusInfo: advertised names do not map back to GPUs";
+    int32_t topo[64] = {0};
+    for (size_t i = 0; i < gpuOfSlot.size(); i++)
+        for (size_t j = 0; j < gpuOfSlot.size(); j++)
+            if (i != j) {
+                const int32_t l = links[gpuOfSlot[i] * n + gpuOfSlot[j]];
+                if (l < 0 || l >= KGPU_NUM_LEVELS) return lastError_ = "AddNodeFromGpusInfo: link level outside 0..15";
+                topo[i * 8 + j] = l;
+            }
+    return SetNodeTopology(nodeName, topo);
 }
 
 // Push the host-side node array to the device(s) if it changed since the last launch.

@@ -155,6 +155,11 @@ public:
     // Real NVML link matrix for a node (int32[8][8] row-major, levels 0..15) instead of the
     // one derived from its 2-level group names.
     std::string SetNodeTopology(const std::string &nodeName, const int32_t topo[64]);
+    // Node from the node agent's GPU inventory JSON (nvgputypes.GpusInfo): names exactly as the
+    // agent would advertise them, then AddNode, then the REAL link matrix (not the one implied by
+    // the two group levels).  Fills *nodeInfo like the agent's UpdateNodeInfo.  "" or error text.
+    std::string AddNodeFromGpusInfo(const std::string &nodeName, const std::string &gpusInfoJSON, bool useNVML,
+                                    types::NodeInfo *nodeInfo);
     // Score a whole scheduling cycle in one kernel launch: best node + GPU set per pod.
     std::string ScoreBatch(const std::vector<const types::PodInfo *> &pods, std::vector<Placement> *out);
     std::string LastError() const { return lastError_; }

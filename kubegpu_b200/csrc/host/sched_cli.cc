@@ -15,6 +15,8 @@
 //   allocate NODE POD                           PodAllocate    -> error text + AllocateFrom
 //   take POD | return POD                       TakePodResources / ReturnPodResources
 //   scorebatch POD...                           ScoreBatch (GPU)
+//   addjson NAME FILE [nvml]                    AddNodeFromGpusInfo (node agent JSON), dumps names + matrix
+//   visible POD                                 NVIDIA_VISIBLE_DEVICES per container (node agent Allocate)
 //   cache                                       dump the tree cache
 //   best K                                      findBestTreeInCache(K)
 #include <cstdio>
@@ -23,7 +25,10 @@
 #include <iostream>
 #include <sstream>
 
+#include <fstream>
+
 #include "device_scheduler.h"
+#include "gpus_info.h"
 
 using namespace gpuschedulerplugin;
 namespace types = kubedevice::types;
@@ -83,6 +88,29 @@ int main(int argc, char **argv) {
                 if (splitKV(tok, &k, &v)) ni.Allocatable[k] = v;
             sched.AddNode(name, &ni);
             for (const auto &kv : ni.Allocatable) printf("  alloc %s=%lld\n", kv.first.c_str(), (long long)kv.second);
+        } else if (cmd == "addjson") {
+            std::string name, file, mode;
+            in >> name >> file >> mode;
+            std::ifstream f(file);
+            std::stringstream buf;
+            buf << f.rdbuf();
+            types::NodeInfo &ni = g_nodes[name];
+            const std::string err = sched.AddNodeFromGpusInfo(name, buf.str(), mode == "nvml", &ni);
+            printf("  err=%s\n", err.c_str());
+            for (const auto &kv : ni.Allocatable) printf("  alloc %s=%lld\n", kv.first.c_str(), (long long)kv.second);
+            if (const auto *rec = sched.node(name)) {
+                for (int i = 0; i < 8; i++) {
+                    printf("  topo");
+                    for (int j = 0; j < 8; j++) printf(" %d", rec->topo[i * 8 + j]);
+                    printf("\n");
+                }
+            }
+        } else if (cmd == "visible") {
+            std::string podName;
+            in >> podName;
+            if (!g_pods.count(podName)) { printf("  unknown pod\n"); continue; }
+            for (const auto &c : g_pods[podName].RunningContainers)
+                printf("  %s NVIDIA_VISIBLE_DEVICES=%s\n", c.first.c_str(), nvidia::VisibleDevices(c.second).c_str());
         } else if (cmd == "rmnode") {
             std::string name;
             in >> name;

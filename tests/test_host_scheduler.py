@@ -60,6 +60,30 @@ def run_oracle(script):
             nodes[toks[1]] = ni
             sched.AddNode(toks[1], ni)
             out += ["  alloc %s=%d" % (k, ni.Allocatable[k]) for k in sorted(ni.Allocatable)]
+        elif cmd == "addjson":
+            gpus = oa.parse_gpus_info(open(toks[2]).read())
+            mgr = oa.NvidiaGPUManager(gpus, use_nvml=(len(toks) > 3 and toks[3] == "nvml"))
+            ni = oa.NodeInfo()
+            mgr.UpdateNodeInfo(ni)
+            nodes[toks[1]] = ni
+            sched.AddNode(toks[1], ni)
+            out.append("  err=")
+            out += ["  alloc %s=%d" % (k, ni.Allocatable[k]) for k in sorted(ni.Allocatable)]
+            # slot i = i-th advertised cards key in sorted order -> GPU index -> real link matrix
+            slot_names = [k[len(P) + 1:-len("/cards")] for k in sorted(ni.Allocatable) if k.endswith("/cards")]
+            by_name = {g.Name: i for i, g in enumerate(mgr.gpus[uid] for uid in mgr.index_to_id)}
+            links = oa.link_matrix_from_gpus(gpus)
+            topo = [[0] * 8 for _ in range(8)]
+            for i, a in enumerate(slot_names):
+                for j, b in enumerate(slot_names):
+                    if i != j:
+                        topo[i][j] = links[by_name[a]][by_name[b]]
+            out += ["  topo " + " ".join(str(v) for v in row) for row in topo]
+        elif cmd == "visible":
+            pod = pods[toks[1]]
+            for name in sorted(pod.RunningContainers):
+                env = oa.NvidiaGPUManager([]).Allocate(pod, pod.RunningContainers[name])
+                out.append("  %s NVIDIA_VISIBLE_DEVICES=%s" % (name, "" if env is None else ",".join(sorted_ids(pod.RunningContainers[name]))))
         elif cmd == "rmnode":
             sched.RemoveNode(toks[1])
         elif cmd == "pod":
@@ -104,6 +128,14 @@ def run_oracle(script):
         else:
             out.append("  unknown command")
     return "\n".join(out) + "\n"
+
+
+def sorted_ids(cont):
+    """The node agent's Allocate walks AllocateFrom (a Go map); the C++ mirror walks it in
+    sorted-key order, so compare in that order."""
+    import re
+    rx = re.compile(P + r"/gpugrp1/.*/gpugrp0/.*/gpu/(.*?)/cards")
+    return [rx.search(cont.AllocateFrom[k]).group(1) for k in sorted(cont.AllocateFrom) if rx.search(cont.AllocateFrom[k])]
 
 
 def node_line(name, shape, kube=None, ids=None):
@@ -179,6 +211,56 @@ def test_random_scripts_match_oracle(cli, seed):
     assert run_cli(cli, script) == run_oracle(script)
 
 
+def _inventory_json(rng, n, sockets, pair_level=5, socket_level=3, cross=None):
+    """A GPU inventory in the reference's JSON schema: GPUs paired on switches, grouped on sockets."""
+    import json
+    buses = ["%04X:%02X:00.0" % (rng.randrange(1 << 16), i) for i in range(n)]
+    devs = []
+    for i in range(n):
+        topo = []
+        for j in range(n):
+            if i == j:
+                continue
+            if i // 2 == j // 2:
+                topo.append({"BusID": buses[j], "Link": pair_level})
+            elif i * sockets // n == j * sockets // n:
+                topo.append({"BusID": buses[j], "Link": socket_level})
+            elif cross is not None:
+                topo.append({"BusID": buses[j], "Link": cross})
+        devs.append({"UUID": "GPU-%04x-%d" % (rng.randrange(1 << 16), i), "Path": "/dev/nvidia%d" % i, "Model": "B200",
+                     "PCI": {"BusID": buses[i], "Bandwidth": 63000}, "Topology": topo or None,
+                     "Memory": {"Global": 183359}, "Unknown": {"nested": [1, 2.5e3, "x\\y", None, True]}})
+    return json.dumps({"Version": {"Driver": "580.159", "CUDA": "12.9"}, "Devices": devs})
+
+
+def test_gpus_info_json_ingestion_matches_oracle(cli, golden_dir, tmp_path):
+    """node agent JSON -> advertised names (the reference's TestAlloc goldens,
+    nvidia_gpu_manager_test.go:120-145) -> AddNode -> real link matrix, C++ mirror vs Oracle A."""
+    rng = random.Random(11)
+    files = [os.path.join(golden_dir, "gpus_titanx.json"), os.path.join(golden_dir, "gpus_k80.json")]
+    for i, (n, sockets, cross) in enumerate([(8, 2, 1), (8, 1, None), (4, 2, 2), (6, 2, None), (2, 1, None), (8, 4, 1)]):
+        path = tmp_path / ("inv%d.json" % i)
+        path.write_text(_inventory_json(rng, n, sockets, pair_level=rng.choice([4, 5, 6]), socket_level=rng.choice([1, 2, 3]), cross=cross))
+        files.append(str(path))
+    lines = []
+    for i, f in enumerate(files):
+        lines.append("addjson J%d %s%s" % (i, f, " nvml" if i % 3 == 2 else ""))
+    lines += ["cache", "best 4", "pod p run a req=3", "fits J0 p", "rmnode J0", "best 8"]
+    script = "\n".join(lines) + "\n"
+    got = run_cli(cli, script)
+    assert got == run_oracle(script)
+    # the reference's own expectations for its two fixtures
+    titan = got.split("> addjson J1")[0]
+    for i in range(8):
+        assert "alloc %s/gpugrp1/%d/gpugrp0/%d/gpu/GPU0%d/cards=1" % (P, i // 4, i // 2, i) in titan
+        assert "alloc %s/gpugrp1/%d/gpugrp0/%d/gpu/GPU0%d/memory=%d" % (P, i // 4, i // 2, i, 12238 * 1024 * 1024) in titan
+    k80 = got.split("> addjson J1")[1].split("> addjson J2")[0]
+    assert "gpugrp1/3/gpugrp0/3/gpu/GPU-aa4a86d4-3e1b-f48d-a69f-6aadd5f94466/cards=1" in k80
+    bad = tmp_path / "bad.json"
+    bad.write_text('{"Devices": [ {"UUID": "x", ')
+    assert "err=GpusInfo:" in run_cli(cli, "addjson B %s\n" % bad)
+
+
 # ---- GPU part --------------------------------------------------------------------------------
 @pytest.mark.gpu
 def test_score_batch_allocate_take_return_on_gpu(cli, oracle_b):
@@ -231,3 +313,27 @@ def test_score_batch_allocate_take_return_on_gpu(cli, oracle_b):
     for line, pod, key in zip(lines[1:3], ["p4", "p2"], k2):
         u = oracle_b.unpack_key(key)
         assert line == "  %s fits=1 cost=%d node=%s mask=0x%02x" % (pod, u[0], names[u[1]], u[2])
+
+
+@pytest.mark.gpu
+def test_json_node_scored_with_real_matrix_and_visible_devices(cli, golden_dir, oracle_b):
+    """The TITAN X inventory ingested from JSON is scored with its real NVML matrix (cross-socket
+    pairs are absent there -> level 0 -> W[0]=64), not the 5/3/1 matrix its group names imply;
+    PodAllocate + the node agent's Allocate regex give NVIDIA_VISIBLE_DEVICES."""
+    f = os.path.join(golden_dir, "gpus_titanx.json")
+    script = "\n".join([
+        "addjson T %s" % f, "pod p5 run a req=5", "pod p2 run a req=2 run b req=1",
+        "scorebatch p5 p2", "fits T p5", "allocate T p2", "visible p2",
+    ]) + "\n"
+    got = run_cli(cli, script, device=True)
+    gpus = oa.parse_gpus_info(open(f).read())
+    M = np.array(oa.link_matrix_from_gpus(gpus), dtype=np.int32).reshape(64)      # slots are GPU00..GPU07 in order
+    k5 = oracle_b.node_key(M, 0xFF, 5)
+    k3 = oracle_b.node_key(M, 0xFF, 3)
+    assert k5 >> 8 == 2 * 2 + 4 * 8 + 4 * 64         # one whole socket (2 pairs W[5]=2, 4 pairs W[3]=8) + 1 GPU across (4 x W[0]=64)
+    lines = got.split("> scorebatch p5 p2\n")[1].splitlines()
+    assert lines[1] == "  p5 fits=1 cost=%d node=T mask=0x%02x" % (k5 >> 8, k5 & 0xFF)
+    assert lines[2] == "  p2 fits=1 cost=%d node=T mask=0x%02x" % (k3 >> 8, k3 & 0xFF)
+    assert got.split("> fits T p5\n")[1].splitlines()[0] == "  fits=1 reasons=0 score=%.17g" % (1.0 / (1.0 + (k5 >> 8)))
+    vis = got.split("> visible p2\n")[1].splitlines()
+    assert vis[0] == "  a NVIDIA_VISIBLE_DEVICES=GPU00,GPU01" and vis[1] == "  b NVIDIA_VISIBLE_DEVICES=GPU02"
