@@ -128,6 +128,15 @@ int kgpu_score_batch_device(kgpu_t *h, const int32_t *d_pods, int64_t P, uint64_
  * Host buffers, synchronous. */
 int kgpu_score_pairs(kgpu_t *h, const int64_t *node_idx, const int32_t *k, int64_t n, uint32_t *out_node_keys);
 
+/* Stateful sequential placement (what TakePodResources would make of a scheduling cycle;
+ * a no-op in the reference, gpu_scheduler.go:57-63).  Pods are placed IN ORDER; each one gets
+ * the best (cost, node, mask) under the free masks left by the pods before it and then takes
+ * those GPUs: the handle's device-side free masks are updated.  Host buffers, synchronous,
+ * single-device handles only. */
+int kgpu_place_batch(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_keys);
+/* Copy the current free masks (n = kgpu_num_nodes entries) back to the host. */
+int kgpu_get_free_masks(kgpu_t *h, int32_t *out_free_mask, int64_t n);
+
 /* K2: d_out[p] = min over g < G of d_gathered[g*P + p] (after an all-gather of
  * every shard's keys), enqueued on `stream`. */
 int kgpu_reduce_shards_device(kgpu_t *h, const uint64_t *d_gathered, int G, int64_t P,

@@ -13,7 +13,7 @@ SYMBOLS = [
     "kgpu_version", "kgpu_create", "kgpu_destroy", "kgpu_last_error", "kgpu_set_weights",
     "kgpu_get_weights", "kgpu_set_variant", "kgpu_upload_nodes", "kgpu_update_node",
     "kgpu_set_free_mask", "kgpu_remove_node", "kgpu_num_nodes", "kgpu_score_batch",
-    "kgpu_score_batch_device", "kgpu_score_pairs", "kgpu_reduce_shards_device", "kgpu_kernel_launches",
+    "kgpu_score_batch_device", "kgpu_score_pairs", "kgpu_place_batch", "kgpu_get_free_masks", "kgpu_reduce_shards_device", "kgpu_kernel_launches",
     "kgpu_last_kernel_ms",
 ]
 
@@ -66,6 +66,10 @@ def load() -> ctypes.CDLL:
     L.kgpu_score_batch_device.argtypes = [vp, vp, i64, vp, vp]
     L.kgpu_score_pairs.restype = ci
     L.kgpu_score_pairs.argtypes = [vp, ctypes.POINTER(i64), i32p, i64, ctypes.POINTER(ctypes.c_uint32)]
+    L.kgpu_place_batch.restype = ci
+    L.kgpu_place_batch.argtypes = [vp, vp, i64, vp]
+    L.kgpu_get_free_masks.restype = ci
+    L.kgpu_get_free_masks.argtypes = [vp, i32p, i64]
     L.kgpu_reduce_shards_device.restype = ci
     L.kgpu_reduce_shards_device.argtypes = [vp, vp, ci, i64, vp, vp]
     L.kgpu_kernel_launches.restype = i64

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "multi_device.h"
+#include "place_sequential.cuh"
 #include "score_pairs.cuh"
 
 namespace {
@@ -41,6 +42,9 @@ struct kgpu_shard {
     unsigned long long *d_keys = nullptr;    // [pcap]
     unsigned long long *d_gather = nullptr;  // [ndev][pcap] (multi-device only)
     unsigned long long *d_bestk = nullptr;   // [9] memo variant
+    uint32_t *d_nodebest = nullptr;          // [9][Npad]  K3 tables
+    unsigned long long *d_tilebest = nullptr;   // [9][T]
+    int64_t place_cap = 0;
     int64_t pcap = 0;
 };
 
@@ -195,6 +199,8 @@ void free_shard(kgpu_shard &s) {
     if (s.d_keys) cudaFree(s.d_keys);
     if (s.d_gather) cudaFree(s.d_gather);
     if (s.d_bestk) cudaFree(s.d_bestk);
+    if (s.d_nodebest) cudaFree(s.d_nodebest);
+    if (s.d_tilebest) cudaFree(s.d_tilebest);
     if (s.ev0) cudaEventDestroy(s.ev0);
     if (s.ev1) cudaEventDestroy(s.ev1);
     if (s.stream) cudaStreamDestroy(s.stream);
@@ -422,6 +428,67 @@ int kgpu_score_batch(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_ke
         worst = std::max(worst, (double)ms);
     }
     h->last_kernel_ms = worst;
+    return KGPU_OK;
+}
+
+int kgpu_place_batch(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_keys) {
+    if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_place_batch: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (h->shards.size() != 1) return fail(h, KGPU_ERR_STATE, "kgpu_place_batch: needs a single-device handle");
+    if (P < 0 || (P > 0 && (!pods || !out_keys))) return fail(h, KGPU_ERR_INVALID, "kgpu_place_batch: bad arguments");
+    if (P == 0) return KGPU_OK;
+    kgpu_shard &s = h->shards[0];
+    int rc = ensure_pod_capacity(h, s, P);
+    if (rc != KGPU_OK) return rc;
+    KGPU_CUDA(h, cudaSetDevice(s.dev));
+    KGPU_CUDA(h, cudaMemcpyAsync(s.d_pods, pods, (size_t)P * 16, cudaMemcpyHostToDevice, s.stream));
+    if (s.n == 0) {
+        KGPU_CUDA(h, cudaMemsetAsync(s.d_keys, 0xFF, (size_t)P * 8, s.stream));
+    } else {
+        const int64_t T = (s.n + kgpu::PLACE_TILE - 1) / kgpu::PLACE_TILE, Npad = T * kgpu::PLACE_TILE;
+        if (Npad > s.place_cap) {
+            if (s.d_nodebest) cudaFree(s.d_nodebest);
+            if (s.d_tilebest) cudaFree(s.d_tilebest);
+            s.d_nodebest = nullptr; s.d_tilebest = nullptr; s.place_cap = 0;
+            KGPU_CUDA(h, cudaMalloc(&s.d_nodebest, (size_t)Npad * 9 * 4));
+            KGPU_CUDA(h, cudaMalloc(&s.d_tilebest, (size_t)T * 9 * 8));
+            s.place_cap = Npad;
+        }
+        kgpu::Weights W;
+        memcpy(W.w, h->W, sizeof W.w);
+        KGPU_CUDA(h, cudaEventRecord(s.ev0, s.stream));
+        kgpu::place_init<<<(unsigned)T, kgpu::PLACE_TILE, 0, s.stream>>>(reinterpret_cast<const int4 *>(s.d_topo), s.d_free, s.n, Npad,
+                                                                        s.node_id_base, W, PC, s.d_nodebest, s.d_tilebest, T);
+        kgpu::place_sequential<<<1, kgpu::PLACE_THREADS, 0, s.stream>>>(s.d_topo, s.d_free, s.n, Npad, s.node_id_base,
+                                                                        reinterpret_cast<const int4 *>(s.d_pods), P, W, s.d_nodebest,
+                                                                        s.d_tilebest, T, s.d_keys);
+        h->launches += 2;
+        KGPU_CUDA(h, cudaGetLastError());
+        KGPU_CUDA(h, cudaEventRecord(s.ev1, s.stream));
+    }
+    KGPU_CUDA(h, cudaMemcpyAsync(out_keys, s.d_keys, (size_t)P * 8, cudaMemcpyDeviceToHost, s.stream));
+    KGPU_CUDA(h, cudaStreamSynchronize(s.stream));
+    if (s.n > 0) {
+        float ms = 0.f;
+        KGPU_CUDA(h, cudaEventElapsedTime(&ms, s.ev0, s.ev1));
+        h->last_kernel_ms = ms;
+    }
+    return KGPU_OK;
+}
+
+int kgpu_get_free_masks(kgpu_t *h, int32_t *out_free_mask, int64_t n) {
+    if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_get_free_masks: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (n != h->n_total || (n > 0 && !out_free_mask)) return fail(h, KGPU_ERR_INVALID, "kgpu_get_free_masks: n must equal kgpu_num_nodes");
+    int64_t off = 0;
+    for (auto &s : h->shards) {
+        if (s.n > 0) {
+            KGPU_CUDA(h, cudaSetDevice(s.dev));
+            KGPU_CUDA(h, cudaMemcpyAsync(out_free_mask + off, s.d_free, (size_t)s.n * 4, cudaMemcpyDeviceToHost, s.stream));
+            KGPU_CUDA(h, cudaStreamSynchronize(s.stream));
+        }
+        off += s.n;
+    }
     return KGPU_OK;
 }
 

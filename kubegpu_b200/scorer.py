@@ -111,6 +111,20 @@ class Scorer:
         self._check(self._L.kgpu_score_batch(self._h, pods.ctypes.data, P, out.ctypes.data))
         return out
 
+    def place_batch(self, pods, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Stateful sequential placement: pods in order, each takes its GPUs (device free masks change)."""
+        pods = _i32(pods)
+        P = pods.size // 4
+        if out is None:
+            out = np.empty(P, dtype=np.uint64)
+        self._check(self._L.kgpu_place_batch(self._h, pods.ctypes.data, P, out.ctypes.data))
+        return out
+
+    def get_free_masks(self) -> np.ndarray:
+        out = np.empty(self.num_nodes, dtype=np.int32)
+        self._check(self._L.kgpu_get_free_masks(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), out.shape[0]))
+        return out
+
     def score_pairs(self, node_idx, ks) -> np.ndarray:
         """Per-pair query: (cost << 8 | mask) of node node_idx[i] for k = ks[i], or 0xFFFFFFFF."""
         node_idx = np.ascontiguousarray(node_idx, dtype=np.int64)

@@ -195,3 +195,46 @@ void kgpu_oracle_reduce_shards(const uint64_t *gathered, int G, int64_t P, uint6
         out[p] = best;
     }
 }
+
+/* ---- K3 twin: stateful sequential placement ------------------- */
+/* for p in order: key_p = kgpu_oracle_score_batch of pod p alone under the CURRENT free
+ * masks; if it fits, the chosen GPUs leave free_mask[node].  free_mask is updated in place.
+ * Plain version: literally that (small cases). */
+void kgpu_oracle_place_batch_plain(const int32_t *topo, int32_t *free_mask, int64_t N,
+                                   int64_t node_id_base, const int32_t *pods, int64_t P,
+                                   const int32_t *W, uint64_t *out_keys)
+{
+    for (int64_t p = 0; p < P; p++) {
+        kgpu_oracle_score_batch(topo, free_mask, N, node_id_base, pods + 4 * p, 1, W, out_keys + p);
+        if (out_keys[p] == KGPU_NO_FIT) continue;
+        int64_t n = (int64_t)((out_keys[p] >> 8) & 0xFFFFFFFFu) - node_id_base;
+        free_mask[n] = (int32_t)(((uint32_t)free_mask[n] & 0xFFu) & ~(uint32_t)(out_keys[p] & 0xFFu));
+    }
+}
+
+/* Same results with a per-node cache of the 9 node keys (only the chosen node changes). */
+void kgpu_oracle_place_batch(const int32_t *topo, int32_t *free_mask, int64_t N,
+                             int64_t node_id_base, const int32_t *pods, int64_t P,
+                             const int32_t *W, uint64_t *out_keys)
+{
+    uint32_t *nb = (uint32_t *)malloc(sizeof(uint32_t) * 9 * (size_t)(N > 0 ? N : 1));
+    for (int64_t n = 0; n < N; n++)
+        for (int k = 0; k <= 8; k++) nb[9 * n + k] = kgpu_oracle_node_key(topo + 64 * n, free_mask[n], k, W);
+    for (int64_t p = 0; p < P; p++) {
+        int k = pods[4 * p];
+        out_keys[p] = KGPU_NO_FIT;
+        if (k < 0 || k > 8) continue;
+        uint32_t best = NODE_NO_FIT;
+        int64_t bn = -1;
+        for (int64_t n = 0; n < N; n++) {
+            uint32_t nk = nb[9 * n + k];
+            if (nk == NODE_NO_FIT) continue;
+            if (bn < 0 || (nk >> 8) < (best >> 8)) { best = nk; bn = n; }   /* lower cost; ties keep lower node */
+        }
+        if (bn < 0) continue;
+        out_keys[p] = pod_key(best, (uint64_t)(node_id_base + bn));
+        free_mask[bn] = (int32_t)(((uint32_t)free_mask[bn] & 0xFFu) & ~(best & 0xFFu));
+        for (int kk = 0; kk <= 8; kk++) nb[9 * bn + kk] = kgpu_oracle_node_key(topo + 64 * bn, free_mask[bn], kk, W);
+    }
+    free(nb);
+}

@@ -53,6 +53,9 @@ def lib() -> ctypes.CDLL:
         L.kgpu_oracle_score_batch_fast.restype = None
         L.kgpu_oracle_score_batch_fast.argtypes = [i32p, i32p, ctypes.c_int64, ctypes.c_int64, i32p,
                                                    ctypes.c_int64, i32p, u64p, ctypes.c_int]
+        for fn in (L.kgpu_oracle_place_batch, L.kgpu_oracle_place_batch_plain):
+            fn.restype = None
+            fn.argtypes = [i32p, i32p, ctypes.c_int64, ctypes.c_int64, i32p, ctypes.c_int64, i32p, u64p]
         L.kgpu_oracle_reduce_shards.restype = None
         L.kgpu_oracle_reduce_shards.argtypes = [u64p, ctypes.c_int, ctypes.c_int64, u64p]
         _lib = L
@@ -86,6 +89,18 @@ def score_batch(topo, free_mask, pods, W=DEFAULT_WEIGHTS, node_id_base: int = 0,
     else:
         lib().kgpu_oracle_score_batch(*args)
     return out
+
+
+def place_batch(topo, free_mask, pods, W=DEFAULT_WEIGHTS, node_id_base: int = 0, plain: bool = False):
+    """K3 twin: sequential stateful placement.  Returns (keys[P], free_mask_after[N])."""
+    topo, pods, W = _i32(topo), _i32(pods), _i32(W)
+    free_after = np.array(free_mask, dtype=np.int32, copy=True)
+    N, P = free_after.shape[0], pods.shape[0]
+    out = np.empty(P, dtype=np.uint64)
+    fn = lib().kgpu_oracle_place_batch_plain if plain else lib().kgpu_oracle_place_batch
+    fn(_p(topo, ctypes.c_int32), _p(free_after, ctypes.c_int32), N, int(node_id_base), _p(pods, ctypes.c_int32), P,
+       _p(W, ctypes.c_int32), _p(out, ctypes.c_uint64))
+    return out, free_after
 
 
 def reduce_shards(gathered) -> np.ndarray:
