@@ -345,6 +345,22 @@ def main():
                               "keys_identical_to_headline": same}
         scorer.set_variant(_lib.VARIANT_LANE_PER_NODE)
 
+    # ---- context: K3 stateful sequential placement (pods placed in order, masks updated) ----
+    sequential = None
+    if world == 1 and not args.no_variants:
+        scorer.place_batch(pods[:256])                     # warm-up (changes the masks: re-upload below)
+        seq_ms = []
+        for _ in range(3):
+            scorer.upload_nodes(topo, free, node_id_base=lo)
+            scorer.place_batch(pods)
+            seq_ms.append(scorer.last_kernel_ms)
+        scorer.upload_nodes(topo, free, node_id_base=lo)
+        ms = float(np.median(seq_ms))
+        sequential = {"kernel": "place_init + place_sequential (kgpu_place_batch)", "ms_per_batch": ms,
+                      "value": N_PODS / (ms * 1e-3), "unit": UNIT,
+                      "note": "each pod sees the free masks left by the pods before it (no snapshot collapse); "
+                              "bit-exact vs the CPU twin in tests/test_place_sequential.py"}
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         k1_s = (k1_total_ms / K) * 1e-3
@@ -370,6 +386,8 @@ def main():
         }
         if variants:
             line["variants"] = variants
+        if sequential:
+            line["stateful_sequential"] = sequential
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(topo, free, pods)
         elif world == 1:

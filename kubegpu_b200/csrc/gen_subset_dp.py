@@ -35,8 +35,8 @@ import itertools
 import os
 
 PAIRS = list(itertools.combinations(range(8), 2))
-NACC = int(os.environ.get("KGPU_GEN_NACC", "2"))          # independent min/max accumulators (ILP)
-K4_FORMB_EVERY = int(os.environ.get("KGPU_GEN_K4_FORMB", "9"))   # every n-th K=4 subset as IMAD+VIADDMNMX (0 = never)
+NACC = int(os.environ.get("KGPU_GEN_NACC", "3"))          # independent min/max accumulators (ILP)
+K4_FORMB_EVERY = int(os.environ.get("KGPU_GEN_K4_FORMB", "0"))   # every n-th K=4 subset as IMAD+VIADDMNMX (0 = never)
 K3_FORMB_EVERY = int(os.environ.get("KGPU_GEN_K3_FORMB", "0"))   # same for K=3
 STAGE_Y = os.environ.get("KGPU_GEN_STAGE_Y", "0") == "1"   # keep yXY in registers (makes K=2 hoistable: off)
 
