@@ -234,6 +234,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     W = max(3, args.warmup)
     K = max(1, args.steps)
@@ -288,8 +289,11 @@ def main():
     sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
            torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    sync_token = torch.zeros(1, device=dev)
     for i in range(K):
         flush.zero_()                                  # L2 flush between timed iterations (outside the events)
+        if world > 1:
+            dist.all_reduce(sync_token)                # device-side rendezvous so no rank times another's flush
         ev[i][0].record(stream)
         scorer.score_batch_device(d_pods.data_ptr(), N_PODS, d_local.data_ptr(), sptr)
         ev[i][1].record(stream)                        # K1 only: roofline numerator
