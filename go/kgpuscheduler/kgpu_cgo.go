@@ -86,3 +86,28 @@ func (k *handle) scorePair(node int64, gpus int32) (uint32, error) {
 	}
 	return uint32(out), nil
 }
+
+// placeBatch: stateful sequential placement (pods in order, the device-side free masks are
+// updated).  Same buffers as scoreBatch.
+func (k *handle) placeBatch(pods []int32) ([]uint64, error) {
+	keys := make([]uint64, len(pods)/4)
+	if len(keys) == 0 {
+		return keys, nil
+	}
+	if rc := C.kgpu_place_batch(k.h, (*C.int32_t)(unsafe.Pointer(&pods[0])), C.int64_t(len(keys)),
+		(*C.uint64_t)(unsafe.Pointer(&keys[0]))); rc != C.KGPU_OK {
+		return nil, k.err("kgpu_place_batch")
+	}
+	return keys, nil
+}
+
+func (k *handle) freeMasks(n int64) ([]int32, error) {
+	out := make([]int32, n)
+	if n == 0 {
+		return out, nil
+	}
+	if rc := C.kgpu_get_free_masks(k.h, (*C.int32_t)(unsafe.Pointer(&out[0])), C.int64_t(n)); rc != C.KGPU_OK {
+		return nil, k.err("kgpu_get_free_masks")
+	}
+	return out, nil
+}
