@@ -32,8 +32,12 @@
  *                             upper triangle (i<j) is read; values 0..15
  *                             (0 unknown, 1..6 NVML P2P level, 7..12 NVLink links).
  *   free_mask  int32[N]       bit i = GPU i present and free (low 8 bits).
- *   pods       int32[P][4]    {k, pod_id, flags, reserved}; k GPUs wanted, 0..8.
- *                             pod_id/flags/reserved are carried, not interpreted.
+ *   pods       int32[P][4]    {k, pod_id, flags, min_mem_mib}; k GPUs wanted, 0..8;
+ *                             min_mem_mib > 0: only GPUs with at least that much memory are
+ *                             eligible for this pod (see kgpu_upload_gpu_memory); pod_id/flags
+ *                             are carried, not interpreted.
+ *   gpu_mem    int32[N][8]    MiB per GPU slot (the node agent advertises it per GPU as
+ *                             `.../memory`, nvidia_gpu_manager.go:204-211); optional.
  *   keys       uint64[P]      (cost << 40) | (node_id << 8) | gpu_mask, or
  *                             KGPU_NO_FIT.  cost = sum over GPU pairs i<j in the
  *                             mask of W[topo[i][j]]; the key is the minimum over
@@ -104,6 +108,11 @@ int kgpu_set_variant(kgpu_t *h, int variant);
  * index to form the node_id field of the keys (global id of this shard's node 0). */
 int kgpu_upload_nodes(kgpu_t *h, const int32_t *topo, const int32_t *free_mask, int64_t n,
                       int64_t node_id_base);
+/* Per-GPU memory (MiB) of every node, n = kgpu_num_nodes entries of 8.  Until this is called every
+ * GPU has unlimited memory, i.e. the pods' min_mem_mib never excludes anything.  A later
+ * kgpu_upload_nodes resets it to unlimited. */
+int kgpu_upload_gpu_memory(kgpu_t *h, const int32_t *mem_mib, int64_t n);
+int kgpu_update_gpu_memory(kgpu_t *h, int64_t idx, const int32_t mem_mib[8]);
 /* Overwrite one node (AddNode on an existing name / usage update). */
 int kgpu_update_node(kgpu_t *h, int64_t idx, const int32_t topo[64], int32_t free_mask);
 int kgpu_set_free_mask(kgpu_t *h, int64_t idx, int32_t free_mask);

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libkgpu.so")
 SYMBOLS = [
     "kgpu_version", "kgpu_create", "kgpu_destroy", "kgpu_last_error", "kgpu_set_weights",
     "kgpu_get_weights", "kgpu_set_variant", "kgpu_upload_nodes", "kgpu_update_node",
-    "kgpu_set_free_mask", "kgpu_remove_node", "kgpu_num_nodes", "kgpu_score_batch",
+    "kgpu_set_free_mask", "kgpu_remove_node", "kgpu_upload_gpu_memory", "kgpu_update_gpu_memory", "kgpu_num_nodes", "kgpu_score_batch",
     "kgpu_score_batch_device", "kgpu_score_pairs", "kgpu_place_batch", "kgpu_get_free_masks", "kgpu_reduce_shards_device", "kgpu_kernel_launches",
     "kgpu_last_kernel_ms",
 ]
@@ -52,6 +52,10 @@ def load() -> ctypes.CDLL:
     L.kgpu_set_variant.argtypes = [vp, ci]
     L.kgpu_upload_nodes.restype = ci
     L.kgpu_upload_nodes.argtypes = [vp, i32p, i32p, i64, i64]
+    L.kgpu_upload_gpu_memory.restype = ci
+    L.kgpu_upload_gpu_memory.argtypes = [vp, i32p, i64]
+    L.kgpu_update_gpu_memory.restype = ci
+    L.kgpu_update_gpu_memory.argtypes = [vp, i64, i32p]
     L.kgpu_update_node.restype = ci
     L.kgpu_update_node.argtypes = [vp, i64, i32p, ctypes.c_int32]
     L.kgpu_set_free_mask.restype = ci

@@ -161,6 +161,14 @@ def gen():
     w("}")
     w("")
 
+    # memory-aware path: per-pod penalties on GPUs whose memory is too small for the pod
+    w("// out.cXY = in.cXY + pen[X] + pen[Y]  (pen[i] = PEN if GPU i is not eligible for this pod)")
+    w("__device__ __forceinline__ void apply_pens(const PairCosts &p, PairCosts &o, const uint32_t (&pen)[8]) {")
+    for a, b in PAIRS:
+        w("    o.c%d%d = p.c%d%d + pen[%d] + pen[%d];" % (a, b, a, b, a, b))
+    w("}")
+    w("")
+
     # Compiler barrier: tells nvcc the pair costs may have changed, so the subset enumeration
     # below cannot be hoisted out of the per-pod loop (it IS loop invariant under snapshot
     # scoring: that shortcut is the separately reported tile-memo variant).  No instruction.

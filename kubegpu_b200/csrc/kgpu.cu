@@ -36,6 +36,8 @@ struct kgpu_shard {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int32_t *d_topo = nullptr;       // [n][64]
     int32_t *d_free = nullptr;       // [n]
+    int32_t *d_mem = nullptr;        // [n][8] MiB per GPU (0x7F7F7F7F = unconstrained until uploaded)
+    int *d_flag = nullptr;           // "batch has memory-constrained pods"
     int64_t n = 0, cap = 0;
     int64_t node_id_base = 0;
     int32_t *d_pods = nullptr;       // [pcap][4]
@@ -117,8 +119,9 @@ int ensure_pod_capacity(kgpu_ctx *h, kgpu_shard &s, int64_t P) {
 }
 
 // Enqueue K1 for P pods on shard s: d_keys[p] = best placement over this shard's nodes.
+// has_mem: 1 / 0 = the host knows whether some pod carries min_mem > 0; -1 = unknown (device buffers).
 int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, unsigned long long *d_keys,
-                 cudaStream_t st) {
+                 cudaStream_t st, int has_mem) {
     if (P <= 0) return KGPU_OK;
     if ((reinterpret_cast<uintptr_t>(d_pods) & 15u) != 0)
         return fail(h, KGPU_ERR_INVALID, "pods pointer must be 16-byte aligned");
@@ -128,23 +131,23 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
     const int4 *topo4 = reinterpret_cast<const int4 *>(s.d_topo);
     const int4 *pods4 = reinterpret_cast<const int4 *>(d_pods);
 
-    if (h->variant == KGPU_VARIANT_MEMO_BY_K) {
-        KGPU_CUDA(h, cudaMemsetAsync(s.d_bestk, 0xFF, 9 * 8, st));
-        if (s.n > 0) {
-            int blocks = (int)std::min<int64_t>((s.n + kgpu::LPN_THREADS - 1) / kgpu::LPN_THREADS, (int64_t)s.sm_count * 4);
-            kgpu::memo_best_by_k<<<blocks, kgpu::LPN_THREADS, 0, st>>>(topo4, s.d_free, s.n, s.node_id_base, W, PC, s.d_bestk);
-            h->launches++;
-        }
-        kgpu::memo_gather<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(pods4, P, s.d_bestk, d_keys);
-        h->launches++;
-        KGPU_CUDA(h, cudaGetLastError());
-        return KGPU_OK;
-    }
-
+    const int4 *mem4 = reinterpret_cast<const int4 *>(s.d_mem);
     KGPU_CUDA(h, cudaMemsetAsync(d_keys, 0xFF, (size_t)P * 8, st));
     if (s.n == 0) return KGPU_OK;
 
     const bool wpp = h->variant == KGPU_VARIANT_WARP_PER_PAIR;
+    if (!wpp && has_mem != 0) {   // which pods go to K1m?  (flag read by its blocks; skipped when the host knows there are none)
+        KGPU_CUDA(h, cudaMemsetAsync(s.d_flag, 0, sizeof(int), st));
+        kgpu::any_mem_pod<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(pods4, P, s.d_flag);
+        h->launches++;
+    }
+    if (h->variant == KGPU_VARIANT_MEMO_BY_K) {
+        KGPU_CUDA(h, cudaMemsetAsync(s.d_bestk, 0xFF, 9 * 8, st));
+        int blocks = (int)std::min<int64_t>((s.n + kgpu::LPN_THREADS - 1) / kgpu::LPN_THREADS, (int64_t)s.sm_count * 4);
+        kgpu::memo_best_by_k<<<blocks, kgpu::LPN_THREADS, 0, st>>>(topo4, s.d_free, s.n, s.node_id_base, W, PC, s.d_bestk);
+        kgpu::memo_gather<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(pods4, P, s.d_bestk, d_keys);
+        h->launches += 2;
+    }
     const int tile = wpp ? kgpu::WPP_TILE : kgpu::LPN_THREADS;
     const int64_t tiles = (s.n + tile - 1) / tile;
     // Pod splits: enough blocks for ~8 waves of resident CTAs, but each block keeps
@@ -158,16 +161,26 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
     splits = (P + per - 1) / per;
     if (tiles > 0x7FFFFFFFLL || per > 0x7FFFFFFFLL) return fail(h, KGPU_ERR_INVALID, "batch too large for one launch");
     dim3 grid((unsigned)tiles, (unsigned)splits);
-    if (wpp)
-        kgpu::score_pairs_warp_per_pair<<<grid, kgpu::WPP_THREADS, 0, st>>>(topo4, s.d_free, s.n, s.node_id_base, pods4, P,
+    if (wpp) {
+        kgpu::score_pairs_warp_per_pair<<<grid, kgpu::WPP_THREADS, 0, st>>>(topo4, s.d_free, s.d_mem, s.n, s.node_id_base, pods4, P,
                                                                             (int)per, W, PC, d_keys);
-    else if (h->variant == KGPU_VARIANT_TILE_MEMO)
-        kgpu::score_pairs_lane_per_node<false><<<grid, kgpu::LPN_THREADS, 0, st>>>(topo4, s.d_free, s.n, s.node_id_base, pods4,
-                                                                                   P, (int)per, W, PC, d_keys);
-    else
-        kgpu::score_pairs_lane_per_node<true><<<grid, kgpu::LPN_THREADS, 0, st>>>(topo4, s.d_free, s.n, s.node_id_base, pods4,
-                                                                                  P, (int)per, W, PC, d_keys);
-    h->launches++;
+        h->launches++;
+    } else {
+        if (h->variant == KGPU_VARIANT_TILE_MEMO) {
+            kgpu::score_pairs_lane_per_node<false, false><<<grid, kgpu::LPN_THREADS, 0, st>>>(
+                topo4, s.d_free, mem4, s.d_flag, s.n, s.node_id_base, pods4, P, (int)per, W, PC, d_keys);
+            h->launches++;
+        } else if (h->variant == KGPU_VARIANT_LANE_PER_NODE) {
+            kgpu::score_pairs_lane_per_node<true, false><<<grid, kgpu::LPN_THREADS, 0, st>>>(
+                topo4, s.d_free, mem4, s.d_flag, s.n, s.node_id_base, pods4, P, (int)per, W, PC, d_keys);
+            h->launches++;
+        }
+        if (has_mem != 0) {   // K1m: the memory-constrained pods (its blocks exit at once if the flag is 0)
+            kgpu::score_pairs_lane_per_node<true, true><<<grid, kgpu::LPN_THREADS, 0, st>>>(
+                topo4, s.d_free, mem4, s.d_flag, s.n, s.node_id_base, pods4, P, (int)per, W, PC, d_keys);
+            h->launches++;
+        }
+    }
     KGPU_CUDA(h, cudaGetLastError());
     return KGPU_OK;
 }
@@ -195,6 +208,8 @@ void free_shard(kgpu_shard &s) {
     cudaSetDevice(s.dev);
     if (s.d_topo) cudaFree(s.d_topo);
     if (s.d_free) cudaFree(s.d_free);
+    if (s.d_mem) cudaFree(s.d_mem);
+    if (s.d_flag) cudaFree(s.d_flag);
     if (s.d_pods) cudaFree(s.d_pods);
     if (s.d_keys) cudaFree(s.d_keys);
     if (s.d_gather) cudaFree(s.d_gather);
@@ -252,6 +267,7 @@ int kgpu_create(const int *dev_ids, int ndev, kgpu_t **out) {
         step(cudaEventCreate(&s.ev0), "cudaEventCreate");
         step(cudaEventCreate(&s.ev1), "cudaEventCreate");
         step(cudaMalloc(&s.d_bestk, 9 * 8), "cudaMalloc");
+        step(cudaMalloc(&s.d_flag, sizeof(int)), "cudaMalloc");
     }
     if (rc == KGPU_OK && ndev > 1) {
         std::vector<int> devs(dev_ids, dev_ids + ndev);
@@ -327,11 +343,15 @@ int kgpu_upload_nodes(kgpu_t *h, const int32_t *topo, const int32_t *free_mask, 
         if (cnt > s.cap) {
             if (s.d_topo) cudaFree(s.d_topo);
             if (s.d_free) cudaFree(s.d_free);
-            s.d_topo = nullptr; s.d_free = nullptr; s.cap = 0;
+            if (s.d_mem) cudaFree(s.d_mem);
+            s.d_topo = nullptr; s.d_free = nullptr; s.d_mem = nullptr; s.cap = 0;
             KGPU_CUDA(h, cudaMalloc(&s.d_topo, (size_t)cnt * 256));
             KGPU_CUDA(h, cudaMalloc(&s.d_free, (size_t)cnt * 4));
+            KGPU_CUDA(h, cudaMalloc(&s.d_mem, (size_t)cnt * 32));
             s.cap = cnt;
         }
+        // per-GPU memory is unconstrained (0x7F7F7F7F MiB) until kgpu_upload_gpu_memory says otherwise
+        if (cnt > 0) KGPU_CUDA(h, cudaMemsetAsync(s.d_mem, 0x7F, (size_t)cnt * 32, s.stream));
         if (cnt > 0) {
             KGPU_CUDA(h, cudaMemcpyAsync(s.d_topo, topo + off * 64, (size_t)cnt * 256, cudaMemcpyHostToDevice, s.stream));
             KGPU_CUDA(h, cudaMemcpyAsync(s.d_free, free_mask + off, (size_t)cnt * 4, cudaMemcpyHostToDevice, s.stream));
@@ -345,6 +365,38 @@ int kgpu_upload_nodes(kgpu_t *h, const int32_t *topo, const int32_t *free_mask, 
         KGPU_CUDA(h, cudaStreamSynchronize(s.stream));
     }
     h->n_total = n;
+    return KGPU_OK;
+}
+
+int kgpu_upload_gpu_memory(kgpu_t *h, const int32_t *mem_mib, int64_t n) {
+    if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_upload_gpu_memory: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (n != h->n_total || (n > 0 && !mem_mib)) return fail(h, KGPU_ERR_INVALID, "kgpu_upload_gpu_memory: n must equal kgpu_num_nodes");
+    for (int64_t i = 0; i < n * 8; i++)
+        if (mem_mib[i] < 0) return fail(h, KGPU_ERR_INVALID, "kgpu_upload_gpu_memory: negative memory at node %lld", (long long)(i / 8));
+    int64_t off = 0;
+    for (auto &s : h->shards) {
+        if (s.n > 0) {
+            KGPU_CUDA(h, cudaSetDevice(s.dev));
+            KGPU_CUDA(h, cudaMemcpyAsync(s.d_mem, mem_mib + off * 8, (size_t)s.n * 32, cudaMemcpyHostToDevice, s.stream));
+            KGPU_CUDA(h, cudaStreamSynchronize(s.stream));
+        }
+        off += s.n;
+    }
+    return KGPU_OK;
+}
+
+int kgpu_update_gpu_memory(kgpu_t *h, int64_t idx, const int32_t mem_mib[8]) {
+    if (!h || !mem_mib) return fail(h, KGPU_ERR_INVALID, "kgpu_update_gpu_memory: NULL argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (idx < 0 || idx >= h->n_total) return fail(h, KGPU_ERR_INVALID, "kgpu_update_gpu_memory: index %lld out of range", (long long)idx);
+    for (int i = 0; i < 8; i++)
+        if (mem_mib[i] < 0) return fail(h, KGPU_ERR_INVALID, "kgpu_update_gpu_memory: negative memory");
+    int64_t local = 0;
+    kgpu_shard *s = shard_of(h, idx, &local);
+    KGPU_CUDA(h, cudaSetDevice(s->dev));
+    KGPU_CUDA(h, cudaMemcpyAsync(s->d_mem + local * 8, mem_mib, 32, cudaMemcpyHostToDevice, s->stream));
+    KGPU_CUDA(h, cudaStreamSynchronize(s->stream));
     return KGPU_OK;
 }
 
@@ -393,12 +445,14 @@ int kgpu_score_batch(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_ke
         int rc = ensure_pod_capacity(h, s, P);
         if (rc != KGPU_OK) return rc;
     }
+    int has_mem = 0;
+    for (int64_t p = 0; p < P && !has_mem; p++) has_mem = pods[4 * p + 3] > 0;
     // every device: pods H2D, K1 over its node shard (devices run concurrently)
     for (auto &s : h->shards) {
         KGPU_CUDA(h, cudaSetDevice(s.dev));
         KGPU_CUDA(h, cudaMemcpyAsync(s.d_pods, pods, (size_t)P * 16, cudaMemcpyHostToDevice, s.stream));
         KGPU_CUDA(h, cudaEventRecord(s.ev0, s.stream));
-        int rc = launch_score(h, s, s.d_pods, P, s.d_keys, s.stream);
+        int rc = launch_score(h, s, s.d_pods, P, s.d_keys, s.stream, has_mem);
         if (rc != KGPU_OK) return rc;
         KGPU_CUDA(h, cudaEventRecord(s.ev1, s.stream));
     }
@@ -437,6 +491,8 @@ int kgpu_place_batch(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_ke
     if (h->shards.size() != 1) return fail(h, KGPU_ERR_STATE, "kgpu_place_batch: needs a single-device handle");
     if (P < 0 || (P > 0 && (!pods || !out_keys))) return fail(h, KGPU_ERR_INVALID, "kgpu_place_batch: bad arguments");
     if (P == 0) return KGPU_OK;
+    for (int64_t p = 0; p < P; p++)
+        if (pods[4 * p + 3] > 0) return fail(h, KGPU_ERR_INVALID, "kgpu_place_batch: pod %lld has min_mem > 0 (not supported by the sequential path yet)", (long long)p);
     kgpu_shard &s = h->shards[0];
     int rc = ensure_pod_capacity(h, s, P);
     if (rc != KGPU_OK) return rc;
@@ -540,7 +596,7 @@ int kgpu_score_batch_device(kgpu_t *h, const int32_t *d_pods, int64_t P, uint64_
     if (h->shards.size() != 1) return fail(h, KGPU_ERR_STATE, "kgpu_score_batch_device: needs a single-device handle");
     if (P < 0 || (P > 0 && (!d_pods || !d_keys))) return fail(h, KGPU_ERR_INVALID, "kgpu_score_batch_device: bad arguments");
     kgpu_shard &s = h->shards[0];
-    return launch_score(h, s, d_pods, P, reinterpret_cast<unsigned long long *>(d_keys), (cudaStream_t)stream);
+    return launch_score(h, s, d_pods, P, reinterpret_cast<unsigned long long *>(d_keys), (cudaStream_t)stream, -1);
 }
 
 int kgpu_reduce_shards_device(kgpu_t *h, const uint64_t *d_gathered, int G, int64_t P, uint64_t *d_out, void *stream) {

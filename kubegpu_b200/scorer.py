@@ -84,6 +84,19 @@ class Scorer:
         self._check(self._L.kgpu_upload_nodes(self._h, topo.ctypes.data_as(p32), free_mask.ctypes.data_as(p32),
                                               n, int(node_id_base)))
 
+    def upload_gpu_memory(self, mem_mib) -> None:
+        """mem_mib[N,8]: MiB per GPU slot; pods' min_mem_mib (pods[:,3]) is checked against it."""
+        mem = _i32(mem_mib)
+        if mem.size != 8 * self.num_nodes:
+            raise ValueError("mem_mib must be [N,8]")
+        self._check(self._L.kgpu_upload_gpu_memory(self._h, mem.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), self.num_nodes))
+
+    def update_gpu_memory(self, idx: int, mem_mib) -> None:
+        mem = _i32(mem_mib)
+        if mem.size != 8:
+            raise ValueError("mem_mib must have 8 entries")
+        self._check(self._L.kgpu_update_gpu_memory(self._h, int(idx), mem.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+
     def update_node(self, idx: int, topo, free_mask: int) -> None:
         topo = _i32(topo)
         if topo.size != 64:

@@ -124,3 +124,29 @@ def gen_c1():
     topo = np.stack([t1, t2, k80, empty] * 4).astype(np.int32)
     free = np.array([0xFF, 0xFF, 0x0F, 0x00] * 4, dtype=np.int32)
     return topo, free, make_pods(np.array([1, 2, 3, 4], dtype=np.int32))
+
+
+SEED_C6 = 0xB2000006
+GPU_MEM_CLASSES_MIB = (16_384, 32_768, 81_920, 184_320)      # 16 / 32 / 80 / 180 GiB parts
+POD_MIN_MEM_CHOICES_MIB = (0, 0, 0, 8_000, 20_000, 40_000, 100_000)
+
+
+def gen_gpu_memory(N: int, seed: int = SEED_C6, node_start: int = 0) -> np.ndarray:
+    """int32[N][8] MiB per GPU: 80 % of the nodes carry one memory class on all GPUs, 20 % mix classes
+    per GPU (the node agent advertises `<gpu>/memory` per GPU)."""
+    classes = np.array(GPU_MEM_CLASSES_MIB, dtype=np.int32)
+    node_class = rand_below(seed, 11, N, len(classes), node_start)
+    mixed = rand_below(seed, 12, N, 5, node_start) == 0
+    per_gpu = rand_below(seed, 13, N * 8, len(classes), node_start * 8).reshape(N, 8)
+    idx = np.where(mixed[:, None], per_gpu, node_class[:, None])
+    return np.ascontiguousarray(classes[idx], dtype=np.int32)
+
+
+def gen_c6(N: int = 100_000, P: int = 10_000, seed: int = SEED_C6, node_start: int = 0):
+    """Memory-aware config (not in BASELINE.json; exercises the per-pod min_mem path): C4's heterogeneous
+    topologies, per-GPU memory classes, pods with k in 1..8 and a min_mem drawn from
+    POD_MIN_MEM_CHOICES_MIB.  Returns (topo, free, mem, pods)."""
+    topo, free, pods = gen_c4(N, P, seed, node_start)
+    mem = gen_gpu_memory(N, seed, node_start)
+    pods[:, 3] = np.array(POD_MIN_MEM_CHOICES_MIB, dtype=np.int32)[rand_below(seed, 14, P, len(POD_MIN_MEM_CHOICES_MIB))]
+    return topo, free, mem, pods

@@ -28,6 +28,12 @@
  *   podkey   = min over nodes of (cost<<40 | node_id<<8 | S)   (uint64)
  *   no feasible (node,S) anywhere -> UINT64_MAX.
  *   Subsets are enumerated in increasing integer order (Gosper's hack).
+ *
+ * Memory-aware extension (the node agent advertises per-GPU
+ * `.../memory`, nvidia_gpu_manager.go:204-211): with mem = int32[N][8] (MiB per GPU)
+ * and min_mem = pods[4*p+3] > 0, GPU i of node n is eligible for pod p only if
+ * mem[n][i] >= min_mem, i.e. free is replaced by free & eligible(p, n).  mem == NULL or
+ * min_mem <= 0: no constraint.  The *_mem entry points take that extra array.
  */
 #include <pthread.h>
 #include <stdint.h>
@@ -69,6 +75,16 @@ uint32_t kgpu_oracle_node_key(const int32_t *M, int32_t free_mask, int k, const 
     return best;
 }
 
+/* free mask of node n as pod p sees it: GPUs with too little memory drop out */
+static inline int32_t eff_free(int32_t free_mask, const int32_t *mem8, int32_t min_mem)
+{
+    if (!mem8 || min_mem <= 0) return free_mask;
+    unsigned ok = 0;
+    for (int i = 0; i < 8; i++)
+        if (mem8[i] >= min_mem) ok |= 1u << i;
+    return (int32_t)((unsigned)free_mask & ok);
+}
+
 static inline uint64_t pod_key(uint32_t nk, uint64_t node_id)
 {
     return ((uint64_t)(nk >> 8) << 40) | (node_id << 8) | (uint64_t)(nk & 0xFFu);
@@ -76,21 +92,33 @@ static inline uint64_t pod_key(uint32_t nk, uint64_t node_id)
 
 /* out_keys[p] = best placement of pod p over nodes [0,N) whose global ids are
  * node_id_base + index.  Single thread, no precomputation. */
-void kgpu_oracle_score_batch(const int32_t *topo, const int32_t *free_mask, int64_t N,
-                             int64_t node_id_base, const int32_t *pods, int64_t P,
-                             const int32_t *W, uint64_t *out_keys)
+void kgpu_oracle_score_batch_mem(const int32_t *topo, const int32_t *free_mask, const int32_t *mem,
+                                 int64_t N, int64_t node_id_base, const int32_t *pods, int64_t P,
+                                 const int32_t *W, uint64_t *out_keys)
 {
     for (int64_t p = 0; p < P; p++) {
         int k = pods[4 * p];
         uint64_t best = KGPU_NO_FIT;
         for (int64_t n = 0; n < N; n++) {
-            uint32_t nk = kgpu_oracle_node_key(topo + 64 * n, free_mask[n], k, W);
+            int32_t fm = eff_free(free_mask[n], mem ? mem + 8 * n : NULL, pods[4 * p + 3]);
+            uint32_t nk = kgpu_oracle_node_key(topo + 64 * n, fm, k, W);
             if (nk == NODE_NO_FIT) continue;
             uint64_t key = pod_key(nk, (uint64_t)(node_id_base + n));
             if (key < best) best = key;
         }
         out_keys[p] = best;
     }
+}
+
+void kgpu_oracle_score_batch(const int32_t *topo, const int32_t *free_mask, int64_t N,
+                             int64_t node_id_base, const int32_t *pods, int64_t P,
+                             const int32_t *W, uint64_t *out_keys)
+{
+    int32_t *nomem = (int32_t *)malloc(sizeof(int32_t) * 4 * (size_t)(P > 0 ? P : 1));
+    memcpy(nomem, pods, sizeof(int32_t) * 4 * (size_t)P);
+    for (int64_t p = 0; p < P; p++) nomem[4 * p + 3] = 0;      /* the plain entry point ignores min_mem */
+    kgpu_oracle_score_batch_mem(topo, free_mask, NULL, N, node_id_base, nomem, P, W, out_keys);
+    free(nomem);
 }
 
 /* ---- tuned CPU variant: the reported CPU baseline ---------------------- */
@@ -130,7 +158,7 @@ static void build_cost_table(const int32_t *M, const int32_t *W, uint32_t *cost)
 }
 
 struct fast_job {
-    const int32_t *topo, *free_mask, *pods, *W;
+    const int32_t *topo, *free_mask, *mem, *pods, *W;
     int64_t N, node_id_base, p0, p1;
     uint64_t *out;
 };
@@ -141,12 +169,12 @@ static void *fast_worker(void *arg)
     uint32_t cost[256];
     for (int64_t p = j->p0; p < j->p1; p++) j->out[p] = KGPU_NO_FIT;
     for (int64_t n = 0; n < j->N; n++) {
-        unsigned fm = (unsigned)j->free_mask[n] & 0xFFu;
         uint64_t nid = (uint64_t)(j->node_id_base + n);
         build_cost_table(j->topo + 64 * n, j->W, cost);
         for (int64_t p = j->p0; p < j->p1; p++) {
             int k = j->pods[4 * p];
             if (k < 0 || k > 8) continue;
+            unsigned fm = (unsigned)eff_free(j->free_mask[n], j->mem ? j->mem + 8 * n : NULL, j->pods[4 * p + 3]) & 0xFFu;
             int cnt;
             const uint8_t *subs = subsets_of_size(k, &cnt);
             uint32_t best = NODE_NO_FIT;
@@ -164,9 +192,9 @@ static void *fast_worker(void *arg)
     return NULL;
 }
 
-void kgpu_oracle_score_batch_fast(const int32_t *topo, const int32_t *free_mask, int64_t N,
-                                  int64_t node_id_base, const int32_t *pods, int64_t P,
-                                  const int32_t *W, uint64_t *out_keys, int nthreads)
+void kgpu_oracle_score_batch_fast_mem(const int32_t *topo, const int32_t *free_mask, const int32_t *mem,
+                                      int64_t N, int64_t node_id_base, const int32_t *pods, int64_t P,
+                                      const int32_t *W, uint64_t *out_keys, int nthreads)
 {
     int dummy;
     (void)subsets_of_size(0, &dummy); /* build the table before threads start */
@@ -175,7 +203,7 @@ void kgpu_oracle_score_batch_fast(const int32_t *topo, const int32_t *free_mask,
     pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
     struct fast_job *jobs = (struct fast_job *)malloc(sizeof(struct fast_job) * (size_t)nthreads);
     for (int t = 0; t < nthreads; t++) {
-        jobs[t] = (struct fast_job){topo, free_mask, pods, W, N, node_id_base,
+        jobs[t] = (struct fast_job){topo, free_mask, mem, pods, W, N, node_id_base,
                                     P * t / nthreads, P * (t + 1) / nthreads, out_keys};
         if (t > 0) pthread_create(&th[t], NULL, fast_worker, &jobs[t]);
     }
@@ -183,6 +211,17 @@ void kgpu_oracle_score_batch_fast(const int32_t *topo, const int32_t *free_mask,
     for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
     free(th);
     free(jobs);
+}
+
+void kgpu_oracle_score_batch_fast(const int32_t *topo, const int32_t *free_mask, int64_t N,
+                                  int64_t node_id_base, const int32_t *pods, int64_t P,
+                                  const int32_t *W, uint64_t *out_keys, int nthreads)
+{
+    int32_t *nomem = (int32_t *)malloc(sizeof(int32_t) * 4 * (size_t)(P > 0 ? P : 1));
+    memcpy(nomem, pods, sizeof(int32_t) * 4 * (size_t)P);
+    for (int64_t p = 0; p < P; p++) nomem[4 * p + 3] = 0;
+    kgpu_oracle_score_batch_fast_mem(topo, free_mask, NULL, N, node_id_base, nomem, P, W, out_keys, nthreads);
+    free(nomem);
 }
 
 /* K2 twin: column-min over G gathered key arrays. */

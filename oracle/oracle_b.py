@@ -53,6 +53,12 @@ def lib() -> ctypes.CDLL:
         L.kgpu_oracle_score_batch_fast.restype = None
         L.kgpu_oracle_score_batch_fast.argtypes = [i32p, i32p, ctypes.c_int64, ctypes.c_int64, i32p,
                                                    ctypes.c_int64, i32p, u64p, ctypes.c_int]
+        L.kgpu_oracle_score_batch_mem.restype = None
+        L.kgpu_oracle_score_batch_mem.argtypes = [i32p, i32p, i32p, ctypes.c_int64, ctypes.c_int64, i32p,
+                                                  ctypes.c_int64, i32p, u64p]
+        L.kgpu_oracle_score_batch_fast_mem.restype = None
+        L.kgpu_oracle_score_batch_fast_mem.argtypes = [i32p, i32p, i32p, ctypes.c_int64, ctypes.c_int64, i32p,
+                                                       ctypes.c_int64, i32p, u64p, ctypes.c_int]
         for fn in (L.kgpu_oracle_place_batch, L.kgpu_oracle_place_batch_plain):
             fn.restype = None
             fn.argtypes = [i32p, i32p, ctypes.c_int64, ctypes.c_int64, i32p, ctypes.c_int64, i32p, u64p]
@@ -76,12 +82,23 @@ def node_key(M, free_mask: int, k: int, W=DEFAULT_WEIGHTS) -> int:
 
 
 def score_batch(topo, free_mask, pods, W=DEFAULT_WEIGHTS, node_id_base: int = 0,
-                fast: bool = False, nthreads: int = 1) -> np.ndarray:
-    """keys[P] (uint64) for nodes topo[N,64]/free_mask[N] and pods[P,4]."""
+                fast: bool = False, nthreads: int = 1, mem=None) -> np.ndarray:
+    """keys[P] (uint64) for nodes topo[N,64]/free_mask[N] and pods[P,4].  With mem[N,8] (MiB per
+    GPU) the pods' min_mem field (pods[:,3]) is honoured; without it it is ignored."""
     topo, free_mask, pods, W = _i32(topo), _i32(free_mask), _i32(pods), _i32(W)
     N, P = free_mask.shape[0], pods.shape[0]
     assert topo.size == 64 * N and pods.size == 4 * P and W.size == 16
     out = np.empty(P, dtype=np.uint64)
+    if mem is not None:
+        mem = _i32(mem)
+        assert mem.size == 8 * N
+        args = [_p(topo, ctypes.c_int32), _p(free_mask, ctypes.c_int32), _p(mem, ctypes.c_int32), N, int(node_id_base),
+                _p(pods, ctypes.c_int32), P, _p(W, ctypes.c_int32), _p(out, ctypes.c_uint64)]
+        if fast:
+            lib().kgpu_oracle_score_batch_fast_mem(*args, int(nthreads))
+        else:
+            lib().kgpu_oracle_score_batch_mem(*args)
+        return out
     args = [_p(topo, ctypes.c_int32), _p(free_mask, ctypes.c_int32), N, int(node_id_base),
             _p(pods, ctypes.c_int32), P, _p(W, ctypes.c_int32), _p(out, ctypes.c_uint64)]
     if fast:
@@ -125,13 +142,16 @@ def node_key_py(M: Sequence[int], free_mask: int, k: int, W: Sequence[int] = DEF
     return best
 
 
-def score_batch_py(topo, free_mask, pods, W=DEFAULT_WEIGHTS, node_id_base: int = 0) -> np.ndarray:
+def score_batch_py(topo, free_mask, pods, W=DEFAULT_WEIGHTS, node_id_base: int = 0, mem=None) -> np.ndarray:
     topo = np.asarray(topo).reshape(-1, 64)
     out = np.full(len(pods), NO_FIT, dtype=np.uint64)
     for p, pod in enumerate(np.asarray(pods).reshape(-1, 4)):
         best = int(NO_FIT)
         for n in range(topo.shape[0]):
-            nk = node_key_py(topo[n], int(free_mask[n]), int(pod[0]), W)
+            fm = int(free_mask[n])
+            if mem is not None and int(pod[3]) > 0:
+                fm &= sum(1 << i for i in range(8) if int(np.asarray(mem).reshape(-1, 8)[n][i]) >= int(pod[3]))
+            nk = node_key_py(topo[n], fm, int(pod[0]), W)
             if nk != NODE_NO_FIT:
                 best = min(best, ((nk >> 8) << 40) | ((node_id_base + n) << 8) | (nk & 0xFF))
         out[p] = np.uint64(best)

@@ -16,10 +16,16 @@ ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--nodes", type=int, default=100_000)
 ap.add_argument("--pods", type=int, default=10_000)
 a = ap.parse_args()
-gen = synth.gen_c2 if a.config == "c2" else synth.gen_c3
-topo, free, pods = gen(a.nodes, a.pods)
+mem = None
+if a.config == "c6":
+    topo, free, mem, pods = synth.gen_c6(a.nodes, a.pods)
+else:
+    gen = synth.gen_c2 if a.config == "c2" else synth.gen_c3
+    topo, free, pods = gen(a.nodes, a.pods)
 s = Scorer((0,))
 s.upload_nodes(topo, free)
+if mem is not None:
+    s.upload_gpu_memory(mem)
 d_pods = torch.from_numpy(pods).cuda()
 d_keys = torch.empty(a.pods, dtype=torch.int64, device="cuda")
 st = torch.cuda.Stream()
