@@ -162,10 +162,11 @@ def gen():
     w("")
 
     # memory-aware path: per-pod penalties on GPUs whose memory is too small for the pod
-    w("// out.cXY = in.cXY + pen[X] + pen[Y]  (pen[i] = PEN if GPU i is not eligible for this pod)")
+    w("// out.cXY = in.cXY | pen[X] | pen[Y]  (pen[i] = PEN if GPU i is not eligible for this pod).  OR, not")
+    w("// add: a pair must carry PEN at most once (28 * PEN stays below 2^31); the scaled cost is < PEN.")
     w("__device__ __forceinline__ void apply_pens(const PairCosts &p, PairCosts &o, const uint32_t (&pen)[8]) {")
     for a, b in PAIRS:
-        w("    o.c%d%d = p.c%d%d + pen[%d] + pen[%d];" % (a, b, a, b, a, b))
+        w("    o.c%d%d = p.c%d%d | pen[%d] | pen[%d];" % (a, b, a, b, a, b))
     w("}")
     w("")
 
