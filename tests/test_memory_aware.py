@@ -83,8 +83,12 @@ def test_gpu_memory_aware_parity(oracle_b, variant):
         mem2[12_345] = 184_320
         s.update_gpu_memory(12_345, mem2[12_345])
         assert (s.score_batch(pods) == oracle_b.score_batch(topo, free, pods, mem=mem2, node_id_base=5, fast=True, nthreads=8)).all()
+        with pytest.raises(ValueError):
+            s.upload_gpu_memory(mem[:10])          # the wrapper checks the shape before the C call
+        bad = mem.copy()
+        bad[3, 3] = -1
         with pytest.raises(KgpuError):
-            s.upload_gpu_memory(mem[:10])
+            s.upload_gpu_memory(bad)
         with pytest.raises(KgpuError):
             s.place_batch(pods)            # sequential path: min_mem not supported yet, must say so
 
