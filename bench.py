@@ -134,9 +134,44 @@ def cpu_baseline(topo, free, pods, target_s: float = 12.0):
     from oracle import oracle_b
     cores = usable_cores()
     S, dt = _sized_cpu_run(oracle_b, topo, free, pods, cores, target_s)
-    return {"value": S / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "first %d of %d pods x all %d nodes, oracle/oracle_b.c tuned variant, %d threads, %.1f s"
-                      % (S, len(pods), len(free), cores, dt)}
+    out = {"value": S / dt, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": "first %d of %d pods x all %d nodes, oracle/oracle_b.c tuned variant, %d threads, %.1f s"
+                     % (S, len(pods), len(free), cores, dt)}
+    # SURVEY.md 8(d) extras: the same port on ONE thread, and the reference's real per-call path
+    # (PodFitsDevice = regex + map + tree + greedy per (node, pod) call) restated in Python.
+    t0 = time.perf_counter()
+    oracle_b.score_batch(topo, free, pods[:16], fast=True, nthreads=1)
+    out["single_thread"] = {"value": 16 / (time.perf_counter() - t0), "unit": UNIT, "sample": "16 pods x all nodes"}
+    try:
+        out["reference_algorithm_per_call"] = oracle_a_per_call_cost()
+    except Exception as e:     # never let the context line break the bench
+        out["reference_algorithm_per_call"] = {"error": repr(e)}
+    return out
+
+
+def oracle_a_per_call_cost(n_nodes: int = 1000, n_pods: int = 100):
+    """Restatement of the reference algorithm (NOT Go): PodFitsDevice once per (node, pod) pair on a
+    1,000-node x 100-pod subsample, as SURVEY.md 8(d) asks; python, single thread."""
+    from oracle import oracle_a as oa
+    shapes = ([[8]], [[4], [4]], [[2, 2], [2, 2]], [[4, 4]])
+    sched = oa.NvidiaGPUScheduler()
+    nodes = []
+    for i in range(n_nodes):
+        ni = oa.NodeInfo(Allocatable=oa.shape_to_resources(shapes[i % 4]), KubeAlloc={oa.RESOURCE_GPU: 8})
+        sched.AddNode("n%d" % i, ni)
+        nodes.append(ni)
+    t0 = time.perf_counter()
+    calls = 0
+    for p in range(n_pods):
+        for ni in nodes:
+            pod = oa.PodInfo(RunningContainers={"c": oa.ContainerInfo(Requests={oa.RESOURCE_GPU: (1, 2, 4, 8)[p % 4]})})
+            sched.PodFitsDevice(ni, pod, False)
+            calls += 1
+    dt = time.perf_counter() - t0
+    return {"us_per_PodFitsDevice_call": 1e6 * dt / calls, "calls": calls,
+            "placements_per_s_if_100k_nodes": 1.0 / (dt / calls * 100_000),
+            "note": "oracle/oracle_a.py (Python restatement of gpuschedulerplugin/gpu.go:94-324), 1 thread; "
+                    "the Go original would be faster per call but does the same regex/map/tree work per pair"}
 
 
 def usable_cores() -> int:
@@ -387,6 +422,7 @@ def main():
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
             "no_fit_pods": int((final_keys == np.uint64(_lib.NO_FIT)).sum()),
+            "keys_sha256_12": __import__("hashlib").sha256(final_keys.tobytes()).hexdigest()[:12],
         }
         if variants:
             line["variants"] = variants

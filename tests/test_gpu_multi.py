@@ -37,3 +37,28 @@ def test_multi_device_handle_matches_oracle(oracle_b, G):
         free2[50_000] = 0xFF
         s.update_node(50_000, topo2[50_000], 0xFF)
         assert (s.score_batch(pods) == oracle_b.score_batch(topo2, free2, pods, node_id_base=17, fast=True, nthreads=8)).all()
+
+
+def test_torchrun_bench_keys_equal_single_gpu(tmp_path):
+    """The one-process-per-GPU path of bench.py (torch.distributed NCCL all-gather + K2): the final
+    keys at N=2 must be the very same bits as at N=1 (result independent of G)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if _ndev() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+
+    def line(cmd):
+        out = subprocess.run(cmd, cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        return json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+
+    one = line([sys.executable, "bench.py", "--steps", "2", "--warmup", "3", "--no-cpu-baseline", "--no-variants"])
+    two = line([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                "--master-port", "29533", "bench.py", "--gpus", "2", "--steps", "2", "--warmup", "3"])
+    assert one["n_gpus"] == 1 and two["n_gpus"] == 2
+    assert one["keys_sha256_12"] == two["keys_sha256_12"]
+    assert two["config"]["nodes"] == 100_000 and two["scaling"] == "strong"
