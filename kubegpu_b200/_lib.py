@@ -20,6 +20,7 @@ SYMBOLS = [
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_COMM, ERR_STATE = 0, -1, -2, -3, -4, -5
 NO_FIT = 0xFFFFFFFFFFFFFFFF
 VARIANT_AUTO, VARIANT_WARP_PER_PAIR, VARIANT_LANE_PER_NODE, VARIANT_MEMO_BY_K, VARIANT_TILE_MEMO = 0, 1, 2, 3, 4
+VARIANT_SPARSE = 5
 
 _lib = None
 

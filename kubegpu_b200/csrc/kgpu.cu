@@ -15,6 +15,7 @@
 #include "multi_device.h"
 #include "place_sequential.cuh"
 #include "score_pairs.cuh"
+#include "score_pairs_sparse.cuh"
 
 namespace {
 
@@ -38,6 +39,8 @@ struct kgpu_shard {
     int32_t *d_free = nullptr;       // [n]
     int32_t *d_mem = nullptr;        // [n][8] MiB per GPU (0x7F7F7F7F = unconstrained until uploaded)
     int *d_flag = nullptr;           // "batch has memory-constrained pods"
+    int32_t *d_order = nullptr;      // K1s: slot -> node index, grouped by popcount(free), -1 = padding
+    int64_t n_slots = 0, order_cap = 0;
     int64_t n = 0, cap = 0;
     int64_t node_id_base = 0;
     int32_t *d_pods = nullptr;       // [pcap][4]
@@ -136,6 +139,7 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
     if (s.n == 0) return KGPU_OK;
 
     const bool wpp = h->variant == KGPU_VARIANT_WARP_PER_PAIR;
+    const bool sparse = h->variant == KGPU_VARIANT_SPARSE;
     if (!wpp && has_mem != 0) {   // which pods go to K1m?  (flag read by its blocks; skipped when the host knows there are none)
         KGPU_CUDA(h, cudaMemsetAsync(s.d_flag, 0, sizeof(int), st));
         kgpu::any_mem_pod<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(pods4, P, s.d_flag);
@@ -149,7 +153,7 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
         h->launches += 2;
     }
     const int tile = wpp ? kgpu::WPP_TILE : kgpu::LPN_THREADS;
-    const int64_t tiles = (s.n + tile - 1) / tile;
+    const int64_t tiles = sparse ? s.n_slots / kgpu::SP_THREADS : (s.n + tile - 1) / tile;
     // Pod splits: enough blocks for ~8 waves of resident CTAs, but each block keeps
     // >= 128 pods so staging its node tile stays amortised.
     const int64_t resident = (int64_t)s.sm_count * (wpp ? 8 : KGPU_LPN_MINBLOCKS);
@@ -175,7 +179,16 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
                 topo4, s.d_free, mem4, s.d_flag, s.n, s.node_id_base, pods4, P, (int)per, W, PC, d_keys);
             h->launches++;
         }
-        if (has_mem != 0) {   // K1m: the memory-constrained pods (its blocks exit at once if the flag is 0)
+        if (sparse) {
+            kgpu::score_pairs_sparse<true, false><<<grid, kgpu::SP_THREADS, 0, st>>>(
+                topo4, s.d_free, s.d_mem, s.d_order, s.d_flag, s.node_id_base, pods4, P, (int)per, W, PC, d_keys);
+            h->launches++;
+            if (has_mem != 0) {
+                kgpu::score_pairs_sparse<true, true><<<grid, kgpu::SP_THREADS, 0, st>>>(
+                    topo4, s.d_free, s.d_mem, s.d_order, s.d_flag, s.node_id_base, pods4, P, (int)per, W, PC, d_keys);
+                h->launches++;
+            }
+        } else if (has_mem != 0) {   // K1m: the memory-constrained pods (its blocks exit at once if the flag is 0)
             kgpu::score_pairs_lane_per_node<true, true><<<grid, kgpu::LPN_THREADS, 0, st>>>(
                 topo4, s.d_free, mem4, s.d_flag, s.n, s.node_id_base, pods4, P, (int)per, W, PC, d_keys);
             h->launches++;
@@ -210,6 +223,7 @@ void free_shard(kgpu_shard &s) {
     if (s.d_free) cudaFree(s.d_free);
     if (s.d_mem) cudaFree(s.d_mem);
     if (s.d_flag) cudaFree(s.d_flag);
+    if (s.d_order) cudaFree(s.d_order);
     if (s.d_pods) cudaFree(s.d_pods);
     if (s.d_keys) cudaFree(s.d_keys);
     if (s.d_gather) cudaFree(s.d_gather);
@@ -320,7 +334,7 @@ int kgpu_set_variant(kgpu_t *h, int variant) {
     if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_set_variant: NULL handle");
     std::lock_guard<std::mutex> g(h->mu);
     if (variant == KGPU_VARIANT_AUTO) variant = KGPU_VARIANT_LANE_PER_NODE;
-    if (variant < KGPU_VARIANT_WARP_PER_PAIR || variant > KGPU_VARIANT_TILE_MEMO)
+    if (variant < KGPU_VARIANT_WARP_PER_PAIR || variant > KGPU_VARIANT_SPARSE)
         return fail(h, KGPU_ERR_INVALID, "kgpu_set_variant: unknown variant %d", variant);
     h->variant = variant;
     return KGPU_OK;
@@ -358,6 +372,29 @@ int kgpu_upload_nodes(kgpu_t *h, const int32_t *topo, const int32_t *free_mask, 
         }
         s.n = cnt;
         s.node_id_base = node_id_base + off;
+        // K1s order: nodes grouped by number of free GPUs (8 first), each class in increasing node
+        // index and padded to whole 128-slot tiles, so the lanes of a warp share the bound F and the
+        // slots of a tile are in increasing node id (tie-break order).
+        {
+            std::vector<int32_t> order;
+            order.reserve((size_t)cnt + 9 * 128);
+            for (int f = 8; f >= 0; f--) {
+                for (int64_t i = 0; i < cnt; i++)
+                    if (__builtin_popcount((unsigned)free_mask[off + i] & 0xFFu) == f) order.push_back((int32_t)i);
+                while (order.size() % kgpu::SP_THREADS) order.push_back(-1);
+            }
+            if ((int64_t)order.size() > s.order_cap) {
+                if (s.d_order) cudaFree(s.d_order);
+                s.d_order = nullptr; s.order_cap = 0;
+                KGPU_CUDA(h, cudaMalloc(&s.d_order, std::max<size_t>(1, order.size()) * 4));
+                s.order_cap = (int64_t)order.size();
+            }
+            s.n_slots = (int64_t)order.size();
+            if (!order.empty()) {
+                KGPU_CUDA(h, cudaMemcpyAsync(s.d_order, order.data(), order.size() * 4, cudaMemcpyHostToDevice, s.stream));
+                KGPU_CUDA(h, cudaStreamSynchronize(s.stream));   // `order` is a local
+            }
+        }
         off += cnt;
     }
     for (auto &s : h->shards) {

@@ -1,0 +1,252 @@
+// score_pairs_sparse.cuh -- K1s: the lane-per-node scorer made aware of free-mask sparsity.
+//
+// Only subsets of a node's FREE GPUs can be placements (the CPU twin skips the others with
+// `if (S & ~free) continue`).  K1 (score_pairs.cuh) enumerates all C(8,k) subsets for every pair
+// because the 32 lanes of a warp (32 nodes) run in lockstep whatever their free masks are.  K1s
+// removes that waste without leaving the lane-per-node mapping:
+//   * the host keeps an ORDER of the nodes grouped by f = popcount(free_mask) (kgpu_upload_nodes:
+//     each class in increasing node id, padded to whole 128-slot tiles), so all lanes of a warp
+//     have about the same f;
+//   * every lane permutes its node's GPUs so that the free ones sit at positions 0..f-1 (increasing
+//     GPU index, so subset order is preserved) and gathers its 28 pair costs in that order;
+//   * F = max f over the warp (REDUX.MAX on the CURRENT masks, so a stale order only costs speed,
+//     never correctness) selects generated code that enumerates the C(F,k) subsets of positions
+//     0..F-1 only (subset_dp_sparse_gen.cuh); F < k: the warp has nothing to do for those pods.
+// Per pair the enumeration is still done in full for the candidate subsets, with the same
+// per-pod multiplier device as K1 (see score_pairs.cuh); results are bit-identical.
+#pragma once
+#include "score_pairs.cuh"
+#include "subset_dp_sparse_gen.cuh"
+
+namespace kgpu {
+
+constexpr int SP_THREADS = 128;
+constexpr int SP_WARPS = SP_THREADS / 32;
+constexpr int SP_CHUNK = 512;
+constexpr int SP_ROW = 29;          // padded row of 28 pair costs per lane in shared memory
+#ifndef KGPU_SP_MINBLOCKS
+#define KGPU_SP_MINBLOCKS 6
+#endif
+
+__host__ __device__ constexpr int sp_pidx(int i, int j) { return 7 * i - i * (i - 1) / 2 + (j - i - 1); }  // i<j
+
+template <int K, int F>
+__device__ __forceinline__ uint32_t node_key_kf(const PairCosts &C, const PipeConsts pc, uint32_t nfree, bool valid) {
+    if (K == 0) return valid ? 0u : INF32;
+    if (K == 1) return nfree ? pc.one : INF32;          // free GPUs are compacted: the lowest one is position 0
+    return best_kf<(K < 2 ? 2 : K), (F < 2 ? 2 : F)>(C, pc);
+}
+
+// One (K, F) loop: all pods of the chunk that want K GPUs, enumerating positions 0..F-1.
+template <int K, int F, bool PER_PAIR, bool MEM>
+__device__ __forceinline__ void sp_bucket(const PairCosts &C, const PipeConsts pc, uint32_t nfree, bool valid,
+                                          const int32_t (&mem)[8], uint32_t lane_field, const uint16_t *sIdx,
+                                          const uint8_t *sK, const int32_t *sMin, int begin, int end, uint32_t *sBestW) {
+#pragma unroll 1
+    for (int i = begin; i < end; i++) {
+        const int p = sIdx[i];
+        PipeConsts pcl = pc;
+        if (PER_PAIR && !MEM) {                    // un-hoistable per-pair work: see score_pairs.cuh
+            pcl.one = (uint32_t)sK[p] - (uint32_t)(K - 1);
+            pcl.minus_one = 0u - pcl.one;
+        }
+        uint32_t key;
+        if (MEM) {
+            const int32_t need = sMin[p];
+            uint32_t pen[8], elig = 0;
+#pragma unroll
+            for (int g = 0; g < 8; g++) {
+                const bool lt = mem[g] < need;
+                pen[g] = lt ? PEN : 0u;
+                if (!lt && (uint32_t)g < nfree) elig |= 1u << g;      // position g: free and big enough
+            }
+            if (K == 0) key = valid ? 0u : INF32;
+            else if (K == 1) key = elig ? (elig & (0u - elig)) : INF32;
+            else {
+                PairCosts C2;
+                apply_pens(C, C2, pen);
+                key = best_kf<(K < 2 ? 2 : K), (F < 2 ? 2 : F)>(C2, pcl);
+            }
+        } else {
+            key = node_key_kf<K, F>(C, pcl, nfree, valid);
+        }
+        const uint32_t v = key >= PEN ? INF32 : (((key & ~0xFFu) << 5) | lane_field | (key & 0xFFu));
+        const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, v);
+        if (lane_field == 0) sBestW[p] = m;
+    }
+}
+
+template <int K, bool PER_PAIR, bool MEM>
+__device__ __forceinline__ void sp_run_k(int F, const PairCosts &C, const PipeConsts pc, uint32_t nfree, bool valid,
+                                         const int32_t (&mem)[8], uint32_t lane_field, const uint16_t *sIdx,
+                                         const uint8_t *sK, const int32_t *sMin, int begin, int end, uint32_t *sBestW) {
+    if (begin >= end || F < K) return;             // F < K: no lane of this warp has K free GPUs
+#define KGPU_SP_CASE(FF)                                                                                         \
+    case FF:                                                                                                     \
+        if (FF >= K) sp_bucket<K, (FF >= K ? FF : K), PER_PAIR, MEM>(C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, begin, end, sBestW); \
+        break;
+    if (K <= 1) {                                  // F does not matter for k = 0, 1
+        sp_bucket<K, 8, PER_PAIR, MEM>(C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, begin, end, sBestW);
+        return;
+    }
+    switch (F) {
+        KGPU_SP_CASE(2) KGPU_SP_CASE(3) KGPU_SP_CASE(4) KGPU_SP_CASE(5) KGPU_SP_CASE(6) KGPU_SP_CASE(7) KGPU_SP_CASE(8)
+        default: break;
+    }
+#undef KGPU_SP_CASE
+}
+
+// grid = (slot tiles of 128, pod splits); block = 128 threads.  order[slot] = node index or -1 (padding).
+template <bool PER_PAIR, bool MEM>
+__global__ void __launch_bounds__(SP_THREADS, MEM ? 4 : KGPU_SP_MINBLOCKS)
+score_pairs_sparse(const int4 *__restrict__ topo4, const int32_t *__restrict__ free_mask,
+                   const int32_t *__restrict__ gpu_mem, const int32_t *__restrict__ order,
+                   const int *__restrict__ mem_flag, int64_t node_id_base, const int4 *__restrict__ pods4, int64_t P,
+                   int pods_per_split, Weights W, PipeConsts pc, unsigned long long *__restrict__ keys) {
+    if (MEM && *mem_flag == 0) return;
+    __shared__ int32_t sW[16];
+    __shared__ int32_t sCnt[10], sOff[11];
+    __shared__ uint8_t sK[SP_CHUNK];
+    __shared__ uint16_t sIdx[SP_CHUNK];
+    __shared__ uint32_t sBest[SP_WARPS][SP_CHUNK];
+    __shared__ int32_t sMin[MEM ? SP_CHUNK : 1];
+    __shared__ uint32_t sRow[SP_THREADS * SP_ROW];     // staging: each lane's 28 scaled pair costs (then its 8 memories)
+    __shared__ uint32_t sPerm[SP_THREADS];             // position -> GPU index, 8 nibbles
+    __shared__ int32_t sNode[SP_THREADS];              // slot -> node index (-1 = padding)
+
+    const int tid = threadIdx.x;
+    uint32_t *const sBestW = sBest[tid >> 5];
+    const uint32_t lane_field = (uint32_t)(tid & 31) << 8;
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) sW[i] = W.w[i];
+    }
+    __syncthreads();
+
+    // ---- staging -------------------------------------------------------------------------
+    const int64_t slot = (int64_t)blockIdx.x * SP_THREADS + tid;
+    const int32_t node = __ldg(order + slot);
+    const bool valid = node >= 0;
+    sNode[tid] = node;
+    const uint32_t free = valid ? ((uint32_t)__ldg(free_mask + node) & 0xFFu) : 0u;
+    uint32_t *row = sRow + tid * SP_ROW;
+    {   // the node's 28 scaled pair costs in natural GPU order -> this lane's shared-memory row
+        int4 q[16];
+#pragma unroll
+        for (int t = 0; t < 16; t++) q[t] = make_int4(0, 0, 0, 0);
+        if (valid) {
+            const int4 *src = topo4 + (int64_t)node * 16;
+            q[0] = __ldg(src + 0);  q[1] = __ldg(src + 1);
+            q[2] = __ldg(src + 2);  q[3] = __ldg(src + 3);
+            q[4] = __ldg(src + 4);  q[5] = __ldg(src + 5);
+            q[7] = __ldg(src + 7);  q[9] = __ldg(src + 9);
+            q[11] = __ldg(src + 11); q[13] = __ldg(src + 13);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = i + 1; j < 8; j++) {
+                const int4 v = q[i * 2 + (j >> 2)];
+                const int lvl = (j & 3) == 0 ? v.x : (j & 3) == 1 ? v.y : (j & 3) == 2 ? v.z : v.w;
+                row[sp_pidx(i, j)] = (uint32_t)sW[lvl & 15] << 8;
+            }
+    }
+    // permutation: free GPUs first (ascending), then the others (ascending)
+    const uint32_t nfree = (uint32_t)__popc(free);
+    uint32_t perm = 0;
+    {
+        int pos = 0;
+#pragma unroll
+        for (int g = 0; g < 8; g++)
+            if ((free >> g) & 1u) { perm |= (uint32_t)g << (4 * pos); pos++; }
+#pragma unroll
+        for (int g = 0; g < 8; g++)
+            if (!((free >> g) & 1u)) { perm |= (uint32_t)g << (4 * pos); pos++; }
+    }
+    sPerm[tid] = perm;
+    // gather the pair costs in compacted order; a pair touching a position >= f is not placeable
+    PairCosts C;
+    for_each_pair(C, [&](int i, int j) -> uint32_t {          // i < j are POSITIONS here
+        const int a = (int)((perm >> (4 * i)) & 7u), b = (int)((perm >> (4 * j)) & 7u);
+        const int lo = min(a, b), hi = max(a, b);
+        uint32_t cst = row[7 * lo - ((lo * (lo - 1)) >> 1) + (hi - lo - 1)];
+        if ((uint32_t)j >= nfree) cst += PEN;
+        return valid ? cst : PEN;
+    });
+    int32_t mem[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (MEM) {
+        __syncwarp();
+        if (valid) {
+#pragma unroll
+            for (int g = 0; g < 8; g++) row[g] = (uint32_t)__ldg(gpu_mem + (int64_t)node * 8 + g);
+#pragma unroll
+            for (int g = 0; g < 8; g++) mem[g] = (int32_t)row[(perm >> (4 * g)) & 7u];
+        }
+    }
+    const int F = (int)__reduce_max_sync(0xFFFFFFFFu, nfree);    // warp-uniform bound on usable positions
+
+    const int64_t p_begin = (int64_t)blockIdx.y * pods_per_split;
+    const int64_t p_end = min(P, p_begin + pods_per_split);
+
+    for (int64_t c0 = p_begin; c0 < p_end; c0 += SP_CHUNK) {
+        const int cn = (int)min((int64_t)SP_CHUNK, p_end - c0);
+        __syncthreads();
+        if (tid < 10) sCnt[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < cn; i += SP_THREADS) {
+            const int4 req = __ldg(pods4 + c0 + i);
+            const bool wants_mem = req.w > 0;
+            const int b = (req.x < 0 || req.x > 8 || wants_mem != MEM) ? 9 : req.x;
+            sK[i] = (uint8_t)b;
+            if (MEM) sMin[i] = req.w;
+            atomicAdd(&sCnt[b], 1);
+#pragma unroll
+            for (int w = 0; w < SP_WARPS; w++) sBest[w][i] = INF32;      // warps skip the pods they cannot serve
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int acc = 0;
+#pragma unroll
+            for (int b = 0; b < 10; b++) { sOff[b] = acc; acc += sCnt[b]; sCnt[b] = sOff[b]; }
+            sOff[10] = acc;
+        }
+        __syncthreads();
+        for (int i = tid; i < cn; i += SP_THREADS) sIdx[atomicAdd(&sCnt[sK[i]], 1)] = (uint16_t)i;
+        __syncthreads();
+
+        sp_run_k<0, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[0], sOff[1], sBestW);
+        sp_run_k<1, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[1], sOff[2], sBestW);
+        sp_run_k<2, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[2], sOff[3], sBestW);
+        sp_run_k<3, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[3], sOff[4], sBestW);
+        sp_run_k<4, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[4], sOff[5], sBestW);
+        sp_run_k<5, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[5], sOff[6], sBestW);
+        sp_run_k<6, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[6], sOff[7], sBestW);
+        sp_run_k<7, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[7], sOff[8], sBestW);
+        sp_run_k<8, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[8], sOff[9], sBestW);
+        __syncthreads();
+
+        // block result per pod: min over the 4 warps of (cost, slot_in_tile, S'); slots are in increasing
+        // node id inside a tile, so this is (cost, node, mask) order.  S' -> real GPU mask via the winner's perm.
+        for (int i = tid; i < cn; i += SP_THREADS) {
+            if (sK[i] == 9) continue;
+            uint32_t b = INF32;
+#pragma unroll
+            for (int w = 0; w < SP_WARPS; w++) {
+                const uint32_t m = sBest[w][i];
+                if (m != INF32) b = min(b, ((m & ~0x1FFFu) << 2) | ((uint32_t)w << 13) | (m & 0x1FFFu));
+            }
+            if (b != INF32) {
+                const int s = (int)((b >> 8) & 127u);
+                const uint32_t pm = sPerm[s];
+                uint32_t S = 0;
+#pragma unroll
+                for (int g = 0; g < 8; g++)
+                    if ((b >> g) & 1u) S |= 1u << ((pm >> (4 * g)) & 7u);
+                const unsigned long long nid = (unsigned long long)(node_id_base + sNode[s]);
+                atomicMin(&keys[c0 + i], ((unsigned long long)(b >> 15) << 40) | (nid << 8) | S);
+            }
+        }
+    }
+}
+
+}  // namespace kgpu

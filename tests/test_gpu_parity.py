@@ -10,7 +10,8 @@ from kubegpu_b200 import _lib, synth
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [_lib.VARIANT_LANE_PER_NODE, _lib.VARIANT_WARP_PER_PAIR, _lib.VARIANT_MEMO_BY_K, _lib.VARIANT_TILE_MEMO]
+VARIANTS = [_lib.VARIANT_LANE_PER_NODE, _lib.VARIANT_WARP_PER_PAIR, _lib.VARIANT_MEMO_BY_K, _lib.VARIANT_TILE_MEMO,
+            _lib.VARIANT_SPARSE]
 
 
 @pytest.fixture(scope="module")
@@ -146,7 +147,7 @@ def test_heterogeneous_256k_bit_exact(scorer, oracle_b):
     """BASELINE config 4: 256k heterogeneous nodes, every key compared with Oracle B."""
     topo, free, pods = synth.gen_c4(N=262_144, P=64)
     want = oracle_b.score_batch(topo, free, pods, fast=True, nthreads=8)
-    for v in VARIANTS[:2]:
+    for v in (VARIANTS[0], VARIANTS[1], VARIANTS[4]):
         assert (_score(scorer, v, topo, free, pods) == want).all()
 
 
