@@ -72,9 +72,9 @@ extern "C" {
 #define KGPU_MAX_WEIGHT 4095
 
 /* Kernel variants of K1 `score_pairs` (all bit-identical in result). */
-#define KGPU_VARIANT_AUTO 0          /* = LANE_PER_NODE                                      */
+#define KGPU_VARIANT_AUTO 0          /* = SPARSE                                             */
 #define KGPU_VARIANT_WARP_PER_PAIR 1 /* north_star mapping: warp per (pod,node), lane per subset */
-#define KGPU_VARIANT_LANE_PER_NODE 2 /* lane per node, pair costs in registers, full per-pair enumeration */
+#define KGPU_VARIANT_LANE_PER_NODE 2 /* lane per node, pair costs in registers, all C(8,k) subsets per pair */
 #define KGPU_VARIANT_MEMO_BY_K 3     /* global best[k] computed once, pods look it up (NOT the headline) */
 #define KGPU_VARIANT_SPARSE 5        /* lane per node, nodes ordered by free-GPU count, enumeration over free positions only */
 #define KGPU_VARIANT_TILE_MEMO 4     /* lane per node, per-k minima hoisted out of the pod loop (NOT the headline) */

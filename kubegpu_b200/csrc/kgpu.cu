@@ -58,7 +58,7 @@ struct kgpu_ctx {
     std::string err;
     std::vector<kgpu_shard> shards;
     int32_t W[16];
-    int variant = KGPU_VARIANT_LANE_PER_NODE;
+    int variant = KGPU_VARIANT_SPARSE;
     int64_t n_total = 0;
     int64_t launches = 0;
     double last_kernel_ms = 0.0;
@@ -333,7 +333,7 @@ int kgpu_get_weights(kgpu_t *h, int32_t w[KGPU_NUM_LEVELS]) {
 int kgpu_set_variant(kgpu_t *h, int variant) {
     if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_set_variant: NULL handle");
     std::lock_guard<std::mutex> g(h->mu);
-    if (variant == KGPU_VARIANT_AUTO) variant = KGPU_VARIANT_LANE_PER_NODE;
+    if (variant == KGPU_VARIANT_AUTO) variant = KGPU_VARIANT_SPARSE;
     if (variant < KGPU_VARIANT_WARP_PER_PAIR || variant > KGPU_VARIANT_SPARSE)
         return fail(h, KGPU_ERR_INVALID, "kgpu_set_variant: unknown variant %d", variant);
     h->variant = variant;

@@ -79,8 +79,10 @@ def test_edge_cases(scorer, oracle_b, variant):
     assert (got == want).all() and int(got[8]) >> 40 == 28 * 4095
 
 
-def test_update_and_remove_node(scorer, oracle_b):
-    scorer.set_variant(_lib.VARIANT_LANE_PER_NODE)
+@pytest.mark.parametrize("variant", [_lib.VARIANT_SPARSE, _lib.VARIANT_LANE_PER_NODE])
+def test_update_and_remove_node(scorer, oracle_b, variant):
+    """Also the stale-order case of K1s: masks change after upload, the order does not."""
+    scorer.set_variant(variant)
     topo, free, pods = synth.gen_c2(N=2000, P=64)
     topo, free = topo.copy(), free.copy()
     scorer.upload_nodes(topo, free)
@@ -153,7 +155,7 @@ def test_heterogeneous_256k_bit_exact(scorer, oracle_b):
 
 def test_device_buffer_entry_point_and_k2(scorer, oracle_b):
     import torch
-    scorer.set_variant(_lib.VARIANT_LANE_PER_NODE)
+    scorer.set_variant(_lib.VARIANT_SPARSE)
     topo, free, pods = synth.gen_c3(N=5000, P=333)
     G, per = 4, 1250
     d_pods = torch.from_numpy(pods).cuda()
@@ -177,7 +179,7 @@ def test_one_million_nodes_c3_scale(scorer, oracle_b):
     scored one after the other + K2) with the unsharded launch."""
     import torch
     topo, free, pods = synth.gen_c3(N=1_000_000, P=2048)
-    scorer.set_variant(_lib.VARIANT_LANE_PER_NODE)
+    scorer.set_variant(_lib.VARIANT_SPARSE)
     scorer.upload_nodes(topo, free)
     keys = scorer.score_batch(pods)
     sample = np.arange(0, 2048, 128)
@@ -206,7 +208,7 @@ def test_ten_million_nodes_sweep_point(scorer, oracle_b):
     # make the very last node the unique best home for k=8 so the answer must come from the far end
     topo[N - 1] = 9
     free[N - 1] = 0xFF
-    scorer.set_variant(_lib.VARIANT_LANE_PER_NODE)
+    scorer.set_variant(_lib.VARIANT_SPARSE)
     scorer.upload_nodes(topo, free)
     keys = scorer.score_batch(pods)
     sample = np.array([0, 1, 2, 3, 17, 40, 63])
