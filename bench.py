@@ -296,7 +296,7 @@ def main():
 
     def step_device():
         """pods already in HBM -> final keys in HBM (all ranks hold the answer)."""
-        scorer.score_batch_device(d_pods.data_ptr(), N_PODS, d_local.data_ptr(), sptr)
+        scorer.score_batch_device(d_pods.data_ptr(), N_PODS, d_local.data_ptr(), sptr, _lib.BATCH_NO_MIN_MEM)
         if world > 1:
             dist.all_gather_into_tensor(d_gather.view(-1), d_local)
             scorer.reduce_shards_device(d_gather.data_ptr(), world, N_PODS, d_final.data_ptr(), sptr)
@@ -332,7 +332,7 @@ def main():
         if world > 1:
             dist.all_reduce(sync_token)                # device-side rendezvous so no rank times another's flush
         ev[i][0].record(stream)
-        scorer.score_batch_device(d_pods.data_ptr(), N_PODS, d_local.data_ptr(), sptr)
+        scorer.score_batch_device(d_pods.data_ptr(), N_PODS, d_local.data_ptr(), sptr, _lib.BATCH_NO_MIN_MEM)
         ev[i][1].record(stream)                        # K1 only: roofline numerator
         if world > 1:
             dist.all_gather_into_tensor(d_gather.view(-1), d_local)

@@ -132,6 +132,13 @@ int kgpu_score_batch(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_ke
 int kgpu_score_batch_device(kgpu_t *h, const int32_t *d_pods, int64_t P, uint64_t *d_keys,
                             void *stream);
 
+/* Same, with promises about the batch the device-buffer path cannot check for itself:
+ * KGPU_BATCH_NO_MIN_MEM = no pod of this batch has min_mem_mib > 0 (skips the flag kernel and the
+ * K1m launch whose blocks would only read the flag and exit). */
+#define KGPU_BATCH_NO_MIN_MEM 1
+int kgpu_score_batch_device_ex(kgpu_t *h, const int32_t *d_pods, int64_t P, uint64_t *d_keys, void *stream,
+                               int batch_flags);
+
 /* Per-pair query (one PodFitsDevice(node, pod) call, or a list of them): for each i,
  * out_node_keys[i] = (cost << 8) | gpu_mask of the cheapest k[i]-subset of the free GPUs
  * of node node_idx[i] (local index as uploaded), or UINT32_MAX if it does not fit.

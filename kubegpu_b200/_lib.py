@@ -13,7 +13,7 @@ SYMBOLS = [
     "kgpu_version", "kgpu_create", "kgpu_destroy", "kgpu_last_error", "kgpu_set_weights",
     "kgpu_get_weights", "kgpu_set_variant", "kgpu_upload_nodes", "kgpu_update_node",
     "kgpu_set_free_mask", "kgpu_remove_node", "kgpu_upload_gpu_memory", "kgpu_update_gpu_memory", "kgpu_num_nodes", "kgpu_score_batch",
-    "kgpu_score_batch_device", "kgpu_score_pairs", "kgpu_place_batch", "kgpu_get_free_masks", "kgpu_reduce_shards_device", "kgpu_kernel_launches",
+    "kgpu_score_batch_device", "kgpu_score_batch_device_ex", "kgpu_score_pairs", "kgpu_place_batch", "kgpu_get_free_masks", "kgpu_reduce_shards_device", "kgpu_kernel_launches",
     "kgpu_last_kernel_ms",
 ]
 
@@ -21,6 +21,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_COMM, ERR_STATE = 0, -1, -2, -3, -4, -
 NO_FIT = 0xFFFFFFFFFFFFFFFF
 VARIANT_AUTO, VARIANT_WARP_PER_PAIR, VARIANT_LANE_PER_NODE, VARIANT_MEMO_BY_K, VARIANT_TILE_MEMO = 0, 1, 2, 3, 4
 VARIANT_SPARSE = 5
+BATCH_NO_MIN_MEM = 1
 
 _lib = None
 
@@ -69,6 +70,8 @@ def load() -> ctypes.CDLL:
     L.kgpu_score_batch.argtypes = [vp, vp, i64, vp]          # raw addresses: numpy or pinned torch memory
     L.kgpu_score_batch_device.restype = ci
     L.kgpu_score_batch_device.argtypes = [vp, vp, i64, vp, vp]
+    L.kgpu_score_batch_device_ex.restype = ci
+    L.kgpu_score_batch_device_ex.argtypes = [vp, vp, i64, vp, vp, ci]
     L.kgpu_score_pairs.restype = ci
     L.kgpu_score_pairs.argtypes = [vp, ctypes.POINTER(i64), i32p, i64, ctypes.POINTER(ctypes.c_uint32)]
     L.kgpu_place_batch.restype = ci

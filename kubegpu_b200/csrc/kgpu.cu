@@ -636,6 +636,16 @@ int kgpu_score_batch_device(kgpu_t *h, const int32_t *d_pods, int64_t P, uint64_
     return launch_score(h, s, d_pods, P, reinterpret_cast<unsigned long long *>(d_keys), (cudaStream_t)stream, -1);
 }
 
+int kgpu_score_batch_device_ex(kgpu_t *h, const int32_t *d_pods, int64_t P, uint64_t *d_keys, void *stream, int batch_flags) {
+    if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_score_batch_device_ex: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (h->shards.size() != 1) return fail(h, KGPU_ERR_STATE, "kgpu_score_batch_device_ex: needs a single-device handle");
+    if (P < 0 || (P > 0 && (!d_pods || !d_keys))) return fail(h, KGPU_ERR_INVALID, "kgpu_score_batch_device_ex: bad arguments");
+    kgpu_shard &s = h->shards[0];
+    return launch_score(h, s, d_pods, P, reinterpret_cast<unsigned long long *>(d_keys), (cudaStream_t)stream,
+                        (batch_flags & KGPU_BATCH_NO_MIN_MEM) ? 0 : -1);
+}
+
 int kgpu_reduce_shards_device(kgpu_t *h, const uint64_t *d_gathered, int G, int64_t P, uint64_t *d_out, void *stream) {
     if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_reduce_shards_device: NULL handle");
     std::lock_guard<std::mutex> g(h->mu);

@@ -152,9 +152,13 @@ class Scorer:
         """Same call on raw host addresses (e.g. pinned torch tensors' data_ptr())."""
         self._check(self._L.kgpu_score_batch(self._h, pods_addr, int(P), out_addr))
 
-    def score_batch_device(self, d_pods_addr: int, P: int, d_keys_addr: int, stream: int = 0) -> None:
-        """Device buffers, enqueued on `stream` (cudaStream_t as int, 0 = the CUDA default stream)."""
-        self._check(self._L.kgpu_score_batch_device(self._h, d_pods_addr, int(P), d_keys_addr, stream or None))
+    def score_batch_device(self, d_pods_addr: int, P: int, d_keys_addr: int, stream: int = 0, batch_flags: int = 0) -> None:
+        """Device buffers, enqueued on `stream` (cudaStream_t as int, 0 = the CUDA default stream).
+        batch_flags: _lib.BATCH_NO_MIN_MEM promises that no pod carries min_mem_mib > 0."""
+        if batch_flags:
+            self._check(self._L.kgpu_score_batch_device_ex(self._h, d_pods_addr, int(P), d_keys_addr, stream or None, int(batch_flags)))
+        else:
+            self._check(self._L.kgpu_score_batch_device(self._h, d_pods_addr, int(P), d_keys_addr, stream or None))
 
     def reduce_shards_device(self, d_gathered_addr: int, G: int, P: int, d_out_addr: int, stream: int = 0) -> None:
         self._check(self._L.kgpu_reduce_shards_device(self._h, d_gathered_addr, int(G), int(P), d_out_addr,

@@ -35,7 +35,7 @@ d_gather = torch.empty((world, a.pods), dtype=torch.int64, device=dev)
 d_final = torch.empty(a.pods, dtype=torch.int64, device=dev)
 
 def step():
-    s.score_batch_device(d_pods.data_ptr(), a.pods, d_local.data_ptr(), st.cuda_stream)
+    s.score_batch_device(d_pods.data_ptr(), a.pods, d_local.data_ptr(), st.cuda_stream, _lib.BATCH_NO_MIN_MEM)
     if world > 1:
         dist.all_gather_into_tensor(d_gather.view(-1), d_local)
         s.reduce_shards_device(d_gather.data_ptr(), world, a.pods, d_final.data_ptr(), st.cuda_stream)

@@ -78,6 +78,11 @@ def test_gpu_memory_aware_parity(oracle_b, variant):
         s.score_batch_device(d_pods.data_ptr(), len(pods), d_keys.data_ptr(), torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         assert (d_keys.cpu().numpy().view(np.uint64) == oracle_b.score_batch(topo, free, nomem, node_id_base=5, fast=True, nthreads=8)).all()
+        d_keys.zero_()                     # and with the caller's promise that no pod has min_mem
+        s.score_batch_device(d_pods.data_ptr(), len(pods), d_keys.data_ptr(), torch.cuda.current_stream().cuda_stream,
+                             _lib.BATCH_NO_MIN_MEM)
+        torch.cuda.synchronize()
+        assert (d_keys.cpu().numpy().view(np.uint64) == oracle_b.score_batch(topo, free, nomem, node_id_base=5, fast=True, nthreads=8)).all()
         # one node's memory changes
         mem2 = mem.copy()
         mem2[12_345] = 184_320
