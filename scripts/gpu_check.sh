@@ -15,7 +15,7 @@ if [ "${1:-}" != "quick" ]; then
       python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
   grep -c score_pairs gpurun_out/launches.csv
   echo "== ncu full (K1)"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:score_pairs_lane -s 3 -c 2 -f -o gpurun_out/k1_full \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:score_pairs_sparse -s 3 -c 2 -f -o gpurun_out/k1_full \
       python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-variants > gpurun_out/ncu_full.log 2>&1
   ls -la gpurun_out
 fi

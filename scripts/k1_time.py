@@ -6,7 +6,7 @@ import argparse, hashlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
-from kubegpu_b200 import synth
+from kubegpu_b200 import _lib, synth
 from kubegpu_b200.scorer import Scorer
 
 ap = argparse.ArgumentParser()
@@ -35,14 +35,14 @@ ref = None
 for v in [int(x) for x in a.variants.split(",")]:
     s.set_variant(v)
     for _ in range(3):
-        s.score_batch_device(d_pods.data_ptr(), a.pods, d_keys.data_ptr(), st.cuda_stream)
+        s.score_batch_device(d_pods.data_ptr(), a.pods, d_keys.data_ptr(), st.cuda_stream, 0 if mem is not None else _lib.BATCH_NO_MIN_MEM)
     torch.cuda.synchronize()
     ms = []
     for _ in range(a.reps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(st)
-        s.score_batch_device(d_pods.data_ptr(), a.pods, d_keys.data_ptr(), st.cuda_stream)
+        s.score_batch_device(d_pods.data_ptr(), a.pods, d_keys.data_ptr(), st.cuda_stream, 0 if mem is not None else _lib.BATCH_NO_MIN_MEM)
         e1.record(st)
         torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
