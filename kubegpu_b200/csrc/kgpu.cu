@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -157,7 +158,8 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
     // Pod splits: enough blocks for ~8 waves of resident CTAs, but each block keeps
     // >= 128 pods so staging its node tile stays amortised.
     const int64_t resident = (int64_t)s.sm_count * (wpp ? 8 : KGPU_LPN_MINBLOCKS);
-    int64_t splits = std::max<int64_t>(1, (8 * resident + tiles - 1) / tiles);
+    static const int64_t waves = [] { const char *e = getenv("KGPU_WAVES"); int v = e ? atoi(e) : 0; return (int64_t)(v > 0 ? v : 8); }();
+    int64_t splits = std::max<int64_t>(1, (waves * resident + tiles - 1) / tiles);
     splits = std::min<int64_t>(splits, std::max<int64_t>(1, P / 128));
     splits = std::min<int64_t>(splits, 65535);
     int64_t per = (P + splits - 1) / splits;
@@ -373,16 +375,17 @@ int kgpu_upload_nodes(kgpu_t *h, const int32_t *topo, const int32_t *free_mask, 
         s.n = cnt;
         s.node_id_base = node_id_base + off;
         // K1s order: nodes grouped by number of free GPUs (8 first), each class in increasing node
-        // index and padded to whole 128-slot tiles, so the lanes of a warp share the bound F and the
-        // slots of a tile are in increasing node id (tie-break order).
+        // index and padded to whole warps (32 slots), so the lanes of a warp share the bound F and are
+        // in increasing node id (tie-break order inside a warp; across warps the flush compares ids).
         {
             std::vector<int32_t> order;
             order.reserve((size_t)cnt + 9 * 128);
             for (int f = 8; f >= 0; f--) {
                 for (int64_t i = 0; i < cnt; i++)
                     if (__builtin_popcount((unsigned)free_mask[off + i] & 0xFFu) == f) order.push_back((int32_t)i);
-                while (order.size() % kgpu::SP_THREADS) order.push_back(-1);
+                while (order.size() % 32) order.push_back(-1);
             }
+            while (order.size() % kgpu::SP_THREADS) order.push_back(-1);
             if ((int64_t)order.size() > s.order_cap) {
                 if (s.d_order) cudaFree(s.d_order);
                 s.d_order = nullptr; s.order_cap = 0;

@@ -5,8 +5,8 @@
 // because the 32 lanes of a warp (32 nodes) run in lockstep whatever their free masks are.  K1s
 // removes that waste without leaving the lane-per-node mapping:
 //   * the host keeps an ORDER of the nodes grouped by f = popcount(free_mask) (kgpu_upload_nodes:
-//     each class in increasing node id, padded to whole 128-slot tiles), so all lanes of a warp
-//     have about the same f;
+//     each class in increasing node id, padded to whole warps), so all lanes of a warp have the
+//     same f;
 //   * every lane permutes its node's GPUs so that the free ones sit at positions 0..f-1 (increasing
 //     GPU index, so subset order is preserved) and gathers its 28 pair costs in that order;
 //   * F = max f over the warp (REDUX.MAX on the CURRENT masks, so a stale order only costs speed,
@@ -225,25 +225,30 @@ score_pairs_sparse(const int4 *__restrict__ topo4, const int32_t *__restrict__ f
         sp_run_k<8, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[8], sOff[9], sBestW);
         __syncthreads();
 
-        // block result per pod: min over the 4 warps of (cost, slot_in_tile, S'); slots are in increasing
-        // node id inside a tile, so this is (cost, node, mask) order.  S' -> real GPU mask via the winner's perm.
+        // block result per pod: min over the 4 warps of (cost, node id) -- a tile may hold warps of two
+        // adjacent classes, so node ids are compared explicitly -- then S' -> real GPU mask through the
+        // winner's permutation, and REDG.MIN.64 into keys[pod].
         for (int i = tid; i < cn; i += SP_THREADS) {
             if (sK[i] == 9) continue;
-            uint32_t b = INF32;
+            unsigned long long best = ~0ull;       // cost<<40 | node_index<<8 | slot_in_tile... (slot kept aside)
+            int best_slot = -1;
+            uint32_t best_m = 0;
 #pragma unroll
             for (int w = 0; w < SP_WARPS; w++) {
                 const uint32_t m = sBest[w][i];
-                if (m != INF32) b = min(b, ((m & ~0x1FFFu) << 2) | ((uint32_t)w << 13) | (m & 0x1FFFu));
+                if (m == INF32) continue;
+                const int s = w * 32 + (int)((m >> 8) & 31u);
+                const unsigned long long cand = ((unsigned long long)(m >> 13) << 32) | (uint32_t)sNode[s];
+                if (cand < best) { best = cand; best_slot = s; best_m = m; }
             }
-            if (b != INF32) {
-                const int s = (int)((b >> 8) & 127u);
-                const uint32_t pm = sPerm[s];
+            if (best_slot >= 0) {
+                const uint32_t pm = sPerm[best_slot];
                 uint32_t S = 0;
 #pragma unroll
                 for (int g = 0; g < 8; g++)
-                    if ((b >> g) & 1u) S |= 1u << ((pm >> (4 * g)) & 7u);
-                const unsigned long long nid = (unsigned long long)(node_id_base + sNode[s]);
-                atomicMin(&keys[c0 + i], ((unsigned long long)(b >> 15) << 40) | (nid << 8) | S);
+                    if ((best_m >> g) & 1u) S |= 1u << ((pm >> (4 * g)) & 7u);
+                const unsigned long long nid = (unsigned long long)(node_id_base + (long long)(best & 0xFFFFFFFFull));
+                atomicMin(&keys[c0 + i], ((best >> 32) << 40) | (nid << 8) | S);
             }
         }
     }
