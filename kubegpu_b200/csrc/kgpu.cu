@@ -40,6 +40,9 @@ struct kgpu_shard {
     int32_t *d_free = nullptr;       // [n]
     int32_t *d_mem = nullptr;        // [n][8] MiB per GPU (0x7F7F7F7F = unconstrained until uploaded)
     int *d_flag = nullptr;           // "batch has memory-constrained pods"
+    uint32_t *d_cpair = nullptr;     // K1s: [n][28] compacted scaled pair costs (see compact_nodes)
+    uint32_t *d_perm = nullptr;      // K1s: [n] position -> GPU index
+    bool compact_dirty = true;       // topology / free masks / weights changed since the cache was built
     int32_t *d_order = nullptr;      // K1s: slot -> node index, grouped by popcount(free), -1 = padding
     int64_t n_slots = 0, order_cap = 0;
     int64_t n = 0, cap = 0;
@@ -182,12 +185,19 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
             h->launches++;
         }
         if (sparse) {
+            if (s.compact_dirty) {   // rebuild the compacted pair-cost cache (topology / masks / weights changed)
+                kgpu::compact_nodes<<<(unsigned)((s.n + kgpu::SP_THREADS - 1) / kgpu::SP_THREADS), kgpu::SP_THREADS, 0, st>>>(
+                    topo4, s.d_free, s.n, W, s.d_cpair, s.d_perm);
+                h->launches++;
+                s.compact_dirty = false;
+            }
+            const int4 *cpair4 = reinterpret_cast<const int4 *>(s.d_cpair);
             kgpu::score_pairs_sparse<true, false><<<grid, kgpu::SP_THREADS, 0, st>>>(
-                topo4, s.d_free, s.d_mem, s.d_order, s.d_flag, s.node_id_base, pods4, P, (int)per, W, PC, d_keys);
+                cpair4, s.d_perm, s.d_free, s.d_mem, s.d_order, s.d_flag, s.node_id_base, pods4, P, (int)per, PC, d_keys);
             h->launches++;
             if (has_mem != 0) {
                 kgpu::score_pairs_sparse<true, true><<<grid, kgpu::SP_THREADS, 0, st>>>(
-                    topo4, s.d_free, s.d_mem, s.d_order, s.d_flag, s.node_id_base, pods4, P, (int)per, W, PC, d_keys);
+                    cpair4, s.d_perm, s.d_free, s.d_mem, s.d_order, s.d_flag, s.node_id_base, pods4, P, (int)per, PC, d_keys);
                 h->launches++;
             }
         } else if (has_mem != 0) {   // K1m: the memory-constrained pods (its blocks exit at once if the flag is 0)
@@ -226,6 +236,8 @@ void free_shard(kgpu_shard &s) {
     if (s.d_mem) cudaFree(s.d_mem);
     if (s.d_flag) cudaFree(s.d_flag);
     if (s.d_order) cudaFree(s.d_order);
+    if (s.d_cpair) cudaFree(s.d_cpair);
+    if (s.d_perm) cudaFree(s.d_perm);
     if (s.d_pods) cudaFree(s.d_pods);
     if (s.d_keys) cudaFree(s.d_keys);
     if (s.d_gather) cudaFree(s.d_gather);
@@ -322,6 +334,7 @@ int kgpu_set_weights(kgpu_t *h, const int32_t w[KGPU_NUM_LEVELS]) {
         if (w[i] < 0 || w[i] > KGPU_MAX_WEIGHT)
             return fail(h, KGPU_ERR_INVALID, "kgpu_set_weights: w[%d] = %d outside 0..%d", i, w[i], KGPU_MAX_WEIGHT);
     memcpy(h->W, w, sizeof h->W);
+    for (auto &s : h->shards) s.compact_dirty = true;
     return KGPU_OK;
 }
 
@@ -360,7 +373,11 @@ int kgpu_upload_nodes(kgpu_t *h, const int32_t *topo, const int32_t *free_mask, 
             if (s.d_topo) cudaFree(s.d_topo);
             if (s.d_free) cudaFree(s.d_free);
             if (s.d_mem) cudaFree(s.d_mem);
-            s.d_topo = nullptr; s.d_free = nullptr; s.d_mem = nullptr; s.cap = 0;
+            if (s.d_cpair) cudaFree(s.d_cpair);
+            if (s.d_perm) cudaFree(s.d_perm);
+            s.d_topo = nullptr; s.d_free = nullptr; s.d_mem = nullptr; s.d_cpair = nullptr; s.d_perm = nullptr; s.cap = 0;
+            KGPU_CUDA(h, cudaMalloc(&s.d_cpair, (size_t)cnt * 112));
+            KGPU_CUDA(h, cudaMalloc(&s.d_perm, (size_t)cnt * 4));
             KGPU_CUDA(h, cudaMalloc(&s.d_topo, (size_t)cnt * 256));
             KGPU_CUDA(h, cudaMalloc(&s.d_free, (size_t)cnt * 4));
             KGPU_CUDA(h, cudaMalloc(&s.d_mem, (size_t)cnt * 32));
@@ -373,6 +390,7 @@ int kgpu_upload_nodes(kgpu_t *h, const int32_t *topo, const int32_t *free_mask, 
             KGPU_CUDA(h, cudaMemcpyAsync(s.d_free, free_mask + off, (size_t)cnt * 4, cudaMemcpyHostToDevice, s.stream));
         }
         s.n = cnt;
+        s.compact_dirty = true;
         s.node_id_base = node_id_base + off;
         // K1s order: nodes grouped by number of free GPUs (8 first), each class in increasing node
         // index and padded to whole warps (32 slots), so the lanes of a warp share the bound F and are
@@ -449,6 +467,7 @@ int kgpu_update_node(kgpu_t *h, int64_t idx, const int32_t topo[64], int32_t fre
     int64_t local = 0;
     kgpu_shard *s = shard_of(h, idx, &local);
     KGPU_CUDA(h, cudaSetDevice(s->dev));
+    s->compact_dirty = true;
     KGPU_CUDA(h, cudaMemcpyAsync(s->d_topo + local * 64, topo, 256, cudaMemcpyHostToDevice, s->stream));
     KGPU_CUDA(h, cudaMemcpyAsync(s->d_free + local, &free_mask, 4, cudaMemcpyHostToDevice, s->stream));
     KGPU_CUDA(h, cudaStreamSynchronize(s->stream));
@@ -461,6 +480,7 @@ int kgpu_set_free_mask(kgpu_t *h, int64_t idx, int32_t free_mask) {
     if (idx < 0 || idx >= h->n_total) return fail(h, KGPU_ERR_INVALID, "kgpu_set_free_mask: index %lld out of range", (long long)idx);
     int64_t local = 0;
     kgpu_shard *s = shard_of(h, idx, &local);
+    s->compact_dirty = true;
     KGPU_CUDA(h, cudaSetDevice(s->dev));
     KGPU_CUDA(h, cudaMemcpyAsync(s->d_free + local, &free_mask, 4, cudaMemcpyHostToDevice, s->stream));
     KGPU_CUDA(h, cudaStreamSynchronize(s->stream));
@@ -559,6 +579,7 @@ int kgpu_place_batch(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_ke
                                                                         reinterpret_cast<const int4 *>(s.d_pods), P, W, s.d_nodebest,
                                                                         s.d_tilebest, T, s.d_keys);
         h->launches += 2;
+        s.compact_dirty = true;          // the free masks have changed on the device
         KGPU_CUDA(h, cudaGetLastError());
         KGPU_CUDA(h, cudaEventRecord(s.ev1, s.stream));
     }

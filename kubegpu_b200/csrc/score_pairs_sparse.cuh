@@ -96,52 +96,36 @@ __device__ __forceinline__ void sp_run_k(int F, const PairCosts &C, const PipeCo
 #undef KGPU_SP_CASE
 }
 
-// grid = (slot tiles of 128, pod splits); block = 128 threads.  order[slot] = node index or -1 (padding).
-template <bool PER_PAIR, bool MEM>
-__global__ void __launch_bounds__(SP_THREADS, MEM ? 4 : KGPU_SP_MINBLOCKS)
-score_pairs_sparse(const int4 *__restrict__ topo4, const int32_t *__restrict__ free_mask,
-                   const int32_t *__restrict__ gpu_mem, const int32_t *__restrict__ order,
-                   const int *__restrict__ mem_flag, int64_t node_id_base, const int4 *__restrict__ pods4, int64_t P,
-                   int pods_per_split, Weights W, PipeConsts pc, unsigned long long *__restrict__ keys) {
-    if (MEM && *mem_flag == 0) return;
+// Compacted pair-cost cache: for every node the 28 scaled pair costs in COMPACT position order
+// (free GPUs first, ascending; pairs touching a non-free position carry PEN) plus the permutation
+// position -> GPU index (8 nibbles).  Rebuilt by the host wrapper whenever topology, free masks or
+// weights changed since the last launch (kgpu.cu: compact_dirty), so K1s blocks stage a node with
+// seven 16-byte loads instead of redoing the gather in every pod split.
+__global__ void __launch_bounds__(SP_THREADS)
+compact_nodes(const int4 *__restrict__ topo4, const int32_t *__restrict__ free_mask, int64_t N, Weights W,
+              uint32_t *__restrict__ cpair /*[N][28]*/, uint32_t *__restrict__ perm_out /*[N]*/) {
     __shared__ int32_t sW[16];
-    __shared__ int32_t sCnt[10], sOff[11];
-    __shared__ uint8_t sK[SP_CHUNK];
-    __shared__ uint16_t sIdx[SP_CHUNK];
-    __shared__ uint32_t sBest[SP_WARPS][SP_CHUNK];
-    __shared__ int32_t sMin[MEM ? SP_CHUNK : 1];
-    __shared__ uint32_t sRow[SP_THREADS * SP_ROW];     // staging: each lane's 28 scaled pair costs (then its 8 memories)
-    __shared__ uint32_t sPerm[SP_THREADS];             // position -> GPU index, 8 nibbles
-    __shared__ int32_t sNode[SP_THREADS];              // slot -> node index (-1 = padding)
-
+    __shared__ uint32_t sRow[SP_THREADS * SP_ROW];
     const int tid = threadIdx.x;
-    uint32_t *const sBestW = sBest[tid >> 5];
-    const uint32_t lane_field = (uint32_t)(tid & 31) << 8;
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < 16; i++) sW[i] = W.w[i];
     }
     __syncthreads();
-
-    // ---- staging -------------------------------------------------------------------------
-    const int64_t slot = (int64_t)blockIdx.x * SP_THREADS + tid;
-    const int32_t node = __ldg(order + slot);
-    const bool valid = node >= 0;
-    sNode[tid] = node;
-    const uint32_t free = valid ? ((uint32_t)__ldg(free_mask + node) & 0xFFu) : 0u;
+    const int64_t node = (int64_t)blockIdx.x * SP_THREADS + tid;
+    if (node >= N) return;
+    const uint32_t free = (uint32_t)__ldg(free_mask + node) & 0xFFu;
     uint32_t *row = sRow + tid * SP_ROW;
-    {   // the node's 28 scaled pair costs in natural GPU order -> this lane's shared-memory row
+    {
+        const int4 *src = topo4 + node * 16;
         int4 q[16];
 #pragma unroll
         for (int t = 0; t < 16; t++) q[t] = make_int4(0, 0, 0, 0);
-        if (valid) {
-            const int4 *src = topo4 + (int64_t)node * 16;
-            q[0] = __ldg(src + 0);  q[1] = __ldg(src + 1);
-            q[2] = __ldg(src + 2);  q[3] = __ldg(src + 3);
-            q[4] = __ldg(src + 4);  q[5] = __ldg(src + 5);
-            q[7] = __ldg(src + 7);  q[9] = __ldg(src + 9);
-            q[11] = __ldg(src + 11); q[13] = __ldg(src + 13);
-        }
+        q[0] = __ldg(src + 0);  q[1] = __ldg(src + 1);
+        q[2] = __ldg(src + 2);  q[3] = __ldg(src + 3);
+        q[4] = __ldg(src + 4);  q[5] = __ldg(src + 5);
+        q[7] = __ldg(src + 7);  q[9] = __ldg(src + 9);
+        q[11] = __ldg(src + 11); q[13] = __ldg(src + 13);
 #pragma unroll
         for (int i = 0; i < 8; i++)
 #pragma unroll
@@ -151,7 +135,6 @@ score_pairs_sparse(const int4 *__restrict__ topo4, const int32_t *__restrict__ f
                 row[sp_pidx(i, j)] = (uint32_t)sW[lvl & 15] << 8;
             }
     }
-    // permutation: free GPUs first (ascending), then the others (ascending)
     const uint32_t nfree = (uint32_t)__popc(free);
     uint32_t perm = 0;
     {
@@ -163,25 +146,70 @@ score_pairs_sparse(const int4 *__restrict__ topo4, const int32_t *__restrict__ f
         for (int g = 0; g < 8; g++)
             if (!((free >> g) & 1u)) { perm |= (uint32_t)g << (4 * pos); pos++; }
     }
-    sPerm[tid] = perm;
-    // gather the pair costs in compacted order; a pair touching a position >= f is not placeable
-    PairCosts C;
-    for_each_pair(C, [&](int i, int j) -> uint32_t {          // i < j are POSITIONS here
-        const int a = (int)((perm >> (4 * i)) & 7u), b = (int)((perm >> (4 * j)) & 7u);
-        const int lo = min(a, b), hi = max(a, b);
-        uint32_t cst = row[7 * lo - ((lo * (lo - 1)) >> 1) + (hi - lo - 1)];
-        if ((uint32_t)j >= nfree) cst += PEN;
-        return valid ? cst : PEN;
-    });
-    int32_t mem[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (MEM) {
-        __syncwarp();
-        if (valid) {
+    perm_out[node] = perm;
+    uint32_t *dst = cpair + node * 28;
 #pragma unroll
-            for (int g = 0; g < 8; g++) row[g] = (uint32_t)__ldg(gpu_mem + (int64_t)node * 8 + g);
+    for (int i = 0; i < 8; i++)
 #pragma unroll
-            for (int g = 0; g < 8; g++) mem[g] = (int32_t)row[(perm >> (4 * g)) & 7u];
+        for (int j = i + 1; j < 8; j++) {          // i < j are POSITIONS
+            const int a = (int)((perm >> (4 * i)) & 7u), b = (int)((perm >> (4 * j)) & 7u);
+            const int lo = min(a, b), hi = max(a, b);
+            uint32_t cst = row[7 * lo - ((lo * (lo - 1)) >> 1) + (hi - lo - 1)];
+            if ((uint32_t)j >= nfree) cst += PEN;
+            dst[sp_pidx(i, j)] = cst;
         }
+}
+
+// grid = (slot tiles of 128, pod splits); block = 128 threads.  order[slot] = node index or -1 (padding).
+template <bool PER_PAIR, bool MEM>
+__global__ void __launch_bounds__(SP_THREADS, MEM ? 4 : KGPU_SP_MINBLOCKS)
+score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__ perm_in,
+                   const int32_t *__restrict__ free_mask,
+                   const int32_t *__restrict__ gpu_mem, const int32_t *__restrict__ order,
+                   const int *__restrict__ mem_flag, int64_t node_id_base, const int4 *__restrict__ pods4, int64_t P,
+                   int pods_per_split, PipeConsts pc, unsigned long long *__restrict__ keys) {
+    if (MEM && *mem_flag == 0) return;
+    __shared__ int32_t sCnt[10], sOff[11];
+    __shared__ uint8_t sK[SP_CHUNK];
+    __shared__ uint16_t sIdx[SP_CHUNK];
+    __shared__ uint32_t sBest[SP_WARPS][SP_CHUNK];
+    __shared__ int32_t sMin[MEM ? SP_CHUNK : 1];
+    __shared__ uint32_t sPerm[SP_THREADS];             // position -> GPU index, 8 nibbles
+    __shared__ int32_t sNode[SP_THREADS];              // slot -> node index (-1 = padding)
+
+    const int tid = threadIdx.x;
+    uint32_t *const sBestW = sBest[tid >> 5];
+    const uint32_t lane_field = (uint32_t)(tid & 31) << 8;
+
+    // ---- staging: the node's compacted pair costs (7 x 16 B), permutation and free count ----------
+    const int64_t slot = (int64_t)blockIdx.x * SP_THREADS + tid;
+    const int32_t node = __ldg(order + slot);
+    const bool valid = node >= 0;
+    sNode[tid] = node;
+    const uint32_t nfree = valid ? (uint32_t)__popc((uint32_t)__ldg(free_mask + node) & 0xFFu) : 0u;
+    const uint32_t perm = valid ? __ldg(perm_in + node) : 0x76543210u;
+    sPerm[tid] = perm;
+    PairCosts C;
+    {
+        uint32_t wds[28];
+        if (valid) {
+            const int4 *src = cpair4 + (int64_t)node * 7;
+#pragma unroll
+            for (int t = 0; t < 7; t++) {
+                const int4 v = __ldg(src + t);
+                wds[4 * t + 0] = (uint32_t)v.x; wds[4 * t + 1] = (uint32_t)v.y;
+                wds[4 * t + 2] = (uint32_t)v.z; wds[4 * t + 3] = (uint32_t)v.w;
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < 28; t++) wds[t] = PEN;
+        }
+        for_each_pair(C, [&](int i, int j) -> uint32_t { return wds[sp_pidx(i, j)]; });
+    }
+    int32_t mem[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (MEM && valid) {
+#pragma unroll
+        for (int g = 0; g < 8; g++) mem[g] = __ldg(gpu_mem + (int64_t)node * 8 + ((perm >> (4 * g)) & 7u));
     }
     const int F = (int)__reduce_max_sync(0xFFFFFFFFu, nfree);    // warp-uniform bound on usable positions
 
