@@ -81,6 +81,7 @@ namespace gpuschedulerplugin {
 using gpuplugintypes::ResourceGPU;
 
 const char *const GPUTopologyGeneration = "gpu/gpu-generate-topology";
+const char *const GPUMinMemoryMiB = "gpu/gpu-min-memory-mib";
 
 namespace {
 
@@ -424,6 +425,15 @@ void NvidiaGPUScheduler::AddNode(const std::string &nodeName, types::NodeInfo *n
     rec.nGpus = (int)std::min<size_t>(slots.size(), KGPU_MAX_GPUS_PER_NODE);
     rec.gpuNames.clear();
     for (int i = 0; i < rec.nGpus; i++) rec.gpuNames.push_back(slots[(size_t)i].name);
+    rec.hasMem = false;
+    for (int i = 0; i < 8; i++) rec.memMiB[i] = 0;
+    for (int i = 0; i < rec.nGpus; i++) {                   // "<name>/memory" next to "<name>/cards" (bytes)
+        auto m = nodeInfo->Allocatable.find(std::string(types::DeviceGroupPrefix) + "/" + rec.gpuNames[(size_t)i] + "/memory");
+        if (m != nodeInfo->Allocatable.end() && m->second > 0) {
+            rec.memMiB[i] = (int32_t)std::min<int64_t>(m->second >> 20, std::numeric_limits<int32_t>::max());
+            rec.hasMem = true;
+        }
+    }
     rec.presentMask = rec.nGpus >= 8 ? 0xFFu : ((1u << rec.nGpus) - 1u);
     rec.usedMask &= rec.presentMask;
     if (!rec.explicitTopo) {
@@ -504,11 +514,29 @@ std::string NvidiaGPUScheduler::flushNodes() {
     }
     if (kgpu_upload_nodes(handle_, topo.data(), freeMask.data(), (int64_t)n, 0) != KGPU_OK)
         return lastError_ = kgpu_last_error(handle_);
+    bool anyMem = false;
+    std::vector<int32_t> mem(n * 8, std::numeric_limits<int32_t>::max());     // unknown = unconstrained
+    for (size_t i = 0; i < n; i++) {
+        const NodeRecord &rec = nodes_[indexToName_[i]];
+        if (!rec.hasMem) continue;
+        anyMem = true;
+        for (int g = 0; g < 8; g++) mem[i * 8 + (size_t)g] = g < rec.nGpus ? rec.memMiB[g] : 0;
+    }
+    if (anyMem && kgpu_upload_gpu_memory(handle_, mem.data(), (int64_t)n) != KGPU_OK) return lastError_ = kgpu_last_error(handle_);
     dirty_ = false;
     return "";
 }
 
 std::string NvidiaGPUScheduler::ScoreBatch(const std::vector<const types::PodInfo *> &pods, std::vector<Placement> *out) {
+    return runBatch(pods, out, false);
+}
+
+std::string NvidiaGPUScheduler::PlaceBatch(const std::vector<const types::PodInfo *> &pods, std::vector<Placement> *out) {
+    return runBatch(pods, out, true);
+}
+
+std::string NvidiaGPUScheduler::runBatch(const std::vector<const types::PodInfo *> &pods, std::vector<Placement> *out,
+                                         bool sequential) {
     std::string err = flushNodes();
     if (!err.empty()) return err;
     const size_t P = pods.size();
@@ -520,9 +548,13 @@ std::string NvidiaGPUScheduler::ScoreBatch(const std::vector<const types::PodInf
         const int64_t k = PodGPUCount(copy);
         req[p * 4 + 0] = k > 8 ? 9 : (int32_t)k;           // > 8 GPUs never fits one node
         req[p * 4 + 1] = (int32_t)p;
+        const int64_t need = getOr0(pods[p]->Requests, GPUMinMemoryMiB);
+        req[p * 4 + 3] = (int32_t)std::max<int64_t>(0, std::min<int64_t>(need, std::numeric_limits<int32_t>::max()));
     }
     std::vector<uint64_t> keys(P, KGPU_NO_FIT);
-    if (kgpu_score_batch(handle_, req.data(), (int64_t)P, keys.data()) != KGPU_OK) return lastError_ = kgpu_last_error(handle_);
+    const int rc = sequential ? kgpu_place_batch(handle_, req.data(), (int64_t)P, keys.data())
+                              : kgpu_score_batch(handle_, req.data(), (int64_t)P, keys.data());
+    if (rc != KGPU_OK) return lastError_ = kgpu_last_error(handle_);
     out->assign(P, Placement());
     for (size_t p = 0; p < P; p++) {
         Placement &pl = (*out)[p];
@@ -532,6 +564,7 @@ std::string NvidiaGPUScheduler::ScoreBatch(const std::vector<const types::PodInf
             pl.cost = KGPU_KEY_COST(keys[p]);
             pl.gpuMask = KGPU_KEY_MASK(keys[p]);
             pl.nodeName = indexToName_[KGPU_KEY_NODE(keys[p])];
+            if (sequential) nodes_[pl.nodeName].usedMask |= pl.gpuMask;     // the device already took them
         }
         if (!pods[p]->Name.empty()) lastPlacement_[pods[p]->Name] = pl;
     }

@@ -85,6 +85,9 @@ namespace types = kubedevice::types;
 using gpuplugintypes::SortedTreeNode;
 
 extern const char *const GPUTopologyGeneration;   // "gpu/gpu-generate-topology" (gpu_scheduler.go:14)
+// Extension (no reference counterpart): pod-level request "every GPU I get must have at least this
+// many MiB" -- checked against the per-GPU `<gpu>/memory` the node agent advertises.
+extern const char *const GPUMinMemoryMiB;         // "gpu/gpu-min-memory-mib"
 
 // ---- gpu.go, function for function ------------------------------------------------
 types::ResourceList TranslateGPUResources(int64_t neededGPUs, const types::ResourceList &nodeResources,
@@ -162,6 +165,10 @@ public:
                                     types::NodeInfo *nodeInfo);
     // Score a whole scheduling cycle in one kernel launch: best node + GPU set per pod.
     std::string ScoreBatch(const std::vector<const types::PodInfo *> &pods, std::vector<Placement> *out);
+    // Place a whole cycle IN ORDER on the device: each pod takes its GPUs before the next one is
+    // scored (K3).  The placements are remembered like ScoreBatch's and the usage is recorded, so a
+    // later PodAllocate / ReturnPodResources works on them.
+    std::string PlaceBatch(const std::vector<const types::PodInfo *> &pods, std::vector<Placement> *out);
     std::string LastError() const { return lastError_; }
     const TreeCache &cache() const { return cache_; }
     bool hasDevice() const { return handle_ != nullptr; }
@@ -172,6 +179,8 @@ public:
         int nGpus = 0;
         std::vector<std::string> gpuNames;    // slot -> "gpugrp1/a/gpugrp0/b/gpu/<id>"
         int32_t topo[64] = {0};
+        int32_t memMiB[8] = {0};              // per slot, from the advertised <gpu>/memory (0 = unknown)
+        bool hasMem = false;
         uint32_t presentMask = 0, usedMask = 0;
         bool explicitTopo = false;
         bool removed = false;
@@ -183,6 +192,7 @@ private:
     std::string syncNode(const NodeRecord &rec);
     std::string flushNodes();
     std::string scoreOne(const NodeRecord &rec, int k, uint32_t *nodeKey);
+    std::string runBatch(const std::vector<const types::PodInfo *> &pods, std::vector<Placement> *out, bool sequential);
     TreeCache cache_;
     std::map<std::string, NodeRecord> nodes_;
     std::vector<std::string> indexToName_;

@@ -10,11 +10,12 @@
 //   addnode NAME KUBEALLOC [key=val ...]        AddNode with Allocatable = {key: val}
 //   rmnode NAME                                 RemoveNode
 //   topo NAME v0 .. v63                         SetNodeTopology (extension)
-//   pod NAME [topogen=V] {run|init CNAME req=N [kube=N] [dev:key=val ...]}...
+//   pod NAME [topogen=V] [minmem=MiB] {run|init CNAME req=N [kube=N] [dev:key=val ...]}...
 //   fits NODE POD                               PodFitsDevice  -> fits/score + rewritten requests
 //   allocate NODE POD                           PodAllocate    -> error text + AllocateFrom
 //   take POD | return POD                       TakePodResources / ReturnPodResources
 //   scorebatch POD...                           ScoreBatch (GPU)
+//   placebatch POD...                           PlaceBatch (GPU, sequential, takes the GPUs)
 //   addjson NAME FILE [nvml]                    AddNodeFromGpusInfo (node agent JSON), dumps names + matrix
 //   visible POD                                 NVIDIA_VISIBLE_DEVICES per container (node agent Allocate)
 //   cache                                       dump the tree cache
@@ -136,6 +137,8 @@ int main(int argc, char **argv) {
                     cur = tok == "run" ? &pod.RunningContainers[cname] : &pod.InitContainers[cname];
                 } else if (tok.compare(0, 8, "topogen=") == 0) {
                     pod.Requests[GPUTopologyGeneration] = atoll(tok.c_str() + 8);
+                } else if (tok.compare(0, 7, "minmem=") == 0) {
+                    pod.Requests[GPUMinMemoryMiB] = atoll(tok.c_str() + 7);
                 } else if (cur && tok.compare(0, 4, "req=") == 0) {
                     cur->Requests[gpuplugintypes::ResourceGPU] = atoll(tok.c_str() + 4);
                 } else if (cur && tok.compare(0, 5, "kube=") == 0) {
@@ -165,13 +168,13 @@ int main(int argc, char **argv) {
             const std::string err = cmd == "take" ? sched.TakePodResources(nullptr, &g_pods[podName])
                                                   : sched.ReturnPodResources(nullptr, &g_pods[podName]);
             printf("  err=%s\n", err.c_str());
-        } else if (cmd == "scorebatch") {
+        } else if (cmd == "scorebatch" || cmd == "placebatch") {
             std::vector<const types::PodInfo *> pods;
             std::string podName;
             while (in >> podName)
                 if (g_pods.count(podName)) pods.push_back(&g_pods[podName]);
             std::vector<Placement> out;
-            const std::string err = sched.ScoreBatch(pods, &out);
+            const std::string err = cmd == "placebatch" ? sched.PlaceBatch(pods, &out) : sched.ScoreBatch(pods, &out);
             printf("  err=%s\n", err.c_str());
             for (size_t i = 0; i < out.size(); i++)
                 printf("  %s fits=%d cost=%u node=%s mask=0x%02x\n", pods[i]->Name.c_str(), out[i].fits ? 1 : 0, out[i].cost,

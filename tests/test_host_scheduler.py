@@ -337,3 +337,47 @@ def test_json_node_scored_with_real_matrix_and_visible_devices(cli, golden_dir, 
     assert got.split("> fits T p5\n")[1].splitlines()[0] == "  fits=1 reasons=0 score=%.17g" % (1.0 / (1.0 + (k5 >> 8)))
     vis = got.split("> visible p2\n")[1].splitlines()
     assert vis[0] == "  a NVIDIA_VISIBLE_DEVICES=GPU00,GPU01" and vis[1] == "  b NVIDIA_VISIBLE_DEVICES=GPU02"
+
+
+@pytest.mark.gpu
+def test_host_memory_constraint_and_place_batch(cli, golden_dir, tmp_path, oracle_b):
+    """Host layer over K1m and K3: the advertised per-GPU memory becomes the device's gpu_mem, the pod
+    knob gpu/gpu-min-memory-mib becomes min_mem, and PlaceBatch places a cycle in order."""
+    rng = random.Random(5)
+    big = tmp_path / "big.json"
+    big.write_text(_inventory_json(rng, 8, 2, pair_level=6, socket_level=3, cross=1))      # 183359 MiB GPUs
+    titan = os.path.join(golden_dir, "gpus_titanx.json")                                  # 12238 MiB GPUs
+    script = "\n".join([
+        "addjson T %s" % titan, "addjson B %s" % big,
+        "pod small run a req=2", "pod hungry minmem=40000 run a req=2", "pod greedy minmem=400000 run a req=1",
+        "scorebatch small hungry greedy",
+        "pod q1 run a req=4", "pod q2 run a req=4", "pod q3 run a req=4", "pod q4 run a req=4", "pod q5 run a req=4",
+        "placebatch q1 q2 q3 q4 q5", "scorebatch small", "allocate B q1",
+    ]) + "\n"
+    got = run_cli(cli, script, device=True)
+    lines = got.split("> scorebatch small hungry greedy\n")[1].splitlines()
+    # node ids: T = 0, B = 1.  `small` takes the cheapest pair anywhere (T's level-5 pair costs W[5]=2, B's
+    # level-6 pair costs W[6]=1 -> B); `hungry` must go to B; nobody has 400 GB
+    assert lines[1] == "  small fits=1 cost=1 node=B mask=0x03"
+    assert lines[2] == "  hungry fits=1 cost=1 node=B mask=0x03"
+    assert lines[3] == "  greedy fits=0 cost=0 node= mask=0x00"
+    # sequential: four 4-GPU pods fill B's two sockets then T's two; the fifth finds nothing
+    gpusT = oa.parse_gpus_info(open(titan).read())
+    gpusB = oa.parse_gpus_info(open(big).read())
+    topo = np.zeros((2, 64), np.int32)
+    topo[0] = np.array(oa.link_matrix_from_gpus(gpusT), np.int32).reshape(64)
+    topo[1] = np.array(oa.link_matrix_from_gpus(gpusB), np.int32).reshape(64)
+    from kubegpu_b200 import synth
+    want, free_after = oracle_b.place_batch(topo, np.array([0xFF, 0xFF], np.int32), synth.make_pods(np.array([4] * 5, np.int32)))
+    names = ["T", "B"]
+    plines = got.split("> placebatch q1 q2 q3 q4 q5\n")[1].splitlines()
+    assert plines[0] == "  err="
+    for line, pod, key in zip(plines[1:6], ["q1", "q2", "q3", "q4", "q5"], want):
+        u = oracle_b.unpack_key(key)
+        exp = "  %s fits=0 cost=0 node= mask=0x00" % pod if u is None else "  %s fits=1 cost=%d node=%s mask=0x%02x" % (pod, u[0], names[u[1]], u[2])
+        assert line == exp
+    assert free_after.tolist() == [0, 0]
+    after = got.split("> scorebatch small\n")[1].splitlines()
+    assert after[1] == "  small fits=0 cost=0 node= mask=0x00"          # the cluster is full now
+    alloc = got.split("> allocate B q1\n")[1]
+    assert alloc.count("from ") == 4 and "/gpu/" in alloc
