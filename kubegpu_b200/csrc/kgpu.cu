@@ -160,7 +160,7 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
     const int64_t tiles = sparse ? s.n_slots / kgpu::SP_THREADS : (s.n + tile - 1) / tile;
     // Pod splits: enough blocks for ~8 waves of resident CTAs, but each block keeps
     // >= 128 pods so staging its node tile stays amortised.
-    const int64_t resident = (int64_t)s.sm_count * (wpp ? 8 : KGPU_LPN_MINBLOCKS);
+    const int64_t resident = (int64_t)s.sm_count * (wpp ? 8 : sparse ? KGPU_SP_MINBLOCKS : KGPU_LPN_MINBLOCKS);
     static const int64_t waves = [] { const char *e = getenv("KGPU_WAVES"); int v = e ? atoi(e) : 0; return (int64_t)(v > 0 ? v : 8); }();
     int64_t splits = std::max<int64_t>(1, (waves * resident + tiles - 1) / tiles);
     splits = std::min<int64_t>(splits, std::max<int64_t>(1, P / 128));

@@ -25,8 +25,13 @@ constexpr int SP_WARPS = SP_THREADS / 32;
 constexpr int SP_CHUNK = 512;
 constexpr int SP_ROW = 29;          // padded row of 28 pair costs per lane in shared memory
 #ifndef KGPU_SP_MINBLOCKS
-#define KGPU_SP_MINBLOCKS 6
+#define KGPU_SP_MINBLOCKS 8          // 64 registers, no spills, 32 warps/SM (profiles/r01_k1s_sweep.txt)
 #endif
+#ifndef KGPU_SP_UNROLL
+#define KGPU_SP_UNROLL 1          // pods per trip of a (K,F) bucket loop
+#endif
+#define KGPU_PRAGMA(x) _Pragma(#x)
+#define KGPU_UNROLL(n) KGPU_PRAGMA(unroll n)
 
 __host__ __device__ constexpr int sp_pidx(int i, int j) { return 7 * i - i * (i - 1) / 2 + (j - i - 1); }  // i<j
 
@@ -42,7 +47,7 @@ template <int K, int F, bool PER_PAIR, bool MEM>
 __device__ __forceinline__ void sp_bucket(const PairCosts &C, const PipeConsts pc, uint32_t nfree, bool valid,
                                           const int32_t (&mem)[8], uint32_t lane_field, const uint16_t *sIdx,
                                           const uint8_t *sK, const int32_t *sMin, int begin, int end, uint32_t *sBestW) {
-#pragma unroll 1
+    KGPU_UNROLL(KGPU_SP_UNROLL)
     for (int i = begin; i < end; i++) {
         const int p = sIdx[i];
         PipeConsts pcl = pc;
