@@ -81,7 +81,7 @@ func (k *handle) scoreBatch(pods []int32) ([]uint64, error) {
 func (k *handle) scorePair(node int64, gpus int32) (uint32, error) {
 	var out C.uint32_t
 	n, kk := C.int64_t(node), C.int32_t(gpus)
-	if rc := C.kgpu_score_pairs(k.h, &n, &kk, 1, &out); rc != C.KGPU_OK {
+	if rc := C.kgpu_score_pairs(k.h, &n, &kk, nil, 1, &out); rc != C.KGPU_OK {
 		return 0, k.err("kgpu_score_pairs")
 	}
 	return uint32(out), nil

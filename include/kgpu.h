@@ -142,8 +142,10 @@ int kgpu_score_batch_device_ex(kgpu_t *h, const int32_t *d_pods, int64_t P, uint
 /* Per-pair query (one PodFitsDevice(node, pod) call, or a list of them): for each i,
  * out_node_keys[i] = (cost << 8) | gpu_mask of the cheapest k[i]-subset of the free GPUs
  * of node node_idx[i] (local index as uploaded), or UINT32_MAX if it does not fit.
+ * min_mem_mib may be NULL (no memory requirement) or hold one requirement per pair.
  * Host buffers, synchronous. */
-int kgpu_score_pairs(kgpu_t *h, const int64_t *node_idx, const int32_t *k, int64_t n, uint32_t *out_node_keys);
+int kgpu_score_pairs(kgpu_t *h, const int64_t *node_idx, const int32_t *k, const int32_t *min_mem_mib, int64_t n,
+                     uint32_t *out_node_keys);
 
 /* Stateful sequential placement (what TakePodResources would make of a scheduling cycle;
  * a no-op in the reference, gpu_scheduler.go:57-63).  Pods are placed IN ORDER; each one gets

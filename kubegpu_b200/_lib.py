@@ -73,7 +73,7 @@ def load() -> ctypes.CDLL:
     L.kgpu_score_batch_device_ex.restype = ci
     L.kgpu_score_batch_device_ex.argtypes = [vp, vp, i64, vp, vp, ci]
     L.kgpu_score_pairs.restype = ci
-    L.kgpu_score_pairs.argtypes = [vp, ctypes.POINTER(i64), i32p, i64, ctypes.POINTER(ctypes.c_uint32)]
+    L.kgpu_score_pairs.argtypes = [vp, ctypes.POINTER(i64), i32p, i32p, i64, ctypes.POINTER(ctypes.c_uint32)]
     L.kgpu_place_batch.restype = ci
     L.kgpu_place_batch.argtypes = [vp, vp, i64, vp]
     L.kgpu_get_free_masks.restype = ci

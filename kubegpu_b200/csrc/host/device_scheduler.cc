@@ -571,12 +571,12 @@ std::string NvidiaGPUScheduler::runBatch(const std::vector<const types::PodInfo 
     return "";
 }
 
-std::string NvidiaGPUScheduler::scoreOne(const NodeRecord &rec, int k, uint32_t *nodeKey) {
+std::string NvidiaGPUScheduler::scoreOne(const NodeRecord &rec, int k, int32_t minMemMiB, uint32_t *nodeKey) {
     std::string err = flushNodes();
     if (!err.empty()) return err;
     const int64_t idx = rec.index;
     const int32_t kk = k > 8 ? 9 : k;
-    if (kgpu_score_pairs(handle_, &idx, &kk, 1, nodeKey) != KGPU_OK) return lastError_ = kgpu_last_error(handle_);
+    if (kgpu_score_pairs(handle_, &idx, &kk, &minMemMiB, 1, nodeKey) != KGPU_OK) return lastError_ = kgpu_last_error(handle_);
     return "";
 }
 
@@ -603,7 +603,8 @@ bool NvidiaGPUScheduler::PodFitsDevice(types::NodeInfo *nodeInfo, types::PodInfo
     if (rec && rec->removed) rec = nullptr;
     if (!rec) return true;
     uint32_t nk = UINT32_MAX;
-    if (!scoreOne(*rec, (int)PodGPUCount(*podInfo), &nk).empty()) return true;
+    const int64_t need = getOr0(podInfo->Requests, GPUMinMemoryMiB);
+    if (!scoreOne(*rec, (int)PodGPUCount(*podInfo), (int32_t)std::max<int64_t>(0, std::min<int64_t>(need, std::numeric_limits<int32_t>::max())), &nk).empty()) return true;
     if (nk == UINT32_MAX) return false;                        // topology-feasible shape exists, but not on this node now
     *score = 1.0 / (1.0 + (double)(nk >> 8));
     return true;

@@ -191,7 +191,7 @@ public:
 private:
     std::string syncNode(const NodeRecord &rec);
     std::string flushNodes();
-    std::string scoreOne(const NodeRecord &rec, int k, uint32_t *nodeKey);
+    std::string scoreOne(const NodeRecord &rec, int k, int32_t minMemMiB, uint32_t *nodeKey);
     std::string runBatch(const std::vector<const types::PodInfo *> &pods, std::vector<Placement> *out, bool sequential);
     TreeCache cache_;
     std::map<std::string, NodeRecord> nodes_;

@@ -609,7 +609,8 @@ int kgpu_get_free_masks(kgpu_t *h, int32_t *out_free_mask, int64_t n) {
     return KGPU_OK;
 }
 
-int kgpu_score_pairs(kgpu_t *h, const int64_t *node_idx, const int32_t *k, int64_t n, uint32_t *out_node_keys) {
+int kgpu_score_pairs(kgpu_t *h, const int64_t *node_idx, const int32_t *k, const int32_t *min_mem_mib, int64_t n,
+                     uint32_t *out_node_keys) {
     if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_score_pairs: NULL handle");
     std::lock_guard<std::mutex> g(h->mu);
     if (n < 0 || (n > 0 && (!node_idx || !k || !out_node_keys))) return fail(h, KGPU_ERR_INVALID, "kgpu_score_pairs: bad arguments");
@@ -622,28 +623,33 @@ int kgpu_score_pairs(kgpu_t *h, const int64_t *node_idx, const int32_t *k, int64
     int64_t off = 0;
     for (auto &s : h->shards) {
         std::vector<long long> idx;
-        std::vector<int32_t> kk;
+        std::vector<int32_t> kk, mm;
         std::vector<int64_t> pos;
         for (int64_t i = 0; i < n; i++)
-            if (node_idx[i] >= off && node_idx[i] < off + s.n) { idx.push_back(node_idx[i] - off); kk.push_back(k[i]); pos.push_back(i); }
+            if (node_idx[i] >= off && node_idx[i] < off + s.n) {
+                idx.push_back(node_idx[i] - off); kk.push_back(k[i]); mm.push_back(min_mem_mib ? min_mem_mib[i] : 0); pos.push_back(i);
+            }
         off += s.n;
         if (idx.empty()) continue;
         const size_t m = idx.size();
         KGPU_CUDA(h, cudaSetDevice(s.dev));
-        long long *d_idx = nullptr; int32_t *d_k = nullptr; uint32_t *d_out = nullptr;
+        long long *d_idx = nullptr; int32_t *d_k = nullptr, *d_mm = nullptr; uint32_t *d_out = nullptr;
         KGPU_CUDA(h, cudaMallocAsync(&d_idx, m * 8, s.stream));
         KGPU_CUDA(h, cudaMallocAsync(&d_k, m * 4, s.stream));
+        KGPU_CUDA(h, cudaMallocAsync(&d_mm, m * 4, s.stream));
+        KGPU_CUDA(h, cudaMemcpyAsync(d_mm, mm.data(), m * 4, cudaMemcpyHostToDevice, s.stream));
         KGPU_CUDA(h, cudaMallocAsync(&d_out, m * 4, s.stream));
         KGPU_CUDA(h, cudaMemcpyAsync(d_idx, idx.data(), m * 8, cudaMemcpyHostToDevice, s.stream));
         KGPU_CUDA(h, cudaMemcpyAsync(d_k, kk.data(), m * 4, cudaMemcpyHostToDevice, s.stream));
         kgpu::score_pair_list<<<(unsigned)((m + 127) / 128), 128, 0, s.stream>>>(
-            reinterpret_cast<const int4 *>(s.d_topo), s.d_free, s.n, d_idx, d_k, (int64_t)m, W, PC, d_out);
+            reinterpret_cast<const int4 *>(s.d_topo), s.d_free, s.d_mem, s.n, d_idx, d_k, d_mm, (int64_t)m, W, PC, d_out);
         h->launches++;
         KGPU_CUDA(h, cudaGetLastError());
         std::vector<uint32_t> res(m);
         KGPU_CUDA(h, cudaMemcpyAsync(res.data(), d_out, m * 4, cudaMemcpyDeviceToHost, s.stream));
         KGPU_CUDA(h, cudaFreeAsync(d_idx, s.stream));
         KGPU_CUDA(h, cudaFreeAsync(d_k, s.stream));
+        KGPU_CUDA(h, cudaFreeAsync(d_mm, s.stream));
         KGPU_CUDA(h, cudaFreeAsync(d_out, s.stream));
         KGPU_CUDA(h, cudaStreamSynchronize(s.stream));
         for (size_t j = 0; j < m; j++) out_node_keys[pos[j]] = res[j];

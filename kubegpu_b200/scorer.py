@@ -138,13 +138,17 @@ class Scorer:
         self._check(self._L.kgpu_get_free_masks(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), out.shape[0]))
         return out
 
-    def score_pairs(self, node_idx, ks) -> np.ndarray:
-        """Per-pair query: (cost << 8 | mask) of node node_idx[i] for k = ks[i], or 0xFFFFFFFF."""
+    def score_pairs(self, node_idx, ks, min_mem=None) -> np.ndarray:
+        """Per-pair query: (cost << 8 | mask) of node node_idx[i] for k = ks[i] (and min_mem[i] MiB per
+        GPU if given), or 0xFFFFFFFF."""
         node_idx = np.ascontiguousarray(node_idx, dtype=np.int64)
         ks = _i32(ks)
+        mm = None if min_mem is None else _i32(min_mem)
         out = np.empty(node_idx.shape[0], dtype=np.uint32)
         self._check(self._L.kgpu_score_pairs(self._h, node_idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
-                                             ks.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), node_idx.shape[0],
+                                             ks.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                             None if mm is None else mm.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                             node_idx.shape[0],
                                              out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))))
         return out
 

@@ -83,6 +83,14 @@ def test_gpu_memory_aware_parity(oracle_b, variant):
                              _lib.BATCH_NO_MIN_MEM)
         torch.cuda.synchronize()
         assert (d_keys.cpu().numpy().view(np.uint64) == oracle_b.score_batch(topo, free, nomem, node_id_base=5, fast=True, nthreads=8)).all()
+        # per-pair queries honour the requirement too
+        idx = np.array([0, 7, 100, 12_345, 30_000], dtype=np.int64)
+        ks = np.array([1, 2, 3, 4, 2], dtype=np.int32)
+        mm = np.array([0, 20_000, 40_000, 100_000, 8_000], dtype=np.int32)
+        gotp = s.score_pairs(idx, ks, mm)
+        for i, k, m, g in zip(idx, ks, mm, gotp):
+            fm = int(free[i]) & sum(1 << b for b in range(8) if mem[i][b] >= m) if m > 0 else int(free[i])
+            assert int(g) == oracle_b.node_key(topo[i], fm, int(k))
         # one node's memory changes
         mem2 = mem.copy()
         mem2[12_345] = 184_320
