@@ -20,7 +20,10 @@
 namespace kgpu {
 
 constexpr int PLACE_TILE = 128;
-constexpr int PLACE_THREADS = 1024;
+#ifndef KGPU_PLACE_THREADS
+#define KGPU_PLACE_THREADS 512      // 16 warps: cheaper barriers than 1024, still >= 9 warps (one per k)
+#endif
+constexpr int PLACE_THREADS = KGPU_PLACE_THREADS;
 
 __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
 #pragma unroll
@@ -118,7 +121,7 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
         if (lane == 0) sRed[warp] = best;
         __syncthreads();
         if (warp == 0) {
-            unsigned long long b = warp_min_u64(sRed[lane]);
+            unsigned long long b = warp_min_u64(lane < PLACE_THREADS / 32 ? sRed[lane] : ~0ull);
             if (lane == 0) sWin = b;
         }
         __syncthreads();
@@ -138,20 +141,18 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
             sFree = fm;
         }
         __syncthreads();
-        // 3. re-enumerate the node for every k: warp w handles k = w
+        // 3+4. warp w handles k = w: re-enumerate the node (lane per subset), then refresh the minimum of the
+        // node's tile for that k with the fresh value (the other 127 entries are unchanged in memory).
         if (warp <= 8) {
             const uint32_t nk = node_key_warp(warp, sCost, sFree, lane);
             if (lane == 0) nodebest[(int64_t)warp * Npad + node] = nk;
-        }
-        __syncthreads();
-        // 4. refresh the 9 minima of the node's tile: warp w reduces k = w over the tile's 128 nodes
-        if (warp <= 8) {
             const int64_t tile = node / PLACE_TILE;
             unsigned long long b = ~0ull;
 #pragma unroll
             for (int j = 0; j < PLACE_TILE / 32; j++) {
                 const int64_t n = tile * PLACE_TILE + lane + 32 * j;
-                b = min(b, wide_key(nodebest[(int64_t)warp * Npad + n], (unsigned long long)(node_id_base + n)));
+                const uint32_t v = n == node ? nk : nodebest[(int64_t)warp * Npad + n];
+                b = min(b, wide_key(v, (unsigned long long)(node_id_base + n)));
             }
             b = warp_min_u64(b);
             if (lane == 0) tilebest[(int64_t)warp * T + tile] = b;
