@@ -22,7 +22,7 @@ namespace kgpu {
 
 constexpr int SP_THREADS = 128;
 constexpr int SP_WARPS = SP_THREADS / 32;
-constexpr int SP_CHUNK = 512;
+constexpr int SP_CHUNK = 512;       // pods per shared-memory chunk; sIdx packs (position | k << 9) in 16 bits
 constexpr int SP_ROW = 29;          // padded row of 28 pair costs per lane in shared memory
 #ifndef KGPU_SP_MINBLOCKS
 #define KGPU_SP_MINBLOCKS 8          // 64 registers, no spills, 32 warps/SM (profiles/r01_k1s_sweep.txt)
@@ -49,10 +49,11 @@ __device__ __forceinline__ void sp_bucket(const PairCosts &C, const PipeConsts p
                                           const uint8_t *sK, const int32_t *sMin, int begin, int end, uint32_t *sBestW) {
     KGPU_UNROLL(KGPU_SP_UNROLL)
     for (int i = begin; i < end; i++) {
-        const int p = sIdx[i];
+        const uint32_t word = sIdx[i];             // chunk position (9 bits) | the pod's k << 9
+        const int p = (int)(word & (SP_CHUNK - 1));
         PipeConsts pcl = pc;
         if (PER_PAIR && !MEM) {                    // un-hoistable per-pair work: see score_pairs.cuh
-            pcl.one = (uint32_t)sK[p] - (uint32_t)(K - 1);
+            pcl.one = (word >> 9) - (uint32_t)(K - 1);
             pcl.minus_one = 0u - pcl.one;
         }
         uint32_t key;
@@ -244,7 +245,7 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
             sOff[10] = acc;
         }
         __syncthreads();
-        for (int i = tid; i < cn; i += SP_THREADS) sIdx[atomicAdd(&sCnt[sK[i]], 1)] = (uint16_t)i;
+        for (int i = tid; i < cn; i += SP_THREADS) sIdx[atomicAdd(&sCnt[sK[i]], 1)] = (uint16_t)(i | ((int)sK[i] << 9));
         __syncthreads();
 
         sp_run_k<0, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[0], sOff[1], sBestW);
