@@ -100,3 +100,42 @@ def test_weights_monotone_property(oracle_b):
     assert ((k3 == ob.NO_FIT) == ~fit).all()
     assert ((k3[fit] >> np.uint64(40)) == (k1[fit] >> np.uint64(40)) * np.uint64(3)).all()
     assert ((k3[fit] & np.uint64((1 << 40) - 1)) == (k1[fit] & np.uint64((1 << 40) - 1))).all()
+
+
+def test_relabelling_gpus_permutes_the_mask_and_keeps_the_cost(oracle_b):
+    """The definition does not depend on how a node's GPUs are numbered (what K1s' compaction relies on):
+    permuting rows/columns of the matrix and the bits of the free mask permutes the chosen mask when
+    the optimum is unique, and always keeps the optimal cost."""
+    ob = oracle_b
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        M = rng.integers(0, 13, size=(8, 8)).astype(np.int32)
+        M = np.triu(M, 1)
+        M = M + M.T
+        free = int(rng.integers(0, 256))
+        k = int(rng.integers(1, 9))
+        perm = rng.permutation(8)                    # new position i holds old GPU perm[i]
+        M2 = M[np.ix_(perm, perm)]
+        free2 = sum(((free >> int(perm[i])) & 1) << i for i in range(8))
+        a, b = ob.node_key(M.reshape(64), free, k), ob.node_key(M2.reshape(64), free2, k)
+        assert (a == ob.NODE_NO_FIT) == (b == ob.NODE_NO_FIT)
+        if a != ob.NODE_NO_FIT:
+            assert a >> 8 == b >> 8
+            back = sum(((b >> i) & 1) << int(perm[i]) for i in range(8))      # b's mask in the old numbering
+            assert bin(back).count("1") == k and (back & ~free) == 0
+            assert ob.lib().kgpu_oracle_subset_cost is not None
+
+
+def test_freeing_gpus_never_hurts_and_monotone_in_k(oracle_b):
+    ob = oracle_b
+    rng = np.random.default_rng(4)
+    for _ in range(200):
+        M = rng.integers(0, 7, size=64).astype(np.int32)
+        free = int(rng.integers(0, 256))
+        more = free | int(rng.integers(0, 256))
+        for k in range(1, 9):
+            a, b = ob.node_key(M, free, k), ob.node_key(M, more, k)
+            if a != ob.NODE_NO_FIT:
+                assert b != ob.NODE_NO_FIT and (b >> 8) <= (a >> 8)
+        costs = [ob.node_key(M, more, k) >> 8 for k in range(1, bin(more).count("1") + 1)]
+        assert costs == sorted(costs)                # with non-negative weights a bigger set never costs less
