@@ -124,8 +124,9 @@ void kgpu_oracle_score_batch(const int32_t *topo, const int32_t *free_mask, int6
 /* ---- tuned CPU variant: the reported CPU baseline ---------------------- */
 /* Same results (tests assert equality with the plain version).  Per node a
  * 256-entry subset-cost table is built once (cost[S] = cost[S minus lowest
- * bit] + row sum), then every pod of the thread's range enumerates its k-subsets
- * through the table.  Threads split the pod range, so no merge is needed. */
+ * bit] + row sum) together with the lists of its feasible subsets per size, then
+ * every pod of the thread's range enumerates the feasible k-subsets through the
+ * table.  Threads split the pod range, so no merge is needed. */
 
 static const uint8_t *subsets_of_size(int k, int *count)
 {
@@ -163,24 +164,35 @@ struct fast_job {
     uint64_t *out;
 };
 
+/* Per node: the 256-entry subset-cost table, plus the node's feasible subsets (subsets of its free mask)
+ * bucketed by size in increasing mask order -- the same sparsity the GPU headline kernel exploits: a pod
+ * wanting k GPUs only visits the C(f,k) subsets of the f free GPUs.  A pod with a memory requirement sees
+ * a smaller mask and filters the list. */
 static void *fast_worker(void *arg)
 {
     struct fast_job *j = (struct fast_job *)arg;
     uint32_t cost[256];
+    uint8_t list[9][70];
+    int cnt[9];
     for (int64_t p = j->p0; p < j->p1; p++) j->out[p] = KGPU_NO_FIT;
     for (int64_t n = 0; n < j->N; n++) {
+        const unsigned fm0 = (unsigned)j->free_mask[n] & 0xFFu;
         uint64_t nid = (uint64_t)(j->node_id_base + n);
         build_cost_table(j->topo + 64 * n, j->W, cost);
+        for (int k = 0; k <= 8; k++) cnt[k] = 0;
+        for (unsigned S = 0; S < 256; S++)
+            if ((S & ~fm0) == 0) { int k = __builtin_popcount(S); list[k][cnt[k]++] = (uint8_t)S; }
         for (int64_t p = j->p0; p < j->p1; p++) {
             int k = j->pods[4 * p];
             if (k < 0 || k > 8) continue;
-            unsigned fm = (unsigned)eff_free(j->free_mask[n], j->mem ? j->mem + 8 * n : NULL, j->pods[4 * p + 3]) & 0xFFu;
-            int cnt;
-            const uint8_t *subs = subsets_of_size(k, &cnt);
+            unsigned fm = fm0;
+            if (j->mem && j->pods[4 * p + 3] > 0)
+                fm = (unsigned)eff_free((int32_t)fm0, j->mem + 8 * n, j->pods[4 * p + 3]) & 0xFFu;
             uint32_t best = NODE_NO_FIT;
-            for (int s = 0; s < cnt; s++) {
+            const uint8_t *subs = list[k];
+            for (int s = 0; s < cnt[k]; s++) {
                 unsigned S = subs[s];
-                if (S & ~fm) continue;
+                if (S & ~fm) continue;                 /* only bites for memory-constrained pods */
                 uint32_t key = (cost[S] << 8) | S;
                 if (key < best) best = key;
             }
