@@ -192,14 +192,18 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
                 s.compact_dirty = false;
             }
             const int4 *cpair4 = reinterpret_cast<const int4 *>(s.d_cpair);
-            kgpu::score_pairs_sparse<true, false><<<grid, kgpu::SP_THREADS, 0, st>>>(
-                cpair4, s.d_perm, s.d_free, s.d_mem, s.d_order, s.d_flag, s.node_id_base, pods4, P, (int)per, PC, d_keys);
+            bool byte_keys = true;       // every cost < 2^16 <=> 28 * max weight < 65536
+            for (int i = 0; i < 16; i++) byte_keys = byte_keys && h->W[i] <= 2340;
+#define KGPU_LAUNCH_SPARSE(MEMF, BK)                                                                          \
+    kgpu::score_pairs_sparse<true, MEMF, BK><<<grid, kgpu::SP_THREADS, 0, st>>>(                              \
+        cpair4, s.d_perm, s.d_free, s.d_mem, s.d_order, s.d_flag, s.node_id_base, pods4, P, (int)per, PC, d_keys)
+            if (byte_keys) KGPU_LAUNCH_SPARSE(false, true); else KGPU_LAUNCH_SPARSE(false, false);
             h->launches++;
             if (has_mem != 0) {
-                kgpu::score_pairs_sparse<true, true><<<grid, kgpu::SP_THREADS, 0, st>>>(
-                    cpair4, s.d_perm, s.d_free, s.d_mem, s.d_order, s.d_flag, s.node_id_base, pods4, P, (int)per, PC, d_keys);
+                if (byte_keys) KGPU_LAUNCH_SPARSE(true, true); else KGPU_LAUNCH_SPARSE(true, false);
                 h->launches++;
             }
+#undef KGPU_LAUNCH_SPARSE
         } else if (has_mem != 0) {   // K1m: the memory-constrained pods (its blocks exit at once if the flag is 0)
             kgpu::score_pairs_lane_per_node<true, true><<<grid, kgpu::LPN_THREADS, 0, st>>>(
                 topo4, s.d_free, mem4, s.d_flag, s.n, s.node_id_base, pods4, P, (int)per, W, PC, d_keys);

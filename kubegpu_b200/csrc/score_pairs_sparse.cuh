@@ -43,7 +43,9 @@ __device__ __forceinline__ uint32_t node_key_kf(const PairCosts &C, const PipeCo
 }
 
 // One (K, F) loop: all pods of the chunk that want K GPUs, enumerating positions 0..F-1.
-template <int K, int F, bool PER_PAIR, bool MEM>
+// BYTE_KEYS (costs < 2^16, i.e. every weight <= 2340): the warp key is cost<<16 | lane<<8 | S, assembled
+// with one PRMT instead of shift / mask / or.
+template <int K, int F, bool PER_PAIR, bool MEM, bool BYTE_KEYS>
 __device__ __forceinline__ void sp_bucket(const PairCosts &C, const PipeConsts pc, uint32_t nfree, bool valid,
                                           const int32_t (&mem)[8], uint32_t lane_field, const uint16_t *sIdx,
                                           const uint8_t *sK, const int32_t *sMin, int begin, int end, uint32_t *sBestW) {
@@ -76,23 +78,25 @@ __device__ __forceinline__ void sp_bucket(const PairCosts &C, const PipeConsts p
         } else {
             key = node_key_kf<K, F>(C, pcl, nfree, valid);
         }
-        const uint32_t v = key >= PEN ? INF32 : (((key & ~0xFFu) << 5) | lane_field | (key & 0xFFu));
+        const uint32_t v = key >= PEN ? INF32
+                           : BYTE_KEYS ? __byte_perm(key, lane_field, 0x2150)      // [cost_hi, cost_lo, lane, S]
+                                       : (((key & ~0xFFu) << 5) | lane_field | (key & 0xFFu));
         const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, v);
         if (lane_field == 0) sBestW[p] = m;
     }
 }
 
-template <int K, bool PER_PAIR, bool MEM>
+template <int K, bool PER_PAIR, bool MEM, bool BYTE_KEYS>
 __device__ __forceinline__ void sp_run_k(int F, const PairCosts &C, const PipeConsts pc, uint32_t nfree, bool valid,
                                          const int32_t (&mem)[8], uint32_t lane_field, const uint16_t *sIdx,
                                          const uint8_t *sK, const int32_t *sMin, int begin, int end, uint32_t *sBestW) {
     if (begin >= end || F < K) return;             // F < K: no lane of this warp has K free GPUs
 #define KGPU_SP_CASE(FF)                                                                                         \
     case FF:                                                                                                     \
-        if (FF >= K) sp_bucket<K, (FF >= K ? FF : K), PER_PAIR, MEM>(C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, begin, end, sBestW); \
+        if (FF >= K) sp_bucket<K, (FF >= K ? FF : K), PER_PAIR, MEM, BYTE_KEYS>(C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, begin, end, sBestW); \
         break;
     if (K <= 1) {                                  // F does not matter for k = 0, 1
-        sp_bucket<K, 8, PER_PAIR, MEM>(C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, begin, end, sBestW);
+        sp_bucket<K, 8, PER_PAIR, MEM, BYTE_KEYS>(C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, begin, end, sBestW);
         return;
     }
     switch (F) {
@@ -167,7 +171,7 @@ compact_nodes(const int4 *__restrict__ topo4, const int32_t *__restrict__ free_m
 }
 
 // grid = (slot tiles of 128, pod splits); block = 128 threads.  order[slot] = node index or -1 (padding).
-template <bool PER_PAIR, bool MEM>
+template <bool PER_PAIR, bool MEM, bool BYTE_KEYS>
 __global__ void __launch_bounds__(SP_THREADS, MEM ? 4 : KGPU_SP_MINBLOCKS)
 score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__ perm_in,
                    const int32_t *__restrict__ free_mask,
@@ -248,15 +252,15 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
         for (int i = tid; i < cn; i += SP_THREADS) sIdx[atomicAdd(&sCnt[sK[i]], 1)] = (uint16_t)(i | ((int)sK[i] << 9));
         __syncthreads();
 
-        sp_run_k<0, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[0], sOff[1], sBestW);
-        sp_run_k<1, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[1], sOff[2], sBestW);
-        sp_run_k<2, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[2], sOff[3], sBestW);
-        sp_run_k<3, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[3], sOff[4], sBestW);
-        sp_run_k<4, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[4], sOff[5], sBestW);
-        sp_run_k<5, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[5], sOff[6], sBestW);
-        sp_run_k<6, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[6], sOff[7], sBestW);
-        sp_run_k<7, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[7], sOff[8], sBestW);
-        sp_run_k<8, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[8], sOff[9], sBestW);
+        sp_run_k<0, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[0], sOff[1], sBestW);
+        sp_run_k<1, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[1], sOff[2], sBestW);
+        sp_run_k<2, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[2], sOff[3], sBestW);
+        sp_run_k<3, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[3], sOff[4], sBestW);
+        sp_run_k<4, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[4], sOff[5], sBestW);
+        sp_run_k<5, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[5], sOff[6], sBestW);
+        sp_run_k<6, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[6], sOff[7], sBestW);
+        sp_run_k<7, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[7], sOff[8], sBestW);
+        sp_run_k<8, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[8], sOff[9], sBestW);
         __syncthreads();
 
         // block result per pod: min over the 4 warps of (cost, node id) -- a tile may hold warps of two
@@ -272,7 +276,7 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
                 const uint32_t m = sBest[w][i];
                 if (m == INF32) continue;
                 const int s = w * 32 + (int)((m >> 8) & 31u);
-                const unsigned long long cand = ((unsigned long long)(m >> 13) << 32) | (uint32_t)sNode[s];
+                const unsigned long long cand = ((unsigned long long)(m >> (BYTE_KEYS ? 16 : 13)) << 32) | (uint32_t)sNode[s];
                 if (cand < best) { best = cand; best_slot = s; best_m = m; }
             }
             if (best_slot >= 0) {
