@@ -248,6 +248,8 @@ def main():
     ap.add_argument("--impl", default="kgpu", choices=["kgpu", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="(round-2 prep, untested) replay the step (memset + K1s + all-gather + K2) as one CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -296,6 +298,7 @@ def main():
 
     def step_device():
         """pods already in HBM -> final keys in HBM (all ranks hold the answer)."""
+        sptr = torch.cuda.current_stream().cuda_stream          # the capture stream while a graph is recorded
         scorer.score_batch_device(d_pods.data_ptr(), N_PODS, d_local.data_ptr(), sptr, _lib.BATCH_NO_MIN_MEM)
         if world > 1:
             dist.all_gather_into_tensor(d_gather.view(-1), d_local)
@@ -320,6 +323,11 @@ def main():
     for _ in range(W):
         flush.zero_()
         step_device()
+    graph = None
+    if args.graph:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            step_device()
     barrier()
     launches0 = scorer.kernel_launches
     sampler = ClockSampler(local_rank)
@@ -332,11 +340,15 @@ def main():
         if world > 1:
             dist.all_reduce(sync_token)                # device-side rendezvous so no rank times another's flush
         ev[i][0].record(stream)
-        scorer.score_batch_device(d_pods.data_ptr(), N_PODS, d_local.data_ptr(), sptr, _lib.BATCH_NO_MIN_MEM)
-        ev[i][1].record(stream)                        # K1 only: roofline numerator
-        if world > 1:
-            dist.all_gather_into_tensor(d_gather.view(-1), d_local)
-            scorer.reduce_shards_device(d_gather.data_ptr(), world, N_PODS, d_final.data_ptr(), sptr)
+        if graph is not None:
+            graph.replay()
+            ev[i][1].record(stream)                    # (no K1-only split inside a graph replay)
+        else:
+            scorer.score_batch_device(d_pods.data_ptr(), N_PODS, d_local.data_ptr(), sptr, _lib.BATCH_NO_MIN_MEM)
+            ev[i][1].record(stream)                    # K1 only: roofline numerator
+            if world > 1:
+                dist.all_gather_into_tensor(d_gather.view(-1), d_local)
+                scorer.reduce_shards_device(d_gather.data_ptr(), world, N_PODS, d_final.data_ptr(), sptr)
         ev[i][2].record(stream)
     barrier()
     clocks = sampler.finish()
