@@ -1,0 +1,105 @@
+// emu_kernels.cc -- runs the real kernel sources (kubegpu_b200/csrc/*.cuh) on the CPU through cuda_emu.h.
+// TEST INFRASTRUCTURE ONLY.  The small host plans below restate what kgpu.cu does around the launches
+// (node order by free count, pod splits); the kernels themselves are compiled from the product sources.
+#include "cuda_emu.h"
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "score_pairs.cuh"
+#include "score_pairs_sparse.cuh"
+
+namespace {
+
+const kgpu::PipeConsts kPC = {1u, 0xFFFFFFFFu};
+
+kgpu::Weights weights_of(const int32_t *W) {
+    kgpu::Weights w;
+    std::memcpy(w.w, W, sizeof w.w);
+    return w;
+}
+
+int per_split(int64_t P, int splits) {
+    int64_t per = (P + splits - 1) / splits;
+    return (int)((per + 31) / 32 * 32);
+}
+
+template <class T>
+T *aligned_array(size_t n) {
+    void *p = nullptr;
+    if (posix_memalign(&p, 64, std::max<size_t>(64, n * sizeof(T))) != 0) abort();
+    std::memset(p, 0, std::max<size_t>(64, n * sizeof(T)));
+    return (T *)p;
+}
+
+}  // namespace
+
+extern "C" {
+
+// K1s (+ its MEM instantiation) exactly as kgpu.cu launches them: order by free count, compact cache, grid.
+void emu_score_sparse(const int32_t *topo, const int32_t *free_mask, const int32_t *gpu_mem /*nullable*/, int64_t n,
+                      int64_t node_id_base, const int32_t *pods, int64_t P, const int32_t *W, int splits,
+                      unsigned long long *keys) {
+    std::memset(keys, 0xFF, (size_t)P * 8);
+    if (n == 0 || P == 0) return;
+    std::vector<int32_t> order;
+    for (int f = 8; f >= 0; f--) {
+        for (int64_t i = 0; i < n; i++)
+            if (__builtin_popcount((unsigned)free_mask[i] & 0xFFu) == f) order.push_back((int32_t)i);
+        while (order.size() % 32) order.push_back(-1);
+    }
+    while (order.size() % kgpu::SP_THREADS) order.push_back(-1);
+    int4 *topo4 = aligned_array<int4>((size_t)n * 16);
+    std::memcpy(topo4, topo, (size_t)n * 256);
+    int4 *pods4 = aligned_array<int4>((size_t)P);
+    std::memcpy(pods4, pods, (size_t)P * 16);
+    int32_t *mem = aligned_array<int32_t>((size_t)n * 8);
+    if (gpu_mem) std::memcpy(mem, gpu_mem, (size_t)n * 32); else std::memset(mem, 0x7F, (size_t)n * 32);
+    uint32_t *cpair = aligned_array<uint32_t>((size_t)n * 28);
+    uint32_t *perm = aligned_array<uint32_t>((size_t)n);
+    const kgpu::Weights Ws = weights_of(W);
+    emu::launch(dim3((unsigned)((n + kgpu::SP_THREADS - 1) / kgpu::SP_THREADS)), dim3(kgpu::SP_THREADS),
+                [&] { kgpu::compact_nodes(topo4, free_mask, n, Ws, cpair, perm); });
+    int flag = 0;
+    for (int64_t p = 0; p < P; p++) flag |= pods[4 * p + 3] > 0;
+    const dim3 grid((unsigned)(order.size() / kgpu::SP_THREADS), (unsigned)std::max(1, splits));
+    const int per = per_split(P, std::max(1, splits));
+    const int4 *cpair4 = reinterpret_cast<const int4 *>(cpair);
+    emu::launch(grid, dim3(kgpu::SP_THREADS), [&] {
+        kgpu::score_pairs_sparse<true, false>(cpair4, perm, free_mask, mem, order.data(), &flag, node_id_base, pods4, P, per, kPC, keys);
+    });
+    if (flag)
+        emu::launch(grid, dim3(kgpu::SP_THREADS), [&] {
+            kgpu::score_pairs_sparse<true, true>(cpair4, perm, free_mask, mem, order.data(), &flag, node_id_base, pods4, P, per, kPC, keys);
+        });
+    free(topo4); free(pods4); free(mem); free(cpair); free(perm);
+}
+
+// Dense K1 (+ K1m) as kgpu.cu launches them.
+void emu_score_dense(const int32_t *topo, const int32_t *free_mask, const int32_t *gpu_mem /*nullable*/, int64_t n,
+                     int64_t node_id_base, const int32_t *pods, int64_t P, const int32_t *W, int splits,
+                     unsigned long long *keys) {
+    std::memset(keys, 0xFF, (size_t)P * 8);
+    if (n == 0 || P == 0) return;
+    int4 *topo4 = aligned_array<int4>((size_t)n * 16);
+    std::memcpy(topo4, topo, (size_t)n * 256);
+    int4 *pods4 = aligned_array<int4>((size_t)P);
+    std::memcpy(pods4, pods, (size_t)P * 16);
+    int4 *mem4 = aligned_array<int4>((size_t)n * 2);
+    if (gpu_mem) std::memcpy(mem4, gpu_mem, (size_t)n * 32); else std::memset(mem4, 0x7F, (size_t)n * 32);
+    const kgpu::Weights Ws = weights_of(W);
+    int flag = 0;
+    for (int64_t p = 0; p < P; p++) flag |= pods[4 * p + 3] > 0;
+    const dim3 grid((unsigned)((n + kgpu::LPN_THREADS - 1) / kgpu::LPN_THREADS), (unsigned)std::max(1, splits));
+    const int per = per_split(P, std::max(1, splits));
+    emu::launch(grid, dim3(kgpu::LPN_THREADS), [&] {
+        kgpu::score_pairs_lane_per_node<true, false>(topo4, free_mask, mem4, &flag, n, node_id_base, pods4, P, per, Ws, kPC, keys);
+    });
+    if (flag)
+        emu::launch(grid, dim3(kgpu::LPN_THREADS), [&] {
+            kgpu::score_pairs_lane_per_node<true, true>(topo4, free_mask, mem4, &flag, n, node_id_base, pods4, P, per, Ws, kPC, keys);
+        });
+    free(topo4); free(pods4); free(mem4);
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+"""The kernel SOURCES (kubegpu_b200/csrc/score_pairs*.cuh + generated enumeration) compiled with g++ against a
+small CUDA shim (tests/emu/cuda_emu.h: one OS thread per CUDA thread, real barriers, emulated warp
+collectives) and run on the CPU against the oracle.  Small sizes only -- this is a logic check that works
+without a GPU (e.g. for kernel edits between GPU runs); bit-exactness on the B200 is tests/test_gpu_*.py."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from kubegpu_b200 import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "emu", "_build", "libkgpu_emu.so")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "emu")])
+    L = ctypes.CDLL(LIB)
+    i32p, u64p = ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint64)
+    for fn in (L.emu_score_sparse, L.emu_score_dense):
+        fn.restype = None
+        fn.argtypes = [i32p, i32p, i32p, ctypes.c_int64, ctypes.c_int64, i32p, ctypes.c_int64, i32p, ctypes.c_int, u64p]
+    return L
+
+
+def _run(fn, topo, free, pods, W, mem=None, base=0, splits=1):
+    topo, free, pods, W = (np.ascontiguousarray(a, dtype=np.int32) for a in (topo, free, pods, W))
+    P = pods.shape[0]
+    keys = np.empty(P, dtype=np.uint64)
+    p32 = ctypes.POINTER(ctypes.c_int32)
+    memp = None if mem is None else np.ascontiguousarray(mem, dtype=np.int32).ctypes.data_as(p32)
+    fn(topo.ctypes.data_as(p32), free.ctypes.data_as(p32), memp, free.shape[0], base, pods.ctypes.data_as(p32), P,
+       W.ctypes.data_as(p32), splits, keys.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)))
+    return keys
+
+
+@pytest.mark.parametrize("kernel", ["sparse", "dense"])
+def test_emulated_kernels_match_oracle(emu, oracle_b, kernel):
+    fn = emu.emu_score_sparse if kernel == "sparse" else emu.emu_score_dense
+    W = oracle_b.DEFAULT_WEIGHTS
+    # C1 fixture, a C4 sample with k in 1..8 plus invalid k, two pod splits, a node-id base
+    topo, free, pods = synth.gen_c1()
+    assert (_run(fn, topo, free, pods, W) == oracle_b.score_batch(topo, free, pods, W)).all()
+    topo, free, pods = synth.gen_c4(N=300, P=70)
+    pods[5, 0], pods[6, 0], pods[7, 0] = 0, 9, -3
+    want = oracle_b.score_batch(topo, free, pods, W, node_id_base=1000)
+    assert (_run(fn, topo, free, pods, W, base=1000, splits=2) == want).all()
+    # maximum weights (cost field at its largest) and everything free (K1s degenerates to the dense work)
+    wmax = np.full(16, 4095, dtype=np.int32)
+    full = np.full(130, 0xFF, dtype=np.int32)
+    p9 = synth.make_pods(np.arange(0, 9, dtype=np.int32))
+    assert (_run(fn, topo[:130], full, p9, wmax) == oracle_b.score_batch(topo[:130], full, p9, wmax)).all()
+
+
+@pytest.mark.parametrize("kernel", ["sparse", "dense"])
+def test_emulated_memory_aware_path(emu, oracle_b, kernel):
+    fn = emu.emu_score_sparse if kernel == "sparse" else emu.emu_score_dense
+    topo, free, mem, pods = synth.gen_c6(N=260, P=60)
+    want = oracle_b.score_batch(topo, free, pods, mem=mem)
+    assert (_run(fn, topo, free, pods, oracle_b.DEFAULT_WEIGHTS, mem=mem) == want).all()
+    assert (want != oracle_b.score_batch(topo, free, pods)).any()
