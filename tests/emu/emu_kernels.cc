@@ -9,6 +9,10 @@
 #include "score_pairs.cuh"
 #include "score_pairs_sparse.cuh"
 
+#ifndef EMU_BYTE_KEYS
+#define EMU_BYTE_KEYS true
+#endif
+
 namespace {
 
 const kgpu::PipeConsts kPC = {1u, 0xFFFFFFFFu};
@@ -66,11 +70,11 @@ void emu_score_sparse(const int32_t *topo, const int32_t *free_mask, const int32
     const int per = per_split(P, std::max(1, splits));
     const int4 *cpair4 = reinterpret_cast<const int4 *>(cpair);
     emu::launch(grid, dim3(kgpu::SP_THREADS), [&] {
-        kgpu::score_pairs_sparse<true, false>(cpair4, perm, free_mask, mem, order.data(), &flag, node_id_base, pods4, P, per, kPC, keys);
+        kgpu::score_pairs_sparse<true, false, EMU_BYTE_KEYS>(cpair4, perm, free_mask, mem, order.data(), &flag, node_id_base, pods4, P, per, kPC, keys);
     });
     if (flag)
         emu::launch(grid, dim3(kgpu::SP_THREADS), [&] {
-            kgpu::score_pairs_sparse<true, true>(cpair4, perm, free_mask, mem, order.data(), &flag, node_id_base, pods4, P, per, kPC, keys);
+            kgpu::score_pairs_sparse<true, true, EMU_BYTE_KEYS>(cpair4, perm, free_mask, mem, order.data(), &flag, node_id_base, pods4, P, per, kPC, keys);
         });
     free(topo4); free(pods4); free(mem); free(cpair); free(perm);
 }
