@@ -8,6 +8,7 @@
 
 #include "score_pairs.cuh"
 #include "score_pairs_sparse.cuh"
+#include "place_sequential.cuh"
 
 #ifndef EMU_BYTE_KEYS
 #define EMU_BYTE_KEYS true
@@ -104,6 +105,103 @@ void emu_score_dense(const int32_t *topo, const int32_t *free_mask, const int32_
             kgpu::score_pairs_lane_per_node<true, true>(topo4, free_mask, mem4, &flag, n, node_id_base, pods4, P, per, Ws, kPC, keys);
         });
     free(topo4); free(pods4); free(mem4);
+}
+
+// The other K1 variants as kgpu.cu launches them: 1 = warp per pair (north_star mapping), 3 = memo by k,
+// 4 = tile memo.  Memory-constrained pods go to K1m for variants 3 and 4, inline for variant 1.
+void emu_score_variant(int variant, const int32_t *topo, const int32_t *free_mask, const int32_t *gpu_mem, int64_t n,
+                       int64_t node_id_base, const int32_t *pods, int64_t P, const int32_t *W, int splits,
+                       unsigned long long *keys) {
+    std::memset(keys, 0xFF, (size_t)P * 8);
+    if (n == 0 || P == 0) return;
+    for (int k = 0; k <= 8; k++) {                       // what upload_subset_tables() puts in constant memory
+        int c = 0;
+        for (unsigned S = 0; S < 256; S++)
+            if (__builtin_popcount(S) == k) kgpu::c_subsets[k][c++] = (uint8_t)S;
+        kgpu::c_nsub[k] = (uint8_t)c;
+    }
+    int4 *topo4 = aligned_array<int4>((size_t)n * 16);
+    std::memcpy(topo4, topo, (size_t)n * 256);
+    int4 *pods4 = aligned_array<int4>((size_t)P);
+    std::memcpy(pods4, pods, (size_t)P * 16);
+    int32_t *mem = aligned_array<int32_t>((size_t)n * 8);
+    if (gpu_mem) std::memcpy(mem, gpu_mem, (size_t)n * 32); else std::memset(mem, 0x7F, (size_t)n * 32);
+    const int4 *mem4 = reinterpret_cast<const int4 *>(mem);
+    const kgpu::Weights Ws = weights_of(W);
+    int flag = 0;
+    emu::launch(dim3((unsigned)((P + 255) / 256)), dim3(256), [&] { kgpu::any_mem_pod(pods4, P, &flag); });
+    const int per = per_split(P, std::max(1, splits));
+    if (variant == 1) {
+        const dim3 grid((unsigned)((n + kgpu::WPP_TILE - 1) / kgpu::WPP_TILE), (unsigned)std::max(1, splits));
+        emu::launch(grid, dim3(kgpu::WPP_THREADS), [&] {
+            kgpu::score_pairs_warp_per_pair(topo4, free_mask, mem, n, node_id_base, pods4, P, per, Ws, kPC, keys);
+        });
+    } else {
+        const dim3 grid((unsigned)((n + kgpu::LPN_THREADS - 1) / kgpu::LPN_THREADS), (unsigned)std::max(1, splits));
+        if (variant == 3) {
+            unsigned long long bestk[9];
+            std::memset(bestk, 0xFF, sizeof bestk);
+            emu::launch(dim3(std::min<unsigned>(grid.x, 3)), dim3(kgpu::LPN_THREADS),
+                        [&] { kgpu::memo_best_by_k(topo4, free_mask, n, node_id_base, Ws, kPC, bestk); });
+            emu::launch(dim3((unsigned)((P + 255) / 256)), dim3(256), [&] { kgpu::memo_gather(pods4, P, bestk, keys); });
+        } else {
+            emu::launch(grid, dim3(kgpu::LPN_THREADS), [&] {
+                kgpu::score_pairs_lane_per_node<false, false>(topo4, free_mask, mem4, &flag, n, node_id_base, pods4, P, per, Ws, kPC, keys);
+            });
+        }
+        if (flag)
+            emu::launch(grid, dim3(kgpu::LPN_THREADS), [&] {
+                kgpu::score_pairs_lane_per_node<true, true>(topo4, free_mask, mem4, &flag, n, node_id_base, pods4, P, per, Ws, kPC, keys);
+            });
+    }
+    free(topo4); free(pods4); free(mem);
+}
+
+// K2
+void emu_reduce_shards(const unsigned long long *gathered, int G, int64_t P, unsigned long long *out) {
+    emu::launch(dim3((unsigned)((P + 255) / 256)), dim3(256), [&] { kgpu::reduce_shards(gathered, G, P, out); });
+}
+
+// kgpu_score_pairs
+void emu_score_pair_list(const int32_t *topo, const int32_t *free_mask, const int32_t *gpu_mem, int64_t n,
+                         const long long *node_idx, const int32_t *ks, const int32_t *min_mem, int64_t m, const int32_t *W,
+                         uint32_t *out) {
+    int4 *topo4 = aligned_array<int4>((size_t)n * 16);
+    std::memcpy(topo4, topo, (size_t)n * 256);
+    int32_t *mem = aligned_array<int32_t>((size_t)n * 8);
+    if (gpu_mem) std::memcpy(mem, gpu_mem, (size_t)n * 32); else std::memset(mem, 0x7F, (size_t)n * 32);
+    const kgpu::Weights Ws = weights_of(W);
+    emu::launch(dim3((unsigned)((m + 127) / 128)), dim3(128),
+                [&] { kgpu::score_pair_list(topo4, free_mask, mem, n, node_idx, ks, min_mem, m, Ws, kPC, out); });
+    free(topo4); free(mem);
+}
+
+// K3: place_init + place_sequential; free_mask is updated in place like the device copy.
+void emu_place_batch(const int32_t *topo, int32_t *free_mask, int64_t n, int64_t node_id_base, const int32_t *pods,
+                     int64_t P, const int32_t *W, unsigned long long *keys) {
+    std::memset(keys, 0xFF, (size_t)P * 8);
+    if (n == 0 || P == 0) return;
+    for (int k = 0; k <= 8; k++) {
+        int c = 0;
+        for (unsigned S = 0; S < 256; S++)
+            if (__builtin_popcount(S) == k) kgpu::c_subsets[k][c++] = (uint8_t)S;
+        kgpu::c_nsub[k] = (uint8_t)c;
+    }
+    int4 *topo4 = aligned_array<int4>((size_t)n * 16);
+    std::memcpy(topo4, topo, (size_t)n * 256);
+    int4 *pods4 = aligned_array<int4>((size_t)P);
+    std::memcpy(pods4, pods, (size_t)P * 16);
+    const int64_t T = (n + kgpu::PLACE_TILE - 1) / kgpu::PLACE_TILE, Npad = T * kgpu::PLACE_TILE;
+    uint32_t *nodebest = aligned_array<uint32_t>((size_t)Npad * 9);
+    unsigned long long *tilebest = aligned_array<unsigned long long>((size_t)T * 9);
+    const kgpu::Weights Ws = weights_of(W);
+    emu::launch(dim3((unsigned)T), dim3(kgpu::PLACE_TILE),
+                [&] { kgpu::place_init(topo4, free_mask, n, Npad, node_id_base, Ws, kPC, nodebest, tilebest, T); });
+    emu::launch(dim3(1), dim3(kgpu::PLACE_THREADS), [&] {
+        kgpu::place_sequential(reinterpret_cast<const int32_t *>(topo4), free_mask, n, Npad, node_id_base, pods4, P, Ws, nodebest,
+                               tilebest, T, keys);
+    });
+    free(topo4); free(pods4); free(nodebest); free(tilebest);
 }
 
 }  // extern "C"

@@ -62,3 +62,67 @@ def test_emulated_memory_aware_path(emu, oracle_b, kernel):
     want = oracle_b.score_batch(topo, free, pods, mem=mem)
     assert (_run(fn, topo, free, pods, oracle_b.DEFAULT_WEIGHTS, mem=mem) == want).all()
     assert (want != oracle_b.score_batch(topo, free, pods)).any()
+
+
+def _p(a, t=ctypes.c_int32):
+    return a.ctypes.data_as(ctypes.POINTER(t))
+
+
+@pytest.mark.parametrize("variant", [1, 3, 4])
+def test_emulated_other_variants_match_oracle(emu, oracle_b, variant):
+    """warp-per-pair (the north_star mapping), memo-by-k and tile-memo, incl. their memory-aware routes."""
+    emu.emu_score_variant.restype = None
+    W = np.ascontiguousarray(oracle_b.DEFAULT_WEIGHTS, dtype=np.int32)
+    topo, free, mem, pods = synth.gen_c6(N=200, P=40)
+    pods[3, 0], pods[4, 0] = 0, 11
+    for use_mem in (False, True):
+        pp = pods.copy()
+        if not use_mem:
+            pp[:, 3] = 0
+        keys = np.empty(len(pp), dtype=np.uint64)
+        emu.emu_score_variant(variant, _p(topo), _p(free), _p(mem), ctypes.c_int64(len(free)), ctypes.c_int64(77), _p(pp),
+                              ctypes.c_int64(len(pp)), _p(W), 2, _p(keys, ctypes.c_uint64))
+        want = oracle_b.score_batch(topo, free, pp, W, node_id_base=77, mem=mem)
+        assert (keys == want).all(), (variant, use_mem)
+
+
+def test_emulated_reduce_shards(emu, oracle_b):
+    emu.emu_reduce_shards.restype = None
+    rng = np.random.default_rng(5)
+    g = rng.integers(0, 2**63, size=(4, 300), dtype=np.uint64)
+    g[:, 7] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    out = np.empty(300, dtype=np.uint64)
+    emu.emu_reduce_shards(_p(g, ctypes.c_uint64), 4, ctypes.c_int64(300), _p(out, ctypes.c_uint64))
+    assert (out == g.min(axis=0)).all()
+
+
+def test_emulated_pair_list(emu, oracle_b):
+    emu.emu_score_pair_list.restype = None
+    W = np.ascontiguousarray(oracle_b.DEFAULT_WEIGHTS, dtype=np.int32)
+    topo, free, mem, pods = synth.gen_c6(N=150, P=150)
+    rng = np.random.default_rng(6)
+    idx = rng.integers(0, 150, size=150).astype(np.int64)
+    ks = np.ascontiguousarray(pods[:, 0]); mm = np.ascontiguousarray(pods[:, 3])
+    out = np.empty(150, dtype=np.uint32)
+    emu.emu_score_pair_list(_p(topo), _p(free), _p(mem), ctypes.c_int64(150), _p(idx, ctypes.c_longlong), _p(ks), _p(mm),
+                            ctypes.c_int64(150), _p(W), _p(out, ctypes.c_uint32))
+    for i in range(150):
+        one = np.array([[ks[i], 0, 0, mm[i]]], dtype=np.int32)
+        want = oracle_b.score_batch(topo[idx[i]:idx[i] + 1], free[idx[i]:idx[i] + 1], one, W, mem=mem[idx[i]:idx[i] + 1])[0]
+        got = 0xFFFFFFFF if want == 0xFFFFFFFFFFFFFFFF else ((int(want) >> 40) << 8) | (int(want) & 0xFF)
+        assert int(out[i]) == got, i
+
+
+def test_emulated_sequential_placement(emu, oracle_b):
+    """K3 (place_init + the persistent place_sequential block) against the stateful oracle."""
+    emu.emu_place_batch.restype = None
+    W = np.ascontiguousarray(oracle_b.DEFAULT_WEIGHTS, dtype=np.int32)
+    topo, free, pods = synth.gen_c4(N=300, P=120)
+    pods[9, 0] = 0
+    f_emu = free.copy()
+    keys = np.empty(len(pods), dtype=np.uint64)
+    emu.emu_place_batch(_p(topo), _p(f_emu), ctypes.c_int64(len(free)), ctypes.c_int64(5), _p(pods), ctypes.c_int64(len(pods)),
+                        _p(W), _p(keys, ctypes.c_uint64))
+    want_keys, want_free = oracle_b.place_batch(topo, free.copy(), pods, W, node_id_base=5)
+    assert (keys == want_keys).all()
+    assert (f_emu == want_free).all()
