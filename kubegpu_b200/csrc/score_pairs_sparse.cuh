@@ -30,9 +30,19 @@ constexpr int SP_ROW = 29;          // padded row of 28 pair costs per lane in s
 #ifndef KGPU_SP_UNROLL
 #define KGPU_SP_UNROLL 1          // pods per trip of a (K,F) bucket loop
 #endif
+#ifndef KGPU_SP_UNROLL_SMALL
+#define KGPU_SP_UNROLL_SMALL KGPU_SP_UNROLL   // the same for the loops that enumerate <= KGPU_SP_SMALL subsets
+#endif
+#ifndef KGPU_SP_SMALL
+#define KGPU_SP_SMALL 6
+#endif
 #define KGPU_PRAGMA(x) _Pragma(#x)
 #define KGPU_UNROLL(n) KGPU_PRAGMA(unroll n)
 
+__host__ __device__ constexpr int sp_choose(int n, int k) { return k == 0 ? 1 : sp_choose(n - 1, k - 1) * n / k; }
+__host__ __device__ constexpr int sp_unroll(int K, int F) {
+    return (K <= 1 || sp_choose(F, K) <= KGPU_SP_SMALL) ? KGPU_SP_UNROLL_SMALL : KGPU_SP_UNROLL;
+}
 __host__ __device__ constexpr int sp_pidx(int i, int j) { return 7 * i - i * (i - 1) / 2 + (j - i - 1); }  // i<j
 
 template <int K, int F>
@@ -42,25 +52,52 @@ __device__ __forceinline__ uint32_t node_key_kf(const PairCosts &C, const PipeCo
     return best_kf<(K < 2 ? 2 : K), (F < 2 ? 2 : F)>(C, pc);
 }
 
+// Per-warp pod table of a chunk, in BUCKET order (pods grouped by k): the per-pod multiplier the
+// enumeration runs on (see score_pairs.cuh: it makes every instruction of the enumeration depend on
+// per-pod data) next to the slot the warp's result for that pod goes to.  A bucket loop walks one
+// pointer over this table: LDS [ptr], ..., STS [ptr + 4].
+struct alignas(8) SpEnt {
+    uint32_t one;       // MEM: the pod's min_mem instead (the MEM loops derive `one` from K)
+    uint32_t best;      // warp key of the best (node, subset) of this warp for the pod, INF32 = none
+};
+
+// Warp key.  BYTE_KEYS (every cost < 2^16, i.e. every weight <= 2340): cost<<16 | lane<<8 | S, built
+// from the lane key (cost<<8 | S) with ONE PRMT whose selector also encodes "this lane cannot serve
+// k = K" (nfree < K, loop invariant): it then picks four 0xFF bytes = INF32.  Otherwise:
+// cost<<13 | lane<<8 | S with an IMAD for the shift and two LOP3.
+struct SpFmt {
+    uint32_t lane_hi;   // BYTE_KEYS: lane<<8 | 0xFFFF0000          else: feasible ? lane<<8 : 0xFFFFFFFF
+    uint32_t sel;       // BYTE_KEYS: feasible ? 0x2150 : 0x7777     else: unused
+};
+template <bool BYTE_KEYS>
+__device__ __forceinline__ SpFmt sp_fmt(uint32_t lane_field, bool feasible) {
+    SpFmt f;
+    if (BYTE_KEYS) { f.lane_hi = lane_field | 0xFFFF0000u; f.sel = feasible ? 0x2150u : 0x7777u; }
+    else           { f.lane_hi = feasible ? lane_field : 0xFFFFFFFFu; f.sel = 0u; }
+    return f;
+}
+template <bool BYTE_KEYS>
+__device__ __forceinline__ uint32_t sp_warp_key(uint32_t key, const SpFmt f, uint32_t thirty_two) {
+    if (BYTE_KEYS) return __byte_perm(key, f.lane_hi, f.sel);
+    return ((key * thirty_two) & 0xFFFFE000u) | ((key & 0xFFu) | f.lane_hi);
+}
+
 // One (K, F) loop: all pods of the chunk that want K GPUs, enumerating positions 0..F-1.
-// BYTE_KEYS (costs < 2^16, i.e. every weight <= 2340): the warp key is cost<<16 | lane<<8 | S, assembled
-// with one PRMT instead of shift / mask / or.
 template <int K, int F, bool PER_PAIR, bool MEM, bool BYTE_KEYS>
 __device__ __forceinline__ void sp_bucket(const PairCosts &C, const PipeConsts pc, uint32_t nfree, bool valid,
-                                          const int32_t (&mem)[8], uint32_t lane_field, const uint16_t *sIdx,
-                                          const uint8_t *sK, const int32_t *sMin, int begin, int end, uint32_t *sBestW) {
-    KGPU_UNROLL(KGPU_SP_UNROLL)
-    for (int i = begin; i < end; i++) {
-        const uint32_t word = sIdx[i];             // chunk position (9 bits) | the pod's k << 9
-        const int p = (int)(word & (SP_CHUNK - 1));
+                                          const int32_t (&mem)[8], uint32_t lane_field, SpEnt *tab, int begin, int end) {
+    // (begin >> 30) is 0; tying the test to this chunk's bucket offset keeps the compiler from hoisting the
+    // nine per-K selectors to the top of the kernel, where they cost nine registers for the whole run.
+    const uint32_t need_free = (uint32_t)K + ((uint32_t)begin >> 30);
+    const SpFmt fmt = sp_fmt<BYTE_KEYS>(lane_field, MEM ? true : (valid && nfree >= need_free));
+    const uint32_t thirty_two = pc.one << 5;       // a register, so that the shift is an IMAD (kernel parameter: opaque)
+    KGPU_UNROLL((sp_unroll(K, F)))
+    for (int i = begin; i < end; i++) {            // begin, end: warp-uniform (read from shared memory)
+        SpEnt *const ent = tab + i;
         PipeConsts pcl = pc;
-        if (PER_PAIR && !MEM) {                    // un-hoistable per-pair work: see score_pairs.cuh
-            pcl.one = (word >> 9) - (uint32_t)(K - 1);
-            pcl.minus_one = 0u - pcl.one;
-        }
-        uint32_t key;
+        uint32_t v;
         if (MEM) {
-            const int32_t need = sMin[p];
+            const int32_t need = (int32_t)ent->one;
             uint32_t pen[8], elig = 0;
 #pragma unroll
             for (int g = 0; g < 8; g++) {
@@ -68,6 +105,7 @@ __device__ __forceinline__ void sp_bucket(const PairCosts &C, const PipeConsts p
                 pen[g] = lt ? PEN : 0u;
                 if (!lt && (uint32_t)g < nfree) elig |= 1u << g;      // position g: free and big enough
             }
+            uint32_t key;
             if (K == 0) key = valid ? 0u : INF32;
             else if (K == 1) key = elig ? (elig & (0u - elig)) : INF32;
             else {
@@ -75,28 +113,31 @@ __device__ __forceinline__ void sp_bucket(const PairCosts &C, const PipeConsts p
                 apply_pens(C, C2, pen);
                 key = best_kf<(K < 2 ? 2 : K), (F < 2 ? 2 : F)>(C2, pcl);
             }
+            v = key >= PEN ? INF32 : sp_warp_key<BYTE_KEYS>(key, fmt, thirty_two);
         } else {
-            key = node_key_kf<K, F>(C, pcl, nfree, valid);
+            if (PER_PAIR) {                        // un-hoistable per-pair work: see score_pairs.cuh
+                pcl.one = ent->one;
+                if (K >= 5) pcl.minus_one = 0u - pcl.one;
+            }
+            // lanes that cannot serve K (fmt says so) compute a key like the others and drop it
+            const uint32_t key = K == 0 ? 0u : K == 1 ? pcl.one : best_kf<(K < 2 ? 2 : K), (F < 2 ? 2 : F)>(C, pcl);
+            v = sp_warp_key<BYTE_KEYS>(key, fmt, thirty_two);
         }
-        const uint32_t v = key >= PEN ? INF32
-                           : BYTE_KEYS ? __byte_perm(key, lane_field, 0x2150)      // [cost_hi, cost_lo, lane, S]
-                                       : (((key & ~0xFFu) << 5) | lane_field | (key & 0xFFu));
         const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, v);
-        if (lane_field == 0) sBestW[p] = m;
+        if (lane_field == 0) ent->best = m;
     }
 }
 
 template <int K, bool PER_PAIR, bool MEM, bool BYTE_KEYS>
 __device__ __forceinline__ void sp_run_k(int F, const PairCosts &C, const PipeConsts pc, uint32_t nfree, bool valid,
-                                         const int32_t (&mem)[8], uint32_t lane_field, const uint16_t *sIdx,
-                                         const uint8_t *sK, const int32_t *sMin, int begin, int end, uint32_t *sBestW) {
+                                         const int32_t (&mem)[8], uint32_t lane_field, SpEnt *tab, int begin, int end) {
     if (begin >= end || F < K) return;             // F < K: no lane of this warp has K free GPUs
 #define KGPU_SP_CASE(FF)                                                                                         \
     case FF:                                                                                                     \
-        if (FF >= K) sp_bucket<K, (FF >= K ? FF : K), PER_PAIR, MEM, BYTE_KEYS>(C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, begin, end, sBestW); \
+        if (FF >= K) sp_bucket<K, (FF >= K ? FF : K), PER_PAIR, MEM, BYTE_KEYS>(C, pc, nfree, valid, mem, lane_field, tab, begin, end); \
         break;
     if (K <= 1) {                                  // F does not matter for k = 0, 1
-        sp_bucket<K, 8, PER_PAIR, MEM, BYTE_KEYS>(C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, begin, end, sBestW);
+        sp_bucket<K, 8, PER_PAIR, MEM, BYTE_KEYS>(C, pc, nfree, valid, mem, lane_field, tab, begin, end);
         return;
     }
     switch (F) {
@@ -181,14 +222,13 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
     if (MEM && *mem_flag == 0) return;
     __shared__ int32_t sCnt[10], sOff[11];
     __shared__ uint8_t sK[SP_CHUNK];
-    __shared__ uint16_t sIdx[SP_CHUNK];
-    __shared__ uint32_t sBest[SP_WARPS][SP_CHUNK];
-    __shared__ int32_t sMin[MEM ? SP_CHUNK : 1];
+    __shared__ uint16_t sIdx[SP_CHUNK];                // bucket order -> chunk position
+    __shared__ SpEnt sTab[SP_WARPS][SP_CHUNK];         // per warp, bucket order: multiplier | result
     __shared__ uint32_t sPerm[SP_THREADS];             // position -> GPU index, 8 nibbles
     __shared__ int32_t sNode[SP_THREADS];              // slot -> node index (-1 = padding)
 
     const int tid = threadIdx.x;
-    uint32_t *const sBestW = sBest[tid >> 5];
+    SpEnt *const tab = sTab[tid >> 5];
     const uint32_t lane_field = (uint32_t)(tid & 31) << 8;
 
     // ---- staging: the node's compacted pair costs (7 x 16 B), permutation and free count ----------
@@ -236,10 +276,7 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
             const bool wants_mem = req.w > 0;
             const int b = (req.x < 0 || req.x > 8 || wants_mem != MEM) ? 9 : req.x;
             sK[i] = (uint8_t)b;
-            if (MEM) sMin[i] = req.w;
             atomicAdd(&sCnt[b], 1);
-#pragma unroll
-            for (int w = 0; w < SP_WARPS; w++) sBest[w][i] = INF32;      // warps skip the pods they cannot serve
         }
         __syncthreads();
         if (tid == 0) {
@@ -249,31 +286,41 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
             sOff[10] = acc;
         }
         __syncthreads();
-        for (int i = tid; i < cn; i += SP_THREADS) sIdx[atomicAdd(&sCnt[sK[i]], 1)] = (uint16_t)(i | ((int)sK[i] << 9));
+        for (int i = tid; i < cn; i += SP_THREADS) {
+            const int b = sK[i];
+            const int at = atomicAdd(&sCnt[b], 1);
+            sIdx[at] = (uint16_t)i;
+            SpEnt e;
+            // the per-pod multiplier: the pod's own k less what its bucket adds back (= 1 at run time)
+            e.one = MEM ? (uint32_t)__ldg(pods4 + c0 + i).w : (uint32_t)(__ldg(pods4 + c0 + i).x - (b < 9 ? b - 1 : 0));
+            e.best = INF32;                                          // warps skip the pods they cannot serve
+#pragma unroll
+            for (int w = 0; w < SP_WARPS; w++) sTab[w][at] = e;
+        }
         __syncthreads();
 
-        sp_run_k<0, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[0], sOff[1], sBestW);
-        sp_run_k<1, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[1], sOff[2], sBestW);
-        sp_run_k<2, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[2], sOff[3], sBestW);
-        sp_run_k<3, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[3], sOff[4], sBestW);
-        sp_run_k<4, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[4], sOff[5], sBestW);
-        sp_run_k<5, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[5], sOff[6], sBestW);
-        sp_run_k<6, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[6], sOff[7], sBestW);
-        sp_run_k<7, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[7], sOff[8], sBestW);
-        sp_run_k<8, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[8], sOff[9], sBestW);
+        sp_run_k<0, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[0], sOff[1]);
+        sp_run_k<1, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[1], sOff[2]);
+        sp_run_k<2, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[2], sOff[3]);
+        sp_run_k<3, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[3], sOff[4]);
+        sp_run_k<4, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[4], sOff[5]);
+        sp_run_k<5, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[5], sOff[6]);
+        sp_run_k<6, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[6], sOff[7]);
+        sp_run_k<7, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[7], sOff[8]);
+        sp_run_k<8, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[8], sOff[9]);
         __syncthreads();
 
         // block result per pod: min over the 4 warps of (cost, node id) -- a tile may hold warps of two
         // adjacent classes, so node ids are compared explicitly -- then S' -> real GPU mask through the
         // winner's permutation, and REDG.MIN.64 into keys[pod].
-        for (int i = tid; i < cn; i += SP_THREADS) {
-            if (sK[i] == 9) continue;
+        const int served = sOff[9];                // bucket 9 (not for this launch) sits at the end
+        for (int i = tid; i < served; i += SP_THREADS) {
             unsigned long long best = ~0ull;       // cost<<40 | node_index<<8 | slot_in_tile... (slot kept aside)
             int best_slot = -1;
             uint32_t best_m = 0;
 #pragma unroll
             for (int w = 0; w < SP_WARPS; w++) {
-                const uint32_t m = sBest[w][i];
+                const uint32_t m = sTab[w][i].best;
                 if (m == INF32) continue;
                 const int s = w * 32 + (int)((m >> 8) & 31u);
                 const unsigned long long cand = ((unsigned long long)(m >> (BYTE_KEYS ? 16 : 13)) << 32) | (uint32_t)sNode[s];
@@ -286,7 +333,7 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
                 for (int g = 0; g < 8; g++)
                     if ((best_m >> g) & 1u) S |= 1u << ((pm >> (4 * g)) & 7u);
                 const unsigned long long nid = (unsigned long long)(node_id_base + (long long)(best & 0xFFFFFFFFull));
-                atomicMin(&keys[c0 + i], ((best >> 32) << 40) | (nid << 8) | S);
+                atomicMin(&keys[c0 + sIdx[i]], ((best >> 32) << 40) | (nid << 8) | S);
             }
         }
     }

@@ -10,9 +10,6 @@
 #include "score_pairs_sparse.cuh"
 #include "place_sequential.cuh"
 
-#ifndef EMU_BYTE_KEYS
-#define EMU_BYTE_KEYS true
-#endif
 
 namespace {
 
@@ -70,13 +67,15 @@ void emu_score_sparse(const int32_t *topo, const int32_t *free_mask, const int32
     const dim3 grid((unsigned)(order.size() / kgpu::SP_THREADS), (unsigned)std::max(1, splits));
     const int per = per_split(P, std::max(1, splits));
     const int4 *cpair4 = reinterpret_cast<const int4 *>(cpair);
-    emu::launch(grid, dim3(kgpu::SP_THREADS), [&] {
-        kgpu::score_pairs_sparse<true, false, EMU_BYTE_KEYS>(cpair4, perm, free_mask, mem, order.data(), &flag, node_id_base, pods4, P, per, kPC, keys);
-    });
-    if (flag)
-        emu::launch(grid, dim3(kgpu::SP_THREADS), [&] {
-            kgpu::score_pairs_sparse<true, true, EMU_BYTE_KEYS>(cpair4, perm, free_mask, mem, order.data(), &flag, node_id_base, pods4, P, per, kPC, keys);
-        });
+    bool byte_keys = true;                               // kgpu.cu: every cost < 2^16
+    for (int i = 0; i < 16; i++) byte_keys = byte_keys && W[i] <= 2340;
+#define EMU_SPARSE(MEMF, BK)                                                                                   \
+    emu::launch(grid, dim3(kgpu::SP_THREADS), [&] {                                                            \
+        kgpu::score_pairs_sparse<true, MEMF, BK>(cpair4, perm, free_mask, mem, order.data(), &flag, node_id_base, pods4, P, per, kPC, keys); \
+    })
+    if (byte_keys) EMU_SPARSE(false, true); else EMU_SPARSE(false, false);
+    if (flag) { if (byte_keys) EMU_SPARSE(true, true); else EMU_SPARSE(true, false); }
+#undef EMU_SPARSE
     free(topo4); free(pods4); free(mem); free(cpair); free(perm);
 }
 

@@ -126,3 +126,13 @@ def test_emulated_sequential_placement(emu, oracle_b):
     want_keys, want_free = oracle_b.place_batch(topo, free.copy(), pods, W, node_id_base=5)
     assert (keys == want_keys).all()
     assert (f_emu == want_free).all()
+
+
+@pytest.mark.parametrize("wmax", [2340, 2341])
+def test_emulated_sparse_warp_key_layouts(emu, oracle_b, wmax):
+    """2340 is the largest weight served by the byte-aligned warp key (cost < 2^16), 2341 the first that
+    takes the general layout; both with ragged free masks so warps mix lanes that can and cannot serve k."""
+    topo, free, pods = synth.gen_c4(N=400, P=90, seed=77)
+    W = np.array([wmax - i for i in range(16)], dtype=np.int32)
+    want = oracle_b.score_batch(topo, free, pods, W, node_id_base=3)
+    assert (_run(emu.emu_score_sparse, topo, free, pods, W, base=3, splits=3) == want).all()
