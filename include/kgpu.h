@@ -150,8 +150,9 @@ int kgpu_score_pairs(kgpu_t *h, const int64_t *node_idx, const int32_t *k, const
 /* Stateful sequential placement (what TakePodResources would make of a scheduling cycle;
  * a no-op in the reference, gpu_scheduler.go:57-63).  Pods are placed IN ORDER; each one gets
  * the best (cost, node, mask) under the free masks left by the pods before it and then takes
- * those GPUs: the handle's device-side free masks are updated.  Host buffers, synchronous,
- * single-device handles only. */
+ * those GPUs: the handle's device-side free masks are updated.  min_mem_mib is honoured like
+ * in kgpu_score_batch; one batch may carry at most 7 distinct positive min_mem_mib values
+ * (KGPU_ERR_INVALID otherwise).  Host buffers, synchronous, single-device handles only. */
 int kgpu_place_batch(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_keys);
 /* Copy the current free masks (n = kgpu_num_nodes entries) back to the host. */
 int kgpu_get_free_masks(kgpu_t *h, int32_t *out_free_mask, int64_t n);

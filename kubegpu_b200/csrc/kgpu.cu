@@ -51,8 +51,8 @@ struct kgpu_shard {
     unsigned long long *d_keys = nullptr;    // [pcap]
     unsigned long long *d_gather = nullptr;  // [ndev][pcap] (multi-device only)
     unsigned long long *d_bestk = nullptr;   // [9] memo variant
-    uint32_t *d_nodebest = nullptr;          // [9][Npad]  K3 tables
-    unsigned long long *d_tilebest = nullptr;   // [9][T]
+    uint32_t *d_nodebest = nullptr;          // [views][9][Npad]  K3 tables
+    unsigned long long *d_tilebest = nullptr;   // [views][9][T]
     int64_t place_cap = 0;
     int64_t pcap = 0;
 };
@@ -555,8 +555,20 @@ int kgpu_place_batch(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_ke
     if (h->shards.size() != 1) return fail(h, KGPU_ERR_STATE, "kgpu_place_batch: needs a single-device handle");
     if (P < 0 || (P > 0 && (!pods || !out_keys))) return fail(h, KGPU_ERR_INVALID, "kgpu_place_batch: bad arguments");
     if (P == 0) return KGPU_OK;
-    for (int64_t p = 0; p < P; p++)
-        if (pods[4 * p + 3] > 0) return fail(h, KGPU_ERR_INVALID, "kgpu_place_batch: pod %lld has min_mem > 0 (not supported by the sequential path yet)", (long long)p);
+    // the batch's distinct memory requirements are the views the sequential kernels keep tables for
+    kgpu::PlaceViews views;
+    memset(&views, 0, sizeof views);
+    views.n = 1;
+    for (int64_t p = 0; p < P; p++) {
+        const int32_t need = pods[4 * p + 3];
+        if (need <= 0 || pods[4 * p] < 0 || pods[4 * p] > 8) continue;
+        bool seen = false;
+        for (int j = 1; j < views.n; j++) seen = seen || views.min_mem[j] == need;
+        if (seen) continue;
+        if (views.n == kgpu::PLACE_MAX_VIEWS)
+            return fail(h, KGPU_ERR_INVALID, "kgpu_place_batch: more than %d distinct min_mem values in one batch", kgpu::PLACE_MAX_VIEWS - 1);
+        views.min_mem[views.n++] = need;
+    }
     kgpu_shard &s = h->shards[0];
     int rc = ensure_pod_capacity(h, s, P);
     if (rc != KGPU_OK) return rc;
@@ -566,22 +578,23 @@ int kgpu_place_batch(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_ke
         KGPU_CUDA(h, cudaMemsetAsync(s.d_keys, 0xFF, (size_t)P * 8, s.stream));
     } else {
         const int64_t T = (s.n + kgpu::PLACE_TILE - 1) / kgpu::PLACE_TILE, Npad = T * kgpu::PLACE_TILE;
-        if (Npad > s.place_cap) {
+        if (Npad * views.n > s.place_cap) {
             if (s.d_nodebest) cudaFree(s.d_nodebest);
             if (s.d_tilebest) cudaFree(s.d_tilebest);
             s.d_nodebest = nullptr; s.d_tilebest = nullptr; s.place_cap = 0;
-            KGPU_CUDA(h, cudaMalloc(&s.d_nodebest, (size_t)Npad * 9 * 4));
-            KGPU_CUDA(h, cudaMalloc(&s.d_tilebest, (size_t)T * 9 * 8));
-            s.place_cap = Npad;
+            KGPU_CUDA(h, cudaMalloc(&s.d_nodebest, (size_t)Npad * views.n * 9 * 4));
+            KGPU_CUDA(h, cudaMalloc(&s.d_tilebest, (size_t)T * views.n * 9 * 8));
+            s.place_cap = Npad * views.n;
         }
         kgpu::Weights W;
         memcpy(W.w, h->W, sizeof W.w);
         KGPU_CUDA(h, cudaEventRecord(s.ev0, s.stream));
-        kgpu::place_init<<<(unsigned)T, kgpu::PLACE_TILE, 0, s.stream>>>(reinterpret_cast<const int4 *>(s.d_topo), s.d_free, s.n, Npad,
-                                                                        s.node_id_base, W, PC, s.d_nodebest, s.d_tilebest, T);
-        kgpu::place_sequential<<<1, kgpu::PLACE_THREADS, 0, s.stream>>>(s.d_topo, s.d_free, s.n, Npad, s.node_id_base,
-                                                                        reinterpret_cast<const int4 *>(s.d_pods), P, W, s.d_nodebest,
-                                                                        s.d_tilebest, T, s.d_keys);
+        kgpu::place_init<<<dim3((unsigned)T, (unsigned)views.n), kgpu::PLACE_TILE, 0, s.stream>>>(
+            reinterpret_cast<const int4 *>(s.d_topo), s.d_free, s.d_mem, s.n, Npad, s.node_id_base, W, PC, views, s.d_nodebest,
+            s.d_tilebest, T);
+        kgpu::place_sequential<<<1, kgpu::PLACE_THREADS, 0, s.stream>>>(s.d_topo, s.d_free, s.d_mem, s.n, Npad, s.node_id_base,
+                                                                        reinterpret_cast<const int4 *>(s.d_pods), P, W, views,
+                                                                        s.d_nodebest, s.d_tilebest, T, s.d_keys);
         h->launches += 2;
         s.compact_dirty = true;          // the free masks have changed on the device
         KGPU_CUDA(h, cudaGetLastError());

@@ -122,7 +122,7 @@ inline T warp_read(T v, int src_lane) {  // every lane contributes v and reads l
 
 // ---- synchronisation and warp collectives ---------------------------------------------------------
 inline void __syncthreads() { emu::ctx.block->bar.arrive_and_wait(); }
-inline void __syncwarp(unsigned = 0xFFFFFFFFu) {}
+inline void __syncwarp(unsigned = 0xFFFFFFFFu) { emu::my_warp().bar.arrive_and_wait(); }
 inline int __syncthreads_or(int pred) {
     emu::Block &b = *emu::ctx.block;
     b.bar.arrive_and_wait();

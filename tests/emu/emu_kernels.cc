@@ -175,11 +175,24 @@ void emu_score_pair_list(const int32_t *topo, const int32_t *free_mask, const in
     free(topo4); free(mem);
 }
 
-// K3: place_init + place_sequential; free_mask is updated in place like the device copy.
-void emu_place_batch(const int32_t *topo, int32_t *free_mask, int64_t n, int64_t node_id_base, const int32_t *pods,
-                     int64_t P, const int32_t *W, unsigned long long *keys) {
+// K3: place_init + place_sequential as kgpu_place_batch launches them (views from the batch's distinct
+// min_mem values); free_mask is updated in place like the device copy.  Returns 0, or -1 for too many views.
+int emu_place_batch(const int32_t *topo, int32_t *free_mask, const int32_t *gpu_mem /*nullable*/, int64_t n,
+                    int64_t node_id_base, const int32_t *pods, int64_t P, const int32_t *W, unsigned long long *keys) {
     std::memset(keys, 0xFF, (size_t)P * 8);
-    if (n == 0 || P == 0) return;
+    if (n == 0 || P == 0) return 0;
+    kgpu::PlaceViews views;
+    std::memset(&views, 0, sizeof views);
+    views.n = 1;
+    for (int64_t p = 0; p < P; p++) {
+        const int32_t need = pods[4 * p + 3];
+        if (need <= 0 || pods[4 * p] < 0 || pods[4 * p] > 8) continue;
+        bool seen = false;
+        for (int j = 1; j < views.n; j++) seen = seen || views.min_mem[j] == need;
+        if (seen) continue;
+        if (views.n == kgpu::PLACE_MAX_VIEWS) return -1;
+        views.min_mem[views.n++] = need;
+    }
     for (int k = 0; k <= 8; k++) {
         int c = 0;
         for (unsigned S = 0; S < 256; S++)
@@ -190,17 +203,20 @@ void emu_place_batch(const int32_t *topo, int32_t *free_mask, int64_t n, int64_t
     std::memcpy(topo4, topo, (size_t)n * 256);
     int4 *pods4 = aligned_array<int4>((size_t)P);
     std::memcpy(pods4, pods, (size_t)P * 16);
+    int32_t *mem = aligned_array<int32_t>((size_t)n * 8);
+    if (gpu_mem) std::memcpy(mem, gpu_mem, (size_t)n * 32); else std::memset(mem, 0x7F, (size_t)n * 32);
     const int64_t T = (n + kgpu::PLACE_TILE - 1) / kgpu::PLACE_TILE, Npad = T * kgpu::PLACE_TILE;
-    uint32_t *nodebest = aligned_array<uint32_t>((size_t)Npad * 9);
-    unsigned long long *tilebest = aligned_array<unsigned long long>((size_t)T * 9);
+    uint32_t *nodebest = aligned_array<uint32_t>((size_t)Npad * 9 * views.n);
+    unsigned long long *tilebest = aligned_array<unsigned long long>((size_t)T * 9 * views.n);
     const kgpu::Weights Ws = weights_of(W);
-    emu::launch(dim3((unsigned)T), dim3(kgpu::PLACE_TILE),
-                [&] { kgpu::place_init(topo4, free_mask, n, Npad, node_id_base, Ws, kPC, nodebest, tilebest, T); });
+    emu::launch(dim3((unsigned)T, (unsigned)views.n), dim3(kgpu::PLACE_TILE),
+                [&] { kgpu::place_init(topo4, free_mask, mem, n, Npad, node_id_base, Ws, kPC, views, nodebest, tilebest, T); });
     emu::launch(dim3(1), dim3(kgpu::PLACE_THREADS), [&] {
-        kgpu::place_sequential(reinterpret_cast<const int32_t *>(topo4), free_mask, n, Npad, node_id_base, pods4, P, Ws, nodebest,
-                               tilebest, T, keys);
+        kgpu::place_sequential(reinterpret_cast<const int32_t *>(topo4), free_mask, mem, n, Npad, node_id_base, pods4, P, Ws, views,
+                               nodebest, tilebest, T, keys);
     });
-    free(topo4); free(pods4); free(nodebest); free(tilebest);
+    free(topo4); free(pods4); free(mem); free(nodebest); free(tilebest);
+    return 0;
 }
 
 }  // extern "C"

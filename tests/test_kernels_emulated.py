@@ -113,19 +113,57 @@ def test_emulated_pair_list(emu, oracle_b):
         assert int(out[i]) == got, i
 
 
+def _place(emu, topo, free, pods, W, mem=None, base=0):
+    emu.emu_place_batch.restype = ctypes.c_int
+    f = np.ascontiguousarray(free, dtype=np.int32).copy()
+    pods = np.ascontiguousarray(pods, dtype=np.int32)
+    keys = np.empty(len(pods), dtype=np.uint64)
+    memp = None if mem is None else _p(np.ascontiguousarray(mem, dtype=np.int32))
+    rc = emu.emu_place_batch(_p(np.ascontiguousarray(topo, dtype=np.int32)), _p(f), memp, ctypes.c_int64(len(f)),
+                             ctypes.c_int64(base), _p(pods), ctypes.c_int64(len(pods)), _p(W), _p(keys, ctypes.c_uint64))
+    return rc, keys, f
+
+
 def test_emulated_sequential_placement(emu, oracle_b):
     """K3 (place_init + the persistent place_sequential block) against the stateful oracle."""
-    emu.emu_place_batch.restype = None
     W = np.ascontiguousarray(oracle_b.DEFAULT_WEIGHTS, dtype=np.int32)
     topo, free, pods = synth.gen_c4(N=300, P=120)
     pods[9, 0] = 0
-    f_emu = free.copy()
-    keys = np.empty(len(pods), dtype=np.uint64)
-    emu.emu_place_batch(_p(topo), _p(f_emu), ctypes.c_int64(len(free)), ctypes.c_int64(5), _p(pods), ctypes.c_int64(len(pods)),
-                        _p(W), _p(keys, ctypes.c_uint64))
+    pods[10, 0] = 12
+    rc, keys, f_emu = _place(emu, topo, free, pods, W, base=5)
     want_keys, want_free = oracle_b.place_batch(topo, free.copy(), pods, W, node_id_base=5)
-    assert (keys == want_keys).all()
-    assert (f_emu == want_free).all()
+    assert rc == 0 and (keys == want_keys).all() and (f_emu == want_free).all()
+
+
+def test_emulated_sequential_placement_many_tiles(emu, oracle_b):
+    """More than one supertile (33+ tiles) and a cluster that fills up: later pods find nothing."""
+    W = np.ascontiguousarray(oracle_b.DEFAULT_WEIGHTS, dtype=np.int32)
+    topo, free, _ = synth.gen_c2(N=128 * 34 + 17, P=0)
+    free[:] = 0
+    free[[5, 4300, 4368]] = [0x0F, 0xF0, 0xFF]           # three nodes with room, in different supertiles
+    pods = synth.make_pods(np.array([4, 4, 2, 8, 4, 2, 1, 1, 1, 1, 1], dtype=np.int32))
+    rc, keys, f_emu = _place(emu, topo, free, pods, W)
+    want_keys, want_free = oracle_b.place_batch(topo, free.copy(), pods, W)
+    assert rc == 0 and (keys == want_keys).all() and (f_emu == want_free).all()
+    assert (keys == np.uint64(0xFFFFFFFFFFFFFFFF)).any() and f_emu.sum() == 0
+
+
+def test_emulated_sequential_placement_memory_aware(emu, oracle_b):
+    """Pods with min_mem: one table set ("view") per distinct requirement; 4 requirements + the plain view."""
+    W = np.ascontiguousarray(oracle_b.DEFAULT_WEIGHTS, dtype=np.int32)
+    topo, free, mem, pods = synth.gen_c6(N=300, P=150)
+    assert len(set(pods[:, 3].tolist())) == 5
+    rc, keys, f_emu = _place(emu, topo, free, pods, W, mem=mem, base=9)
+    want_keys, want_free = oracle_b.place_batch(topo, free.copy(), pods, W, node_id_base=9, mem=mem)
+    assert rc == 0 and (keys == want_keys).all() and (f_emu == want_free).all()
+    plain_keys, _ = oracle_b.place_batch(topo, free.copy(), np.hstack([pods[:, :3], np.zeros((150, 1), np.int32)]), W, node_id_base=9)
+    assert (plain_keys != want_keys).any()
+    # without uploaded GPU memory the requirement excludes nothing (kgpu.h): same as the plain batch
+    rc, keys, _ = _place(emu, topo, free, pods, W, mem=None, base=9)
+    assert rc == 0 and (keys == plain_keys).all()
+    # eight distinct requirements are one too many
+    pods[:8, 3] = np.arange(1, 9) * 1000
+    assert _place(emu, topo, free, pods, W, mem=mem)[0] == -1
 
 
 @pytest.mark.parametrize("wmax", [2340, 2341])
