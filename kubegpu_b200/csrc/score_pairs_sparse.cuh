@@ -20,7 +20,10 @@
 
 namespace kgpu {
 
-constexpr int SP_THREADS = 128;
+#ifndef KGPU_SP_THREADS
+#define KGPU_SP_THREADS 128          // threads per block; 256 halves the per-pod block flushes (set KGPU_SP_MINBLOCKS 4 with it)
+#endif
+constexpr int SP_THREADS = KGPU_SP_THREADS;
 constexpr int SP_WARPS = SP_THREADS / 32;
 constexpr int SP_CHUNK = 512;       // pods per shared-memory chunk; sIdx packs (position | k << 9) in 16 bits
 constexpr int SP_ROW = 29;          // padded row of 28 pair costs per lane in shared memory
