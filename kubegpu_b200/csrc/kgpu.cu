@@ -15,6 +15,7 @@
 
 #include "multi_device.h"
 #include "place_sequential.cuh"
+#include "sparse_work.h"
 #include "score_pairs.cuh"
 #include "score_pairs_sparse.cuh"
 
@@ -51,6 +52,10 @@ struct kgpu_shard {
     unsigned long long *d_keys = nullptr;    // [pcap]
     unsigned long long *d_gather = nullptr;  // [ndev][pcap] (multi-device only)
     unsigned long long *d_bestk = nullptr;   // [9] memo variant
+    std::vector<uint8_t> tile_class;         // K1s: max free-GPU count per 128-slot tile of the order (host copy)
+    std::vector<kgpu::SparseWorkItem> h_work;   // K1s work list for work_P pods (sparse_work.h)
+    int4 *d_work = nullptr;
+    int64_t work_cap = 0, work_P = -1;
     uint32_t *d_nodebest = nullptr;          // [views][9][Npad]  K3 tables
     unsigned long long *d_tilebest = nullptr;   // [views][9][T]
     int64_t place_cap = 0;
@@ -192,11 +197,32 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
                 s.compact_dirty = false;
             }
             const int4 *cpair4 = reinterpret_cast<const int4 *>(s.d_cpair);
+            // Work list instead of the plain grid: auto = for small shards (few tiles per resident block), where
+            // equal pod ranges are either too few or too short; KGPU_SP_WORKLIST=0/1 forces it off/on.
+            static const int worklist_mode = [] { const char *e = getenv("KGPU_SP_WORKLIST"); return e ? atoi(e) : -1; }();
+            const bool use_work = worklist_mode >= 0 ? worklist_mode != 0 : tiles * 4 < resident;
+            const int4 *d_work = nullptr;
+            if (use_work) {
+                if (s.work_P != P) {
+                    kgpu::build_sparse_work(s.tile_class, P, resident, s.h_work);
+                    if ((int64_t)s.h_work.size() > s.work_cap) {
+                        if (s.d_work) cudaFree(s.d_work);
+                        s.d_work = nullptr; s.work_cap = 0;
+                        KGPU_CUDA(h, cudaMalloc(&s.d_work, s.h_work.size() * sizeof(int4)));
+                        s.work_cap = (int64_t)s.h_work.size();
+                    }
+                    static_assert(sizeof(kgpu::SparseWorkItem) == sizeof(int4), "work item layout");
+                    KGPU_CUDA(h, cudaMemcpyAsync(s.d_work, s.h_work.data(), s.h_work.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+                    s.work_P = P;
+                }
+                d_work = s.d_work;
+                grid = dim3((unsigned)s.h_work.size(), 1);
+            }
             bool byte_keys = true;       // every cost < 2^16 <=> 28 * max weight < 65536
             for (int i = 0; i < 16; i++) byte_keys = byte_keys && h->W[i] <= 2340;
 #define KGPU_LAUNCH_SPARSE(MEMF, BK)                                                                          \
     kgpu::score_pairs_sparse<true, MEMF, BK><<<grid, kgpu::SP_THREADS, 0, st>>>(                              \
-        cpair4, s.d_perm, s.d_free, s.d_mem, s.d_order, s.d_flag, s.node_id_base, pods4, P, (int)per, PC, d_keys)
+        cpair4, s.d_perm, s.d_free, s.d_mem, s.d_order, s.d_flag, s.node_id_base, pods4, P, (int)per, d_work, PC, d_keys)
             if (byte_keys) KGPU_LAUNCH_SPARSE(false, true); else KGPU_LAUNCH_SPARSE(false, false);
             h->launches++;
             if (has_mem != 0) {
@@ -248,6 +274,7 @@ void free_shard(kgpu_shard &s) {
     if (s.d_bestk) cudaFree(s.d_bestk);
     if (s.d_nodebest) cudaFree(s.d_nodebest);
     if (s.d_tilebest) cudaFree(s.d_tilebest);
+    if (s.d_work) cudaFree(s.d_work);
     if (s.ev0) cudaEventDestroy(s.ev0);
     if (s.ev1) cudaEventDestroy(s.ev1);
     if (s.stream) cudaStreamDestroy(s.stream);
@@ -415,6 +442,14 @@ int kgpu_upload_nodes(kgpu_t *h, const int32_t *topo, const int32_t *free_mask, 
                 s.order_cap = (int64_t)order.size();
             }
             s.n_slots = (int64_t)order.size();
+            s.tile_class.assign(order.size() / kgpu::SP_THREADS, 0);
+            for (size_t sl = 0; sl < order.size(); sl++)
+                if (order[sl] >= 0) {
+                    const uint8_t f = (uint8_t)__builtin_popcount((unsigned)free_mask[off + order[sl]] & 0xFFu);
+                    uint8_t &tc = s.tile_class[sl / kgpu::SP_THREADS];
+                    tc = std::max(tc, f);
+                }
+            s.work_P = -1;
             if (!order.empty()) {
                 KGPU_CUDA(h, cudaMemcpyAsync(s.d_order, order.data(), order.size() * 4, cudaMemcpyHostToDevice, s.stream));
                 KGPU_CUDA(h, cudaStreamSynchronize(s.stream));   // `order` is a local

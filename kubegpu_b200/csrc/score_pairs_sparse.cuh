@@ -95,8 +95,11 @@ __device__ __forceinline__ void sp_bucket(const PairCosts &C, const PipeConsts p
     const SpFmt fmt = sp_fmt<BYTE_KEYS>(lane_field, MEM ? true : (valid && nfree >= need_free));
     const uint32_t thirty_two = pc.one << 5;       // a register, so that the shift is an IMAD (kernel parameter: opaque)
     KGPU_UNROLL((sp_unroll(K, F)))
-    for (int i = begin; i < end; i++) {            // begin, end: warp-uniform (read from shared memory)
-        SpEnt *const ent = tab + i;
+    // byte offsets: uniform (begin, end come from shared memory), so the loop runs on the uniform datapath
+    // and the entry address is tab + offset with no arithmetic of its own
+    for (uint32_t off = (uint32_t)begin * (uint32_t)sizeof(SpEnt); off != (uint32_t)end * (uint32_t)sizeof(SpEnt);
+         off += (uint32_t)sizeof(SpEnt)) {
+        SpEnt *const ent = reinterpret_cast<SpEnt *>(reinterpret_cast<char *>(tab) + off);
         PipeConsts pcl = pc;
         uint32_t v;
         if (MEM) {
@@ -214,14 +217,14 @@ compact_nodes(const int4 *__restrict__ topo4, const int32_t *__restrict__ free_m
         }
 }
 
-// grid = (slot tiles of 128, pod splits); block = 128 threads.  order[slot] = node index or -1 (padding).
+// grid = (work items) or (slot tiles, pod splits); block = SP_THREADS.  order[slot] = node index or -1 (padding).
 template <bool PER_PAIR, bool MEM, bool BYTE_KEYS>
 __global__ void __launch_bounds__(SP_THREADS, MEM ? 4 : KGPU_SP_MINBLOCKS)
 score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__ perm_in,
                    const int32_t *__restrict__ free_mask,
                    const int32_t *__restrict__ gpu_mem, const int32_t *__restrict__ order,
                    const int *__restrict__ mem_flag, int64_t node_id_base, const int4 *__restrict__ pods4, int64_t P,
-                   int pods_per_split, PipeConsts pc, unsigned long long *__restrict__ keys) {
+                   int pods_per_split, const int4 *__restrict__ work, PipeConsts pc, unsigned long long *__restrict__ keys) {
     if (MEM && *mem_flag == 0) return;
     __shared__ int32_t sCnt[10], sOff[11];
     __shared__ uint8_t sK[SP_CHUNK];
@@ -235,7 +238,14 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
     const uint32_t lane_field = (uint32_t)(tid & 31) << 8;
 
     // ---- staging: the node's compacted pair costs (7 x 16 B), permutation and free count ----------
-    const int64_t slot = (int64_t)blockIdx.x * SP_THREADS + tid;
+    // which tile, which pods: a work item {tile, pod_begin, pod_end} of the host's list (sparse_work.h), or the
+    // plain grid (tile = blockIdx.x, equal pod ranges along blockIdx.y) when there is no list
+    int64_t tile_index = blockIdx.x, p_begin = (int64_t)blockIdx.y * pods_per_split, p_end = min(P, p_begin + pods_per_split);
+    if (work != nullptr) {
+        const int4 item = __ldg(work + blockIdx.x);
+        tile_index = item.x; p_begin = item.y; p_end = item.z;
+    }
+    const int64_t slot = tile_index * SP_THREADS + tid;
     const int32_t node = __ldg(order + slot);
     const bool valid = node >= 0;
     sNode[tid] = node;
@@ -265,9 +275,6 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
         for (int g = 0; g < 8; g++) mem[g] = __ldg(gpu_mem + (int64_t)node * 8 + ((perm >> (4 * g)) & 7u));
     }
     const int F = (int)__reduce_max_sync(0xFFFFFFFFu, nfree);    // warp-uniform bound on usable positions
-
-    const int64_t p_begin = (int64_t)blockIdx.y * pods_per_split;
-    const int64_t p_end = min(P, p_begin + pods_per_split);
 
     for (int64_t c0 = p_begin; c0 < p_end; c0 += SP_CHUNK) {
         const int cn = (int)min((int64_t)SP_CHUNK, p_end - c0);

@@ -9,6 +9,7 @@
 #include "score_pairs.cuh"
 #include "score_pairs_sparse.cuh"
 #include "place_sequential.cuh"
+#include "sparse_work.h"
 
 
 namespace {
@@ -64,19 +65,41 @@ void emu_score_sparse(const int32_t *topo, const int32_t *free_mask, const int32
                 [&] { kgpu::compact_nodes(topo4, free_mask, n, Ws, cpair, perm); });
     int flag = 0;
     for (int64_t p = 0; p < P; p++) flag |= pods[4 * p + 3] > 0;
-    const dim3 grid((unsigned)(order.size() / kgpu::SP_THREADS), (unsigned)std::max(1, splits));
+    dim3 grid((unsigned)(order.size() / kgpu::SP_THREADS), (unsigned)std::max(1, splits));
     const int per = per_split(P, std::max(1, splits));
     const int4 *cpair4 = reinterpret_cast<const int4 *>(cpair);
+    // splits < 0: the work list of sparse_work.h for -splits resident blocks, as kgpu.cu builds it
+    std::vector<kgpu::SparseWorkItem> items;
+    const int4 *work = nullptr;
+    if (splits < 0) {
+        std::vector<uint8_t> tile_class(order.size() / kgpu::SP_THREADS, 0);
+        for (size_t sl = 0; sl < order.size(); sl++)
+            if (order[sl] >= 0)
+                tile_class[sl / kgpu::SP_THREADS] = std::max<uint8_t>(tile_class[sl / kgpu::SP_THREADS],
+                                                                      (uint8_t)__builtin_popcount((unsigned)free_mask[order[sl]] & 0xFFu));
+        kgpu::build_sparse_work(tile_class, P, -splits, items);
+        static_assert(sizeof(kgpu::SparseWorkItem) == sizeof(int4), "work item layout");
+        work = reinterpret_cast<const int4 *>(items.data());
+        grid = dim3((unsigned)items.size(), 1);
+    }
     bool byte_keys = true;                               // kgpu.cu: every cost < 2^16
     for (int i = 0; i < 16; i++) byte_keys = byte_keys && W[i] <= 2340;
 #define EMU_SPARSE(MEMF, BK)                                                                                   \
     emu::launch(grid, dim3(kgpu::SP_THREADS), [&] {                                                            \
-        kgpu::score_pairs_sparse<true, MEMF, BK>(cpair4, perm, free_mask, mem, order.data(), &flag, node_id_base, pods4, P, per, kPC, keys); \
+        kgpu::score_pairs_sparse<true, MEMF, BK>(cpair4, perm, free_mask, mem, order.data(), &flag, node_id_base, pods4, P, per, work, kPC, keys); \
     })
     if (byte_keys) EMU_SPARSE(false, true); else EMU_SPARSE(false, false);
     if (flag) { if (byte_keys) EMU_SPARSE(true, true); else EMU_SPARSE(true, false); }
 #undef EMU_SPARSE
     free(topo4); free(pods4); free(mem); free(cpair); free(perm);
+}
+
+// The host-side work-list builder alone (sparse_work.h): items as int32[.][4], returns the count.
+int64_t emu_sparse_work(const uint8_t *tile_class, int64_t tiles, int64_t P, int64_t resident, int32_t *out, int64_t cap) {
+    std::vector<kgpu::SparseWorkItem> items;
+    kgpu::build_sparse_work(std::vector<uint8_t>(tile_class, tile_class + tiles), P, resident, items);
+    for (size_t i = 0; i < items.size() && (int64_t)i < cap; i++) std::memcpy(out + 4 * i, &items[i], 16);
+    return (int64_t)items.size();
 }
 
 // Dense K1 (+ K1m) as kgpu.cu launches them.

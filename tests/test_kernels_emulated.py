@@ -174,3 +174,33 @@ def test_emulated_sparse_warp_key_layouts(emu, oracle_b, wmax):
     W = np.array([wmax - i for i in range(16)], dtype=np.int32)
     want = oracle_b.score_batch(topo, free, pods, W, node_id_base=3)
     assert (_run(emu.emu_score_sparse, topo, free, pods, W, base=3, splits=3) == want).all()
+
+
+def test_emulated_sparse_work_list(emu, oracle_b):
+    """K1s driven by the work list (per-tile pod ranges of about equal work, heaviest first) instead of the
+    plain (tiles x splits) grid: same keys; every (tile, pod) covered exactly once."""
+    W = oracle_b.DEFAULT_WEIGHTS
+    topo, free, mem, pods = synth.gen_c6(N=900, P=700)
+    pods[5, 0], pods[6, 0] = 0, 9
+    want = oracle_b.score_batch(topo, free, pods, W, node_id_base=4, mem=mem)
+    for resident in (1, 16, 1184):
+        assert (_run(emu.emu_score_sparse, topo, free, pods, W, mem=mem, base=4, splits=-resident) == want).all(), resident
+
+
+@pytest.mark.parametrize("P", [1, 31, 32, 1000, 10_000])
+@pytest.mark.parametrize("resident", [1, 1184])
+def test_sparse_work_list_partitions_every_tile(emu, P, resident):
+    emu.emu_sparse_work.restype = ctypes.c_int64
+    rng = np.random.default_rng(P + resident)
+    tile_class = rng.integers(0, 9, size=57).astype(np.uint8)
+    out = np.zeros((200_000, 4), dtype=np.int32)
+    n = emu.emu_sparse_work(_p(tile_class, ctypes.c_uint8), ctypes.c_int64(57), ctypes.c_int64(P), ctypes.c_int64(resident),
+                            _p(out), ctypes.c_int64(len(out)))
+    items = out[:n]
+    assert 57 <= n <= len(out)
+    assert (np.diff(items[:, 3]) <= 0).all()                     # heaviest first
+    for t in range(57):
+        mine = items[items[:, 0] == t]
+        mine = mine[np.argsort(mine[:, 1])]
+        assert mine[0, 1] == 0 and mine[-1, 2] == P and (mine[1:, 1] == mine[:-1, 2]).all()   # a partition of [0, P)
+        assert (mine[:, 1] % 32 == 0).all() and (mine[:, 2] > mine[:, 1]).all()
