@@ -230,7 +230,7 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
     __shared__ uint8_t sK[SP_CHUNK];
     __shared__ uint16_t sIdx[SP_CHUNK];                // bucket order -> chunk position
     __shared__ SpEnt sTab[SP_WARPS][SP_CHUNK];         // per warp, bucket order: multiplier | result
-    __shared__ uint32_t sPerm[SP_THREADS];             // position -> GPU index, 8 nibbles
+    __shared__ uint32_t sHotLo[SP_THREADS], sHotHi[SP_THREADS];   // position g -> byte (1 << GPU index), g = 0..3 | 4..7
     __shared__ int32_t sNode[SP_THREADS];              // slot -> node index (-1 = padding)
 
     const int tid = threadIdx.x;
@@ -251,7 +251,23 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
     sNode[tid] = node;
     const uint32_t nfree = valid ? (uint32_t)__popc((uint32_t)__ldg(free_mask + node) & 0xFFu) : 0u;
     const uint32_t perm = valid ? __ldg(perm_in + node) : 0x76543210u;
-    sPerm[tid] = perm;
+    {
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            lo |= (1u << ((perm >> (4 * g)) & 7u)) << (8 * g);
+            hi |= (1u << ((perm >> (4 * g + 16)) & 7u)) << (8 * g);
+        }
+        sHotLo[tid] = lo;
+        sHotHi[tid] = hi;
+    }
+    // Are the tile's slots in increasing node id (one class, padding only at the end)?  Then (cost, warp, lane)
+    // order IS (cost, node) order and the flush can min the four warp keys directly.
+    bool ordered = false;
+    if (BYTE_KEYS) {
+        const int32_t prev = tid > 0 ? __ldg(order + slot - 1) : -1;
+        ordered = __syncthreads_and(tid == 0 || node < 0 || (prev >= 0 && prev < node)) != 0;
+    }
     PairCosts C;
     {
         uint32_t wds[28];
@@ -320,30 +336,38 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
         sp_run_k<8, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[8], sOff[9]);
         __syncthreads();
 
-        // block result per pod: min over the 4 warps of (cost, node id) -- a tile may hold warps of two
-        // adjacent classes, so node ids are compared explicitly -- then S' -> real GPU mask through the
-        // winner's permutation, and REDG.MIN.64 into keys[pod].
+        // block result per pod: min over the warps of (cost, node id), S' -> real GPU mask through the
+        // winner's one-hot bytes, REDG.MIN.64 into keys[pod].  Ordered tile + byte keys: the warp index goes
+        // into bits 13.. of the warp key (its lane byte has 3 spare bits) and plain 32-bit mins decide;
+        // otherwise (a tile of two classes) node ids are compared explicitly.
         const int served = sOff[9];                // bucket 9 (not for this launch) sits at the end
         for (int i = tid; i < served; i += SP_THREADS) {
-            unsigned long long best = ~0ull;       // cost<<40 | node_index<<8 | slot_in_tile... (slot kept aside)
+            uint32_t best_m = INF32, cost = 0;
             int best_slot = -1;
-            uint32_t best_m = 0;
+            if (BYTE_KEYS && ordered) {
 #pragma unroll
-            for (int w = 0; w < SP_WARPS; w++) {
-                const uint32_t m = sTab[w][i].best;
-                if (m == INF32) continue;
-                const int s = w * 32 + (int)((m >> 8) & 31u);
-                const unsigned long long cand = ((unsigned long long)(m >> (BYTE_KEYS ? 16 : 13)) << 32) | (uint32_t)sNode[s];
-                if (cand < best) { best = cand; best_slot = s; best_m = m; }
+                for (int w = 0; w < SP_WARPS; w++) best_m = min(best_m, sTab[w][i].best | ((uint32_t)w << 13));   // INF32 stays INF32
+                if (best_m != INF32) { best_slot = (int)((best_m >> 8) & (uint32_t)(SP_THREADS - 1)); cost = best_m >> 16; }
+            } else {
+                unsigned long long best = ~0ull;   // cost<<32 | node index
+#pragma unroll
+                for (int w = 0; w < SP_WARPS; w++) {
+                    const uint32_t m = sTab[w][i].best;
+                    if (m == INF32) continue;
+                    const int s = w * 32 + (int)((m >> 8) & 31u);
+                    const unsigned long long cand = ((unsigned long long)(m >> (BYTE_KEYS ? 16 : 13)) << 32) | (uint32_t)sNode[s];
+                    if (cand < best) { best = cand; best_slot = s; best_m = m; cost = (uint32_t)(best >> 32); }
+                }
             }
             if (best_slot >= 0) {
-                const uint32_t pm = sPerm[best_slot];
-                uint32_t S = 0;
-#pragma unroll
-                for (int g = 0; g < 8; g++)
-                    if ((best_m >> g) & 1u) S |= 1u << ((pm >> (4 * g)) & 7u);
-                const unsigned long long nid = (unsigned long long)(node_id_base + (long long)(best & 0xFFFFFFFFull));
-                atomicMin(&keys[c0 + sIdx[i]], ((best >> 32) << 40) | (nid << 8) | S);
+                // S' bit g set -> byte g of the one-hot words; OR the selected bytes together
+                const uint32_t sel_lo = (((best_m & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+                const uint32_t sel_hi = ((((best_m >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+                uint32_t t = (sHotLo[best_slot] & sel_lo) | (sHotHi[best_slot] & sel_hi);
+                t |= t >> 16;
+                const uint32_t S = (t | (t >> 8)) & 0xFFu;
+                const unsigned long long nid = (unsigned long long)(node_id_base + (long long)sNode[best_slot]);
+                atomicMin(&keys[c0 + sIdx[i]], ((unsigned long long)cost << 40) | (nid << 8) | S);
             }
         }
     }

@@ -132,6 +132,7 @@ inline int __syncthreads_or(int pred) {
     b.bar.arrive_and_wait();
     return b.or_flag.load();
 }
+inline int __syncthreads_and(int pred) { return !__syncthreads_or(!pred); }
 inline unsigned __reduce_min_sync(unsigned, unsigned v) { return emu::warp_all(v, [](unsigned a, unsigned b) { return a < b ? a : b; }); }
 inline unsigned __reduce_max_sync(unsigned, unsigned v) { return emu::warp_all(v, [](unsigned a, unsigned b) { return a > b ? a : b; }); }
 inline unsigned __ballot_sync(unsigned, int pred) {

@@ -204,3 +204,20 @@ def test_sparse_work_list_partitions_every_tile(emu, P, resident):
         mine = mine[np.argsort(mine[:, 1])]
         assert mine[0, 1] == 0 and mine[-1, 2] == P and (mine[1:, 1] == mine[:-1, 2]).all()   # a partition of [0, P)
         assert (mine[:, 1] % 32 == 0).all() and (mine[:, 2] > mine[:, 1]).all()
+
+
+def test_emulated_sparse_single_class_tiles(emu, oracle_b):
+    """Tiles whose slots are one class in increasing node id take the flush's direct 32-bit min over the
+    warp keys (warp index in the key); C2's few shapes make cost ties across warps and nodes the rule."""
+    W = oracle_b.DEFAULT_WEIGHTS
+    topo, free, pods = synth.gen_c2(N=300, P=64)
+    free[:] = 0xFF
+    free[[7, 100, 299]] = [0x0F, 0x00, 0x3C]              # stragglers form small mixed tail tiles
+    pods = synth.make_pods(np.array([1, 2, 3, 4, 5, 6, 7, 8, 0] * 7, dtype=np.int32))
+    want = oracle_b.score_batch(topo, free, pods, W, node_id_base=40)
+    assert (_run(emu.emu_score_sparse, topo, free, pods, W, base=40, splits=2) == want).all()
+    # the same with every pod's cheapest nodes taken away one by one: winners move across warps and tiles
+    for taken in (0, 1, 2, 31, 32, 127, 128, 129):
+        free[taken] = 0
+        want = oracle_b.score_batch(topo, free, pods, W, node_id_base=40)
+        assert (_run(emu.emu_score_sparse, topo, free, pods, W, base=40) == want).all(), taken
