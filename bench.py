@@ -248,6 +248,9 @@ def main():
     ap.add_argument("--impl", default="kgpu", choices=["kgpu", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "push"],
+                    help="multi-GPU key exchange: NCCL all-gather + K2 (default, measured in round 1) or the "
+                         "(round-2 prep, untested) peer-memory push kernel of kgpu_score_batch_exchange")
     ap.add_argument("--graph", action="store_true",
                     help="(round-2 prep, untested) replay the step (memset + K1s + all-gather + K2) as one CUDA graph")
     args = ap.parse_args()
@@ -296,22 +299,44 @@ def main():
     torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
 
+    push = args.exchange == "push"
+    if push and args.graph:
+        raise SystemExit("--exchange push cannot be captured in a graph (the epoch is a kernel argument)")
+    if push:                                        # every rank maps every rank's result array (CUDA IPC)
+        mine = scorer.exchange_init(world, rank, N_PODS)
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, mine)
+        else:
+            handles = [mine]
+        scorer.exchange_connect(handles)
+    wrapped = {}
+
+    class _DeviceKeys:                              # zero-copy view of the handle-owned result array
+        def __init__(self, ptr):
+            self.__cuda_array_interface__ = {"shape": (N_PODS,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
     def step_device():
-        """pods already in HBM -> final keys in HBM (all ranks hold the answer)."""
+        """pods already in HBM -> final keys in HBM (all ranks hold the answer); returns the tensor holding them."""
         sptr = torch.cuda.current_stream().cuda_stream          # the capture stream while a graph is recorded
+        if push:
+            ptr = scorer.score_batch_exchange(d_pods.data_ptr(), N_PODS, sptr, _lib.BATCH_NO_MIN_MEM)
+            if ptr not in wrapped:
+                wrapped[ptr] = torch.as_tensor(_DeviceKeys(ptr), device=dev)
+            return wrapped[ptr]
         scorer.score_batch_device(d_pods.data_ptr(), N_PODS, d_local.data_ptr(), sptr, _lib.BATCH_NO_MIN_MEM)
         if world > 1:
             dist.all_gather_into_tensor(d_gather.view(-1), d_local)
             scorer.reduce_shards_device(d_gather.data_ptr(), world, N_PODS, d_final.data_ptr(), sptr)
+        return d_final
 
     def step_e2e():
         """host pods -> host keys through the public call."""
-        if world == 1:
+        if world == 1 and not push:
             scorer.score_batch_ptr(h_pods.data_ptr(), N_PODS, h_keys.data_ptr())   # kgpu_score_batch: H2D + K1 + D2H
         else:
             d_pods.copy_(h_pods, non_blocking=True)
-            step_device()
-            h_keys.copy_(d_final, non_blocking=True)
+            h_keys.copy_(step_device(), non_blocking=True)
             stream.synchronize()
 
     def barrier():
@@ -343,6 +368,9 @@ def main():
         if graph is not None:
             graph.replay()
             ev[i][1].record(stream)                    # (no K1-only split inside a graph replay)
+        elif push:
+            step_device()
+            ev[i][1].record(stream)                    # (K1 and the push/sync kernel are one call)
         else:
             scorer.score_batch_device(d_pods.data_ptr(), N_PODS, d_local.data_ptr(), sptr, _lib.BATCH_NO_MIN_MEM)
             ev[i][1].record(stream)                    # K1 only: roofline numerator
@@ -378,7 +406,7 @@ def main():
 
     # ---- context lines: the other K1 variants (few steps, rank-local, N=1 only) ---------
     variants = {}
-    if world == 1 and not args.no_variants:
+    if world == 1 and not args.no_variants and not push:
         for name, var, reps in (("lane_per_node_dense_all_C8k_subsets", _lib.VARIANT_LANE_PER_NODE, 5),
                                 ("warp_per_pair_north_star_mapping", _lib.VARIANT_WARP_PER_PAIR, 3),
                                 ("tile_memo_not_headline", _lib.VARIANT_TILE_MEMO, 10),
@@ -424,7 +452,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "nodes": N_NODES, "pods": N_PODS,
-                       "parallelism": "node list sharded over %d GPU(s), 1 NCCL all-gather + K2" % world if world > 1 else "1 GPU, no collective",
+                       "parallelism": ("node list sharded over %d GPU(s), " % world + ("peer-memory push + flag barrier (1 kernel)" if push else "1 NCCL all-gather + K2")) if world > 1 else "1 GPU, no collective",
                        "kernel": "score_pairs_sparse (per pair: every k-subset of the node's free-GPU positions)",
                        "l2": "flushed between timed iterations (256 MiB write); node array is 26 MB < L2"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -16,6 +16,7 @@
 #include "multi_device.h"
 #include "place_sequential.cuh"
 #include "sparse_work.h"
+#include "peer_exchange.cuh"
 #include "score_pairs.cuh"
 #include "score_pairs_sparse.cuh"
 
@@ -73,6 +74,17 @@ struct kgpu_ctx {
     double last_kernel_ms = 0.0;
     bool subsets_uploaded = false;
     kgpu::MultiDevice *multi = nullptr;   // NCCL communicator set, ndev > 1 only
+    // peer-memory key exchange (kgpu_exchange_*): one allocation per rank, mapped by every peer:
+    //   results[2][max_pods] uint64 | flags[PEER_MAX_WORLD] uint32 | ticket uint32 ;  local[] is private
+    struct {
+        int world = 0, rank = 0;
+        int64_t max_pods = 0;
+        void *base = nullptr;
+        void *peer_base[kgpu::PEER_MAX_WORLD] = {};
+        unsigned long long *local = nullptr;
+        uint32_t epoch = 0;
+        bool connected = false;
+    } xch;
 };
 
 namespace {
@@ -353,6 +365,12 @@ int kgpu_destroy(kgpu_t *h) {
         if (s.dev >= 0) { cudaSetDevice(s.dev); cudaStreamSynchronize(s.stream); }
     }
     delete h->multi;
+    if (h->xch.base) {
+        for (int r = 0; r < h->xch.world; r++)
+            if (h->xch.connected && r != h->xch.rank && h->xch.peer_base[r]) cudaIpcCloseMemHandle(h->xch.peer_base[r]);
+        cudaFree(h->xch.base);
+        cudaFree(h->xch.local);
+    }
     for (auto &s : h->shards) free_shard(s);
     delete h;
     return KGPU_OK;
@@ -726,6 +744,83 @@ int kgpu_score_batch_device_ex(kgpu_t *h, const int32_t *d_pods, int64_t P, uint
     kgpu_shard &s = h->shards[0];
     return launch_score(h, s, d_pods, P, reinterpret_cast<unsigned long long *>(d_keys), (cudaStream_t)stream,
                         (batch_flags & KGPU_BATCH_NO_MIN_MEM) ? 0 : -1);
+}
+
+namespace {
+size_t xch_bytes(int64_t max_pods) { return (size_t)max_pods * 16 + kgpu::PEER_MAX_WORLD * 4 + 16; }
+unsigned long long *xch_results(void *base, int64_t max_pods, int buf) { return reinterpret_cast<unsigned long long *>(base) + (int64_t)buf * max_pods; }
+uint32_t *xch_flags(void *base, int64_t max_pods) { return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(base) + (size_t)max_pods * 16); }
+}  // namespace
+
+int kgpu_exchange_init(kgpu_t *h, int world, int rank, int64_t max_pods, unsigned char *out_handle) {
+    if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_exchange_init: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    static_assert(sizeof(cudaIpcMemHandle_t) == KGPU_IPC_HANDLE_BYTES, "IPC handle size");
+    if (h->shards.size() != 1) return fail(h, KGPU_ERR_STATE, "kgpu_exchange_init: needs a single-device handle");
+    if (world < 1 || world > kgpu::PEER_MAX_WORLD || rank < 0 || rank >= world || max_pods < 1 || !out_handle)
+        return fail(h, KGPU_ERR_INVALID, "kgpu_exchange_init: bad arguments (world <= %d)", kgpu::PEER_MAX_WORLD);
+    if (h->xch.base) return fail(h, KGPU_ERR_STATE, "kgpu_exchange_init: already initialised");
+    kgpu_shard &s = h->shards[0];
+    KGPU_CUDA(h, cudaSetDevice(s.dev));
+    KGPU_CUDA(h, cudaMalloc(&h->xch.base, xch_bytes(max_pods)));
+    KGPU_CUDA(h, cudaMalloc(&h->xch.local, (size_t)max_pods * 8));
+    KGPU_CUDA(h, cudaMemset(h->xch.base, 0xFF, (size_t)max_pods * 16));                                   // both result buffers: NO_FIT
+    KGPU_CUDA(h, cudaMemset(xch_flags(h->xch.base, max_pods), 0, kgpu::PEER_MAX_WORLD * 4 + 16));         // flags, ticket
+    KGPU_CUDA(h, cudaDeviceSynchronize());
+    cudaIpcMemHandle_t ipc;
+    KGPU_CUDA(h, cudaIpcGetMemHandle(&ipc, h->xch.base));
+    memcpy(out_handle, &ipc, sizeof ipc);
+    h->xch.world = world; h->xch.rank = rank; h->xch.max_pods = max_pods; h->xch.epoch = 0; h->xch.connected = false;
+    return KGPU_OK;
+}
+
+int kgpu_exchange_connect(kgpu_t *h, const unsigned char *handles) {
+    if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_exchange_connect: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->xch.base) return fail(h, KGPU_ERR_STATE, "kgpu_exchange_connect: call kgpu_exchange_init first");
+    if (!handles) return fail(h, KGPU_ERR_INVALID, "kgpu_exchange_connect: NULL handles");
+    if (h->xch.connected) return fail(h, KGPU_ERR_STATE, "kgpu_exchange_connect: already connected");
+    KGPU_CUDA(h, cudaSetDevice(h->shards[0].dev));
+    for (int r = 0; r < h->xch.world; r++) {
+        if (r == h->xch.rank) { h->xch.peer_base[r] = h->xch.base; continue; }
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, handles + (size_t)r * KGPU_IPC_HANDLE_BYTES, sizeof ipc);
+        KGPU_CUDA(h, cudaIpcOpenMemHandle(&h->xch.peer_base[r], ipc, cudaIpcMemLazyEnablePeerAccess));
+    }
+    h->xch.connected = true;
+    return KGPU_OK;
+}
+
+int kgpu_score_batch_exchange(kgpu_t *h, const int32_t *d_pods, int64_t P, const uint64_t **d_final_keys, void *stream,
+                              int batch_flags) {
+    if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_score_batch_exchange: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->xch.connected) return fail(h, KGPU_ERR_STATE, "kgpu_score_batch_exchange: exchange not connected");
+    if (P < 0 || P > h->xch.max_pods || (P > 0 && !d_pods) || !d_final_keys)
+        return fail(h, KGPU_ERR_INVALID, "kgpu_score_batch_exchange: bad arguments (P <= max_pods of kgpu_exchange_init)");
+    kgpu_shard &s = h->shards[0];
+    cudaStream_t st = (cudaStream_t)stream;
+    KGPU_CUDA(h, cudaSetDevice(s.dev));
+    const uint32_t epoch = ++h->xch.epoch;
+    const int buf = (int)(epoch & 1u);
+    const int64_t mp = h->xch.max_pods;
+    *d_final_keys = reinterpret_cast<const uint64_t *>(xch_results(h->xch.base, mp, buf));
+    if (P == 0) return KGPU_OK;
+    // the other buffer is what peers push into NEXT epoch: clean it before this rank can reach this epoch's barrier
+    KGPU_CUDA(h, cudaMemsetAsync(xch_results(h->xch.base, mp, buf ^ 1), 0xFF, (size_t)P * 8, st));
+    const int rc = launch_score(h, s, d_pods, P, h->xch.local, st, (batch_flags & KGPU_BATCH_NO_MIN_MEM) ? 0 : -1);
+    if (rc != KGPU_OK) return rc;
+    kgpu::PeerTable tab;
+    memset(&tab, 0, sizeof tab);
+    for (int r = 0; r < h->xch.world; r++) {
+        tab.results[r] = xch_results(h->xch.peer_base[r], mp, buf);
+        tab.flags[r] = xch_flags(h->xch.peer_base[r], mp);
+    }
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(xch_flags(h->xch.base, mp) + kgpu::PEER_MAX_WORLD);
+    kgpu::push_and_sync<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(h->xch.local, P, tab, h->xch.rank, h->xch.world, epoch, ticket);
+    h->launches++;
+    KGPU_CUDA(h, cudaGetLastError());
+    return KGPU_OK;
 }
 
 int kgpu_reduce_shards_device(kgpu_t *h, const uint64_t *d_gathered, int G, int64_t P, uint64_t *d_out, void *stream) {
