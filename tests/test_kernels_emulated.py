@@ -221,3 +221,22 @@ def test_emulated_sparse_single_class_tiles(emu, oracle_b):
         free[taken] = 0
         want = oracle_b.score_batch(topo, free, pods, W, node_id_base=40)
         assert (_run(emu.emu_score_sparse, topo, free, pods, W, base=40) == want).all(), taken
+
+
+    assert (keys == want_keys).all()
+    assert (f_emu == want_free).all()
+
+
+@pytest.mark.parametrize("kernel", ["sparse", "dense"])
+def test_emulated_ragged_sizes(emu, oracle_b, kernel):
+    """More pods than one shared-memory chunk (three chunks, the last one ragged), pod splits that do not
+    divide the batch, a node count that fills neither a warp nor a tile, and a single node."""
+    fn = emu.emu_score_sparse if kernel == "sparse" else emu.emu_score_dense
+    W = oracle_b.DEFAULT_WEIGHTS
+    topo, free, pods = synth.gen_c4(N=33, P=1100)
+    want = oracle_b.score_batch(topo, free, pods, W, node_id_base=2**31 - 40)     # ids near the top of the 32-bit field
+    assert (_run(fn, topo, free, pods, W, base=2**31 - 40, splits=3) == want).all()
+    assert (_run(fn, topo[:1], free[:1], pods[:40], W) == oracle_b.score_batch(topo[:1], free[:1], pods[:40], W)).all()
+    none_free = np.zeros(5, dtype=np.int32)
+    got = _run(fn, topo[:5], none_free, pods[:16], W)
+    assert (got == oracle_b.score_batch(topo[:5], none_free, pods[:16], W)).all()
