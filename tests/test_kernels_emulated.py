@@ -223,10 +223,6 @@ def test_emulated_sparse_single_class_tiles(emu, oracle_b):
         assert (_run(emu.emu_score_sparse, topo, free, pods, W, base=40) == want).all(), taken
 
 
-    assert (keys == want_keys).all()
-    assert (f_emu == want_free).all()
-
-
 @pytest.mark.parametrize("kernel", ["sparse", "dense"])
 def test_emulated_ragged_sizes(emu, oracle_b, kernel):
     """More pods than one shared-memory chunk (three chunks, the last one ragged), pod splits that do not
