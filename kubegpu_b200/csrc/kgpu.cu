@@ -807,7 +807,8 @@ int kgpu_score_batch_exchange(kgpu_t *h, const int32_t *d_pods, int64_t P, const
     *d_final_keys = reinterpret_cast<const uint64_t *>(xch_results(h->xch.base, mp, buf));
     if (P == 0) return KGPU_OK;
     // the other buffer is what peers push into NEXT epoch: clean it before this rank can reach this epoch's barrier
-    KGPU_CUDA(h, cudaMemsetAsync(xch_results(h->xch.base, mp, buf ^ 1), 0xFF, (size_t)P * 8, st));
+    // (all max_pods entries: the next batch may be longer than this one)
+    KGPU_CUDA(h, cudaMemsetAsync(xch_results(h->xch.base, mp, buf ^ 1), 0xFF, (size_t)mp * 8, st));
     const int rc = launch_score(h, s, d_pods, P, h->xch.local, st, (batch_flags & KGPU_BATCH_NO_MIN_MEM) ? 0 : -1);
     if (rc != KGPU_OK) return rc;
     kgpu::PeerTable tab;
