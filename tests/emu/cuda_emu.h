@@ -160,6 +160,11 @@ inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v)
     return old;
 }
 
+inline unsigned long long atomicMin_system(unsigned long long *p, unsigned long long v) { return atomicMin(p, v); }
+inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+
 // ---- integer intrinsics ----------------------------------------------------------------------------------
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline unsigned __vimin3_u32(unsigned a, unsigned b, unsigned c) { unsigned m = a < b ? a : b; return m < c ? m : c; }

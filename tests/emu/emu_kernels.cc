@@ -10,6 +10,7 @@
 #include "score_pairs_sparse.cuh"
 #include "place_sequential.cuh"
 #include "sparse_work.h"
+#include "peer_exchange.cuh"
 
 
 namespace {
@@ -92,6 +93,17 @@ void emu_score_sparse(const int32_t *topo, const int32_t *free_mask, const int32
     if (flag) { if (byte_keys) EMU_SPARSE(true, true); else EMU_SPARSE(true, false); }
 #undef EMU_SPARSE
     free(topo4); free(pods4); free(mem); free(cpair); free(perm);
+}
+
+// The peer-exchange kernel with world = 1 (the rank pushes into its own result array and passes its own
+// barrier): exercises the push, the last-block ticket and the flag protocol, not the cross-GPU part.
+void emu_push_and_sync(const unsigned long long *local, int64_t P, unsigned long long *result, uint32_t *flags,
+                       uint32_t epoch, unsigned int *ticket) {
+    kgpu::PeerTable tab;
+    std::memset(&tab, 0, sizeof tab);
+    tab.results[0] = result;
+    tab.flags[0] = flags;
+    emu::launch(dim3((unsigned)((P + 255) / 256)), dim3(256), [&] { kgpu::push_and_sync(local, P, tab, 0, 1, epoch, ticket); });
 }
 
 // The host-side work-list builder alone (sparse_work.h): items as int32[.][4], returns the count.

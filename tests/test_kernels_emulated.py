@@ -236,3 +236,24 @@ def test_emulated_ragged_sizes(emu, oracle_b, kernel):
     none_free = np.zeros(5, dtype=np.int32)
     got = _run(fn, topo[:5], none_free, pods[:16], W)
     assert (got == oracle_b.score_batch(topo[:5], none_free, pods[:16], W)).all()
+
+
+def test_emulated_push_and_sync_single_rank(emu):
+    """peer_exchange.cuh with world = 1: pushes land (NO_FIT is not sent), the last block resets the ticket
+    and publishes the epoch; a second epoch into the same array keeps the minimum."""
+    emu.emu_push_and_sync.restype = None
+    P = 700
+    rng = np.random.default_rng(3)
+    local = rng.integers(1, 2**60, size=P, dtype=np.uint64)
+    local[::7] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    result = np.full(P, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)
+    flags = np.zeros(16, dtype=np.uint32)
+    ticket = np.zeros(1, dtype=np.uint32)
+    u64, u32 = ctypes.c_uint64, ctypes.c_uint32
+    emu.emu_push_and_sync(_p(local, u64), ctypes.c_int64(P), _p(result, u64), _p(flags, u32), 1, _p(ticket, u32))
+    assert (result == local).all() and flags[0] == 1 and ticket[0] == 0
+    lower = local.copy()
+    lower[5:50] = np.uint64(7)
+    lower[::7] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    emu.emu_push_and_sync(_p(lower, u64), ctypes.c_int64(P), _p(result, u64), _p(flags, u32), 2, _p(ticket, u32))
+    assert (result == np.minimum(local, lower)).all() and flags[0] == 2 and ticket[0] == 0
