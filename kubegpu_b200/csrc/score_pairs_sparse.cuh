@@ -57,11 +57,21 @@ __device__ __forceinline__ uint32_t node_key_kf(const PairCosts &C, const PipeCo
 
 // Per-warp pod table of a chunk, in BUCKET order (pods grouped by k): the per-pod multiplier the
 // enumeration runs on (see score_pairs.cuh: it makes every instruction of the enumeration depend on
-// per-pod data) next to the slot the warp's result for that pod goes to.  A bucket loop walks one
-// pointer over this table: LDS [ptr], ..., STS [ptr + 4].
-struct alignas(8) SpEnt {
-    uint32_t one;       // MEM: the pod's min_mem instead (the MEM loops derive `one` from K)
-    uint32_t best;      // warp key of the best (node, subset) of this warp for the pod, INF32 = none
+// per-pod data) next to the slot the warp's result for that pod goes to.  Pods sit in groups of
+// SP_GROUP; a bucket loop handles one group per trip: one LDS of the multipliers, the enumerations, one
+// STS of the results, loop control once.  Buckets are padded to whole groups with dummy pods
+// (multiplier 1, result never read: sIdx marks them).
+#ifndef KGPU_SP_GROUP
+#define KGPU_SP_GROUP 2          // pods per trip of a bucket loop: 1 or 2
+#endif
+constexpr int SP_GROUP = KGPU_SP_GROUP;
+static_assert(SP_GROUP == 1 || SP_GROUP == 2, "KGPU_SP_GROUP must be 1 or 2");
+constexpr int SP_POS = SP_CHUNK + 10 * (SP_GROUP - 1);          // positions of a chunk in bucket order, dummies included
+constexpr int SP_TAB = (SP_POS + SP_GROUP - 1) / SP_GROUP;      // groups
+constexpr uint16_t SP_DUMMY = 0xFFFFu;
+struct alignas(8 * KGPU_SP_GROUP) SpEnt {
+    uint32_t one[SP_GROUP];     // MEM: the pods' min_mem instead (the MEM loops derive `one` from K)
+    uint32_t best[SP_GROUP];    // warp key of the best (node, subset) of this warp for the pod, INF32 = none
 };
 
 // Warp key.  BYTE_KEYS (every cost < 2^16, i.e. every weight <= 2340): cost<<16 | lane<<8 | S, built
@@ -95,42 +105,55 @@ __device__ __forceinline__ void sp_bucket(const PairCosts &C, const PipeConsts p
     const SpFmt fmt = sp_fmt<BYTE_KEYS>(lane_field, MEM ? true : (valid && nfree >= need_free));
     const uint32_t thirty_two = pc.one << 5;       // a register, so that the shift is an IMAD (kernel parameter: opaque)
     KGPU_UNROLL((sp_unroll(K, F)))
-    // byte offsets: uniform (begin, end come from shared memory), so the loop runs on the uniform datapath
-    // and the entry address is tab + offset with no arithmetic of its own
-    for (uint32_t off = (uint32_t)begin * (uint32_t)sizeof(SpEnt); off != (uint32_t)end * (uint32_t)sizeof(SpEnt);
-         off += (uint32_t)sizeof(SpEnt)) {
+    // byte offsets (8 bytes per position, begin and end are whole groups): uniform, because begin and end
+    // come from shared memory, so the loop runs on the uniform datapath and the group address is tab + offset
+    for (uint32_t off = (uint32_t)begin * 8u; off != (uint32_t)end * 8u; off += (uint32_t)sizeof(SpEnt)) {
         SpEnt *const ent = reinterpret_cast<SpEnt *>(reinterpret_cast<char *>(tab) + off);
-        PipeConsts pcl = pc;
-        uint32_t v;
-        if (MEM) {
-            const int32_t need = (int32_t)ent->one;
-            uint32_t pen[8], elig = 0;
-#pragma unroll
-            for (int g = 0; g < 8; g++) {
-                const bool lt = mem[g] < need;
-                pen[g] = lt ? PEN : 0u;
-                if (!lt && (uint32_t)g < nfree) elig |= 1u << g;      // position g: free and big enough
-            }
-            uint32_t key;
-            if (K == 0) key = valid ? 0u : INF32;
-            else if (K == 1) key = elig ? (elig & (0u - elig)) : INF32;
-            else {
-                PairCosts C2;
-                apply_pens(C, C2, pen);
-                key = best_kf<(K < 2 ? 2 : K), (F < 2 ? 2 : F)>(C2, pcl);
-            }
-            v = key >= PEN ? INF32 : sp_warp_key<BYTE_KEYS>(key, fmt, thirty_two);
+        uint32_t ones[SP_GROUP], v[SP_GROUP];
+        if (SP_GROUP == 2) {
+            const uint2 o = *reinterpret_cast<const uint2 *>(ent->one);      // one LDS.64
+            ones[0] = o.x; ones[SP_GROUP - 1] = o.y;
         } else {
-            if (PER_PAIR) {                        // un-hoistable per-pair work: see score_pairs.cuh
-                pcl.one = ent->one;
-                if (K >= 5) pcl.minus_one = 0u - pcl.one;
-            }
-            // lanes that cannot serve K (fmt says so) compute a key like the others and drop it
-            const uint32_t key = K == 0 ? 0u : K == 1 ? pcl.one : best_kf<(K < 2 ? 2 : K), (F < 2 ? 2 : F)>(C, pcl);
-            v = sp_warp_key<BYTE_KEYS>(key, fmt, thirty_two);
+            ones[0] = ent->one[0];
         }
-        const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, v);
-        if (lane_field == 0) ent->best = m;
+#pragma unroll
+        for (int g = 0; g < SP_GROUP; g++) {
+            PipeConsts pcl = pc;
+            if (MEM) {
+                const int32_t need = (int32_t)ones[g];
+                uint32_t pen[8], elig = 0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const bool lt = mem[q] < need;
+                    pen[q] = lt ? PEN : 0u;
+                    if (!lt && (uint32_t)q < nfree) elig |= 1u << q;      // position q: free and big enough
+                }
+                uint32_t key;
+                if (K == 0) key = valid ? 0u : INF32;
+                else if (K == 1) key = elig ? (elig & (0u - elig)) : INF32;
+                else {
+                    PairCosts C2;
+                    apply_pens(C, C2, pen);
+                    key = best_kf<(K < 2 ? 2 : K), (F < 2 ? 2 : F)>(C2, pcl);
+                }
+                v[g] = key >= PEN ? INF32 : sp_warp_key<BYTE_KEYS>(key, fmt, thirty_two);
+            } else {
+                if (PER_PAIR) {                        // un-hoistable per-pair work: see score_pairs.cuh
+                    pcl.one = ones[g];
+                    if (K >= 5) pcl.minus_one = 0u - pcl.one;
+                }
+                // lanes that cannot serve K (fmt says so) compute a key like the others and drop it
+                const uint32_t key = K == 0 ? 0u : K == 1 ? pcl.one : best_kf<(K < 2 ? 2 : K), (F < 2 ? 2 : F)>(C, pcl);
+                v[g] = sp_warp_key<BYTE_KEYS>(key, fmt, thirty_two);
+            }
+        }
+        uint32_t m[SP_GROUP];
+#pragma unroll
+        for (int g = 0; g < SP_GROUP; g++) m[g] = __reduce_min_sync(0xFFFFFFFFu, v[g]);
+        if (lane_field == 0) {
+            if (SP_GROUP == 2) *reinterpret_cast<uint2 *>(ent->best) = make_uint2(m[0], m[SP_GROUP - 1]);   // one STS.64
+            else ent->best[0] = m[0];
+        }
     }
 }
 
@@ -228,8 +251,9 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
     if (MEM && *mem_flag == 0) return;
     __shared__ int32_t sCnt[10], sOff[11];
     __shared__ uint8_t sK[SP_CHUNK];
-    __shared__ uint16_t sIdx[SP_CHUNK];                // bucket order -> chunk position
-    __shared__ SpEnt sTab[SP_WARPS][SP_CHUNK];         // per warp, bucket order: multiplier | result
+    __shared__ int32_t sReal[10];                      // pods per bucket before padding to whole groups
+    __shared__ uint16_t sIdx[SP_POS];                  // bucket-order position -> chunk position (SP_DUMMY: padding)
+    __shared__ SpEnt sTab[SP_WARPS][SP_TAB];           // per warp, bucket order: multipliers | results
     __shared__ uint32_t sHotLo[SP_THREADS], sHotHi[SP_THREADS];   // position g -> byte (1 << GPU index), g = 0..3 | 4..7
     __shared__ int32_t sNode[SP_THREADS];              // slot -> node index (-1 = padding)
 
@@ -308,7 +332,11 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
         if (tid == 0) {
             int acc = 0;
 #pragma unroll
-            for (int b = 0; b < 10; b++) { sOff[b] = acc; acc += sCnt[b]; sCnt[b] = sOff[b]; }
+            for (int b = 0; b < 10; b++) {         // every bucket starts on a group boundary
+                sOff[b] = acc; sReal[b] = sCnt[b];
+                acc += (sCnt[b] + SP_GROUP - 1) / SP_GROUP * SP_GROUP;
+                sCnt[b] = sOff[b];
+            }
             sOff[10] = acc;
         }
         __syncthreads();
@@ -316,12 +344,22 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
             const int b = sK[i];
             const int at = atomicAdd(&sCnt[b], 1);
             sIdx[at] = (uint16_t)i;
-            SpEnt e;
             // the per-pod multiplier: the pod's own k less what its bucket adds back (= 1 at run time)
-            e.one = MEM ? (uint32_t)__ldg(pods4 + c0 + i).w : (uint32_t)(__ldg(pods4 + c0 + i).x - (b < 9 ? b - 1 : 0));
-            e.best = INF32;                                          // warps skip the pods they cannot serve
+            const uint32_t one = MEM ? (uint32_t)__ldg(pods4 + c0 + i).w : (uint32_t)(__ldg(pods4 + c0 + i).x - (b < 9 ? b - 1 : 0));
 #pragma unroll
-            for (int w = 0; w < SP_WARPS; w++) sTab[w][at] = e;
+            for (int w = 0; w < SP_WARPS; w++) {
+                sTab[w][at / SP_GROUP].one[at % SP_GROUP] = one;
+                sTab[w][at / SP_GROUP].best[at % SP_GROUP] = INF32;          // warps skip the pods they cannot serve
+            }
+        }
+        if (SP_GROUP > 1 && tid < 10 && (sReal[tid] % SP_GROUP) != 0) {    // the bucket's padding: a dummy pod
+            const int at = sOff[tid] + sReal[tid];
+            sIdx[at] = SP_DUMMY;
+#pragma unroll
+            for (int w = 0; w < SP_WARPS; w++) {
+                sTab[w][at / SP_GROUP].one[at % SP_GROUP] = MEM ? 0u : 1u;
+                sTab[w][at / SP_GROUP].best[at % SP_GROUP] = INF32;
+            }
         }
         __syncthreads();
 
@@ -342,17 +380,18 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
         // otherwise (a tile of two classes) node ids are compared explicitly.
         const int served = sOff[9];                // bucket 9 (not for this launch) sits at the end
         for (int i = tid; i < served; i += SP_THREADS) {
+            if (SP_GROUP > 1 && sIdx[i] == SP_DUMMY) continue;
             uint32_t best_m = INF32, cost = 0;
             int best_slot = -1;
             if (BYTE_KEYS && ordered) {
 #pragma unroll
-                for (int w = 0; w < SP_WARPS; w++) best_m = min(best_m, sTab[w][i].best | ((uint32_t)w << 13));   // INF32 stays INF32
+                for (int w = 0; w < SP_WARPS; w++) best_m = min(best_m, sTab[w][i / SP_GROUP].best[i % SP_GROUP] | ((uint32_t)w << 13));   // INF32 stays INF32
                 if (best_m != INF32) { best_slot = (int)((best_m >> 8) & (uint32_t)(SP_THREADS - 1)); cost = best_m >> 16; }
             } else {
                 unsigned long long best = ~0ull;   // cost<<32 | node index
 #pragma unroll
                 for (int w = 0; w < SP_WARPS; w++) {
-                    const uint32_t m = sTab[w][i].best;
+                    const uint32_t m = sTab[w][i / SP_GROUP].best[i % SP_GROUP];
                     if (m == INF32) continue;
                     const int s = w * 32 + (int)((m >> 8) & 31u);
                     const unsigned long long cand = ((unsigned long long)(m >> (BYTE_KEYS ? 16 : 13)) << 32) | (uint32_t)sNode[s];

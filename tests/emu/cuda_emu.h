@@ -29,6 +29,10 @@ struct int4 {
     int x, y, z, w;
 };
 inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+struct alignas(8) uint2 {
+    unsigned x, y;
+};
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 struct dim3 {
     unsigned x = 1, y = 1, z = 1;
     dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
