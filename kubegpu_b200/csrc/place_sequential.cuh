@@ -37,7 +37,7 @@ constexpr int PLACE_TILE = 128;
 constexpr int PLACE_THREADS = KGPU_PLACE_THREADS;
 constexpr int PLACE_WARPS = PLACE_THREADS / 32;
 constexpr int PLACE_MAX_VIEWS = 8;
-constexpr int PLACE_SUPER_CAP = 5376;       // uint64 entries of static shared memory (42 KB) for super[][][]
+constexpr int PLACE_SUPER_CAP = 4608;       // uint64 entries of static shared memory (36 KB) for super[][][]
 
 struct PlaceViews {
     int32_t n;                              // 1 .. PLACE_MAX_VIEWS
@@ -111,21 +111,47 @@ place_init(const int4 *__restrict__ topo4, const int32_t *__restrict__ free_mask
     }
 }
 
+// Subset costs of one node from half tables.  With the 8 GPUs split into halves lo = GPUs 0..3, hi = GPUs 4..7,
+//   cost(S) = A[S_lo] + B[S_hi] + sum over i in S_lo of R[i][S_hi]
+// A, B: link cost inside a half (16 entries each); R[i][h]: links from GPU i of the low half to the GPUs of
+// h (4 x 16 entries).  The warp builds the 96 entries once per placement (three per lane, a handful of adds
+// each); a subset then costs two loads and at most four predicated load-adds instead of 28 tests.
+constexpr int PLACE_HALF = 96;
+__device__ __forceinline__ void build_half_tables(const int32_t *sCost, int32_t *half, int lane) {
+    {
+        const int m = lane & 15, base = lane < 16 ? 0 : 4;
+        int32_t a = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = i + 1; j < 4; j++)
+                if (((m >> i) & 1) && ((m >> j) & 1)) a += sCost[(base + i) * 8 + base + j];
+        half[lane] = a;                                   // A at [0,16), B at [16,32)
+    }
+#pragma unroll
+    for (int e = lane; e < 64; e += 32) {                 // R[i][h] at [32 + 16 i + h]
+        const int i = e >> 4, h = e & 15;
+        int32_t r = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if ((h >> j) & 1) r += sCost[i * 8 + 4 + j];
+        half[32 + e] = r;
+    }
+}
+
 // (cost<<8 | S) of one node for k GPUs, computed by a whole warp: lane per candidate subset.
-// sCost = the node's weight-mapped 8x8 matrix in shared memory.
-__device__ __forceinline__ uint32_t node_key_warp(int k, const int32_t *sCost, uint32_t fm, int lane) {
+__device__ __forceinline__ uint32_t node_key_warp(int k, const int32_t *half, uint32_t fm, int lane) {
     if (k == 0) return 0u;
     const int nsub = c_nsub[k];
     uint32_t key = INF32;
     for (int s = lane; s < nsub; s += 32) {
         const uint32_t S = c_subsets[k][s];
         if (S & ~fm) continue;
-        uint32_t cost = 0;
+        const uint32_t lo = S & 15u, hi = S >> 4;
+        uint32_t cost = (uint32_t)half[lo] + (uint32_t)half[16 + hi];
 #pragma unroll
-        for (int i = 0; i < 8; i++)
-#pragma unroll
-            for (int j = i + 1; j < 8; j++)
-                if ((S & ((1u << i) | (1u << j))) == ((1u << i) | (1u << j))) cost += (uint32_t)sCost[i * 8 + j];
+        for (int i = 0; i < 4; i++)
+            if ((lo >> i) & 1u) cost += (uint32_t)half[32 + 16 * i + hi];
         key = min(key, (cost << 8) | S);
     }
     return __reduce_min_sync(0xFFFFFFFFu, key);
@@ -139,6 +165,7 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
     __shared__ int32_t sW[16];
     __shared__ int32_t sViewMin[PLACE_MAX_VIEWS];                 // static indexing of the kernel parameter only
     __shared__ int32_t sCost[PLACE_WARPS][64];                    // per warp: the winner node's cost matrix
+    __shared__ int32_t sHalf[PLACE_WARPS][PLACE_HALF];            // per warp: its half tables (node_key_warp)
     __shared__ unsigned long long sRed[2][PLACE_WARPS];           // double buffered by pod parity
     __shared__ unsigned long long sSuper[PLACE_SUPER_CAP];        // super[v][k][ST]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -195,6 +222,9 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
             const uint32_t fm = ((uint32_t)free_mask[node] & 0xFFu) & ~S;
             const int32_t my_mem = (gpu_mem != nullptr && lane < 8) ? __ldg(gpu_mem + node * 8 + lane) : 0x7FFFFFFF;
             __syncwarp();
+            int32_t *half = sHalf[warp];
+            build_half_tables(cost, half, lane);
+            __syncwarp();
             if (warp == 0 && lane == 0) free_mask[node] = (int32_t)fm;
             for (int task = warp; task < V * 9; task += PLACE_WARPS) {
                 const int tv = task / 9, tk = task % 9;
@@ -207,7 +237,7 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
                 for (int64_t t = st * super_tiles + lane; t < min(T, (st + 1) * super_tiles); t += 32)
                     if (t != tile) sb = min(sb, tilebest[vk * T + t]);
                 const uint32_t ok = tv == 0 ? 0xFFu : (__ballot_sync(0xFFFFFFFFu, my_mem >= sViewMin[tv]) & 0xFFu);
-                const uint32_t nk = node_key_warp(tk, cost, fm & ok, lane);
+                const uint32_t nk = node_key_warp(tk, half, fm & ok, lane);
                 if (lane == 0) nodebest[vk * Npad + node] = nk;
                 unsigned long long tb = ~0ull;
 #pragma unroll
