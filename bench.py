@@ -248,7 +248,7 @@ def main():
     ap.add_argument("--impl", default="kgpu", choices=["kgpu", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "push"],
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "allreduce", "push"],
                     help="multi-GPU key exchange: NCCL all-gather + K2 (default, measured in round 1) or the "
                          "(round-2 prep, untested) peer-memory push kernel of kgpu_score_batch_exchange")
     ap.add_argument("--graph", action="store_true",
@@ -260,7 +260,7 @@ def main():
     import torch
     import torch.distributed as dist
     from kubegpu_b200 import _lib, synth
-    from kubegpu_b200.distributed import shard_range
+    from kubegpu_b200.distributed import all_reduce_min_keys, shard_range
     from kubegpu_b200.scorer import Scorer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -325,6 +325,8 @@ def main():
                 wrapped[ptr] = torch.as_tensor(_DeviceKeys(ptr), device=dev)
             return wrapped[ptr]
         scorer.score_batch_device(d_pods.data_ptr(), N_PODS, d_local.data_ptr(), sptr, _lib.BATCH_NO_MIN_MEM)
+        if world > 1 and args.exchange == "allreduce":          # one collective, no K2 (round-2 experiment)
+            return all_reduce_min_keys(d_local)
         if world > 1:
             dist.all_gather_into_tensor(d_gather.view(-1), d_local)
             scorer.reduce_shards_device(d_gather.data_ptr(), world, N_PODS, d_final.data_ptr(), sptr)
@@ -374,7 +376,9 @@ def main():
         else:
             scorer.score_batch_device(d_pods.data_ptr(), N_PODS, d_local.data_ptr(), sptr, _lib.BATCH_NO_MIN_MEM)
             ev[i][1].record(stream)                    # K1 only: roofline numerator
-            if world > 1:
+            if world > 1 and args.exchange == "allreduce":
+                all_reduce_min_keys(d_local)
+            elif world > 1:
                 dist.all_gather_into_tensor(d_gather.view(-1), d_local)
                 scorer.reduce_shards_device(d_gather.data_ptr(), world, N_PODS, d_final.data_ptr(), sptr)
         ev[i][2].record(stream)
@@ -452,7 +456,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "nodes": N_NODES, "pods": N_PODS,
-                       "parallelism": ("node list sharded over %d GPU(s), " % world + ("peer-memory push + flag barrier (1 kernel)" if push else "1 NCCL all-gather + K2")) if world > 1 else "1 GPU, no collective",
+                       "parallelism": ("node list sharded over %d GPU(s), " % world + ("peer-memory push + flag barrier (1 kernel)" if push else "1 NCCL all-reduce(min)" if args.exchange == "allreduce" else "1 NCCL all-gather + K2")) if world > 1 else "1 GPU, no collective",
                        "kernel": "score_pairs_sparse (per pair: every k-subset of the node's free-GPU positions)",
                        "l2": "flushed between timed iterations (256 MiB write); node array is 26 MB < L2"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
