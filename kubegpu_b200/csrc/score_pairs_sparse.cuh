@@ -69,6 +69,7 @@ static_assert(SP_GROUP == 1 || SP_GROUP == 2, "KGPU_SP_GROUP must be 1 or 2");
 constexpr int SP_POS = SP_CHUNK + 10 * (SP_GROUP - 1);          // positions of a chunk in bucket order, dummies included
 constexpr int SP_TAB = (SP_POS + SP_GROUP - 1) / SP_GROUP;      // groups
 constexpr uint16_t SP_DUMMY = 0xFFFFu;
+constexpr int SP_MEM_SUB = 4;        // MEM launch: pods of one k are sub-bucketed by a hash of min_mem, so equal requirements sit together
 struct alignas(8 * KGPU_SP_GROUP) SpEnt {
     uint32_t one[SP_GROUP];     // MEM: the pods' min_mem instead (the MEM loops derive `one` from K)
     uint32_t best[SP_GROUP];    // warp key of the best (node, subset) of this warp for the pod, INF32 = none
@@ -104,6 +105,9 @@ __device__ __forceinline__ void sp_bucket(const PairCosts &C, const PipeConsts p
     const uint32_t need_free = (uint32_t)K + ((uint32_t)begin >> 30);
     const SpFmt fmt = sp_fmt<BYTE_KEYS>(lane_field, MEM ? true : (valid && nfree >= need_free));
     const uint32_t thirty_two = pc.one << 5;       // a register, so that the shift is an IMAD (kernel parameter: opaque)
+    int32_t last_need = -1;                        // MEM: the requirement C2 / elig were last built for
+    uint32_t elig = 0;
+    PairCosts C2 = C;
     KGPU_UNROLL((sp_unroll(K, F)))
     // byte offsets (8 bytes per position, begin and end are whole groups): uniform, because begin and end
     // come from shared memory, so the loop runs on the uniform datapath and the group address is tab + offset
@@ -121,21 +125,22 @@ __device__ __forceinline__ void sp_bucket(const PairCosts &C, const PipeConsts p
             PipeConsts pcl = pc;
             if (MEM) {
                 const int32_t need = (int32_t)ones[g];
-                uint32_t pen[8], elig = 0;
+                if (need != last_need) {               // warp-uniform; rare: the sort puts equal requirements together
+                    last_need = need;
+                    uint32_t pen[8];
+                    elig = 0;
 #pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    const bool lt = mem[q] < need;
-                    pen[q] = lt ? PEN : 0u;
-                    if (!lt && (uint32_t)q < nfree) elig |= 1u << q;      // position q: free and big enough
+                    for (int q = 0; q < 8; q++) {
+                        const bool lt = mem[q] < need;
+                        pen[q] = lt ? PEN : 0u;
+                        if (!lt && (uint32_t)q < nfree) elig |= 1u << q;      // position q: free and big enough
+                    }
+                    if (K >= 2) apply_pens(C, C2, pen);
                 }
                 uint32_t key;
                 if (K == 0) key = valid ? 0u : INF32;
                 else if (K == 1) key = elig ? (elig & (0u - elig)) : INF32;
-                else {
-                    PairCosts C2;
-                    apply_pens(C, C2, pen);
-                    key = best_kf<(K < 2 ? 2 : K), (F < 2 ? 2 : F)>(C2, pcl);
-                }
+                else key = best_kf<(K < 2 ? 2 : K), (F < 2 ? 2 : F)>(C2, pcl);
                 v[g] = key >= PEN ? INF32 : sp_warp_key<BYTE_KEYS>(key, fmt, thirty_two);
             } else {
                 if (PER_PAIR) {                        // un-hoistable per-pair work: see score_pairs.cuh
@@ -249,9 +254,9 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
                    const int *__restrict__ mem_flag, int64_t node_id_base, const int4 *__restrict__ pods4, int64_t P,
                    int pods_per_split, const int4 *__restrict__ work, PipeConsts pc, unsigned long long *__restrict__ keys) {
     if (MEM && *mem_flag == 0) return;
-    __shared__ int32_t sCnt[10], sOff[11];
+    constexpr int SUB = MEM ? SP_MEM_SUB : 1, NB = 9 * SUB + 1;     // sort buckets: (k, sub) for k = 0..8, then "not for this launch"
+    __shared__ int32_t sCnt[NB], sOff[11], sPad[9];
     __shared__ uint8_t sK[SP_CHUNK];
-    __shared__ int32_t sReal[10];                      // pods per bucket before padding to whole groups
     __shared__ uint16_t sIdx[SP_POS];                  // bucket-order position -> chunk position (SP_DUMMY: padding)
     __shared__ SpEnt sTab[SP_WARPS][SP_TAB];           // per warp, bucket order: multipliers | results
     __shared__ uint32_t sHotLo[SP_THREADS], sHotHi[SP_THREADS];   // position g -> byte (1 << GPU index), g = 0..3 | 4..7
@@ -319,25 +324,31 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
     for (int64_t c0 = p_begin; c0 < p_end; c0 += SP_CHUNK) {
         const int cn = (int)min((int64_t)SP_CHUNK, p_end - c0);
         __syncthreads();
-        if (tid < 10) sCnt[tid] = 0;
+        if (tid < NB) sCnt[tid] = 0;
         __syncthreads();
         for (int i = tid; i < cn; i += SP_THREADS) {
             const int4 req = __ldg(pods4 + c0 + i);
             const bool wants_mem = req.w > 0;
-            const int b = (req.x < 0 || req.x > 8 || wants_mem != MEM) ? 9 : req.x;
+            int b = 9 * SUB;
+            if (req.x >= 0 && req.x <= 8 && wants_mem == MEM)
+                b = req.x * SUB + (MEM ? (int)(((uint32_t)req.w * 0x9E3779B1u) >> 30) : 0);
             sK[i] = (uint8_t)b;
             atomicAdd(&sCnt[b], 1);
         }
         __syncthreads();
-        if (tid == 0) {
+        if (tid == 0) {                            // sOff[k]: where k's pods start (a group boundary); sCnt: running positions
             int acc = 0;
-#pragma unroll
-            for (int b = 0; b < 10; b++) {         // every bucket starts on a group boundary
-                sOff[b] = acc; sReal[b] = sCnt[b];
-                acc += (sCnt[b] + SP_GROUP - 1) / SP_GROUP * SP_GROUP;
-                sCnt[b] = sOff[b];
+#pragma unroll 1
+            for (int k = 0; k < 9; k++) {
+                sOff[k] = acc;
+                for (int u = 0; u < SUB; u++) { const int c = sCnt[k * SUB + u]; sCnt[k * SUB + u] = acc; acc += c; }
+                sPad[k] = acc % SP_GROUP ? acc : -1;                 // position of k's dummy pod, if it needs one
+                acc = (acc + SP_GROUP - 1) / SP_GROUP * SP_GROUP;
             }
-            sOff[10] = acc;
+            sOff[9] = acc;
+            const int c9 = sCnt[9 * SUB];
+            sCnt[9 * SUB] = acc;
+            sOff[10] = acc + c9;
         }
         __syncthreads();
         for (int i = tid; i < cn; i += SP_THREADS) {
@@ -345,15 +356,16 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
             const int at = atomicAdd(&sCnt[b], 1);
             sIdx[at] = (uint16_t)i;
             // the per-pod multiplier: the pod's own k less what its bucket adds back (= 1 at run time)
-            const uint32_t one = MEM ? (uint32_t)__ldg(pods4 + c0 + i).w : (uint32_t)(__ldg(pods4 + c0 + i).x - (b < 9 ? b - 1 : 0));
+            const int4 req = __ldg(pods4 + c0 + i);
+            const uint32_t one = MEM ? (uint32_t)req.w : (uint32_t)(req.x - (b < 9 ? b - 1 : 0));
 #pragma unroll
             for (int w = 0; w < SP_WARPS; w++) {
                 sTab[w][at / SP_GROUP].one[at % SP_GROUP] = one;
                 sTab[w][at / SP_GROUP].best[at % SP_GROUP] = INF32;          // warps skip the pods they cannot serve
             }
         }
-        if (SP_GROUP > 1 && tid < 10 && (sReal[tid] % SP_GROUP) != 0) {    // the bucket's padding: a dummy pod
-            const int at = sOff[tid] + sReal[tid];
+        if (SP_GROUP > 1 && tid < 9 && sPad[tid] >= 0) {                   // k's padding: a dummy pod
+            const int at = sPad[tid];
             sIdx[at] = SP_DUMMY;
 #pragma unroll
             for (int w = 0; w < SP_WARPS; w++) {
