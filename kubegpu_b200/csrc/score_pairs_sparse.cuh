@@ -62,10 +62,10 @@ __device__ __forceinline__ uint32_t node_key_kf(const PairCosts &C, const PipeCo
 // STS of the results, loop control once.  Buckets are padded to whole groups with dummy pods
 // (multiplier 1, result never read: sIdx marks them).
 #ifndef KGPU_SP_GROUP
-#define KGPU_SP_GROUP 2          // pods per trip of a bucket loop: 1 or 2
+#define KGPU_SP_GROUP 2          // pods per trip of a bucket loop: 1, 2 or 4
 #endif
 constexpr int SP_GROUP = KGPU_SP_GROUP;
-static_assert(SP_GROUP == 1 || SP_GROUP == 2, "KGPU_SP_GROUP must be 1 or 2");
+static_assert(SP_GROUP == 1 || SP_GROUP == 2 || SP_GROUP == 4, "KGPU_SP_GROUP must be 1, 2 or 4");
 constexpr int SP_POS = SP_CHUNK + 10 * (SP_GROUP - 1);          // positions of a chunk in bucket order, dummies included
 constexpr int SP_TAB = (SP_POS + SP_GROUP - 1) / SP_GROUP;      // groups
 constexpr uint16_t SP_DUMMY = 0xFFFFu;
@@ -114,9 +114,12 @@ __device__ __forceinline__ void sp_bucket(const PairCosts &C, const PipeConsts p
     for (uint32_t off = (uint32_t)begin * 8u; off != (uint32_t)end * 8u; off += (uint32_t)sizeof(SpEnt)) {
         SpEnt *const ent = reinterpret_cast<SpEnt *>(reinterpret_cast<char *>(tab) + off);
         uint32_t ones[SP_GROUP], v[SP_GROUP];
-        if (SP_GROUP == 2) {
+        if (SP_GROUP == 4) {
+            const uint4 o = *reinterpret_cast<const uint4 *>(ent->one);      // one LDS.128
+            ones[0] = o.x; ones[1 % SP_GROUP] = o.y; ones[2 % SP_GROUP] = o.z; ones[3 % SP_GROUP] = o.w;
+        } else if (SP_GROUP == 2) {
             const uint2 o = *reinterpret_cast<const uint2 *>(ent->one);      // one LDS.64
-            ones[0] = o.x; ones[SP_GROUP - 1] = o.y;
+            ones[0] = o.x; ones[1 % SP_GROUP] = o.y;
         } else {
             ones[0] = ent->one[0];
         }
@@ -156,7 +159,8 @@ __device__ __forceinline__ void sp_bucket(const PairCosts &C, const PipeConsts p
 #pragma unroll
         for (int g = 0; g < SP_GROUP; g++) m[g] = __reduce_min_sync(0xFFFFFFFFu, v[g]);
         if (lane_field == 0) {
-            if (SP_GROUP == 2) *reinterpret_cast<uint2 *>(ent->best) = make_uint2(m[0], m[SP_GROUP - 1]);   // one STS.64
+            if (SP_GROUP == 4) *reinterpret_cast<uint4 *>(ent->best) = make_uint4(m[0], m[1 % SP_GROUP], m[2 % SP_GROUP], m[3 % SP_GROUP]);
+            else if (SP_GROUP == 2) *reinterpret_cast<uint2 *>(ent->best) = make_uint2(m[0], m[1 % SP_GROUP]);   // one STS.64
             else ent->best[0] = m[0];
         }
     }

@@ -13,8 +13,8 @@ for mb in 8 7 6; do for us in 1 2; do for sm in 6 15; do
   python scripts/k1_time.py --config c2 --variants 5 --reps 8 | cut -c1-100 | tee -a $out
   python scripts/k1_time.py --config c3 --variants 5 --reps 6 | cut -c1-100 | tee -a $out
 done; done; done
-# one pod per trip (KGPU_SP_GROUP=1) against the default of two
-for g in 1 2; do
+# pods per trip of a bucket loop: 1, 2 (default), 4 (7.8k instructions of code: instruction cache?)
+for g in 1 2 4; do
   flags="-DKGPU_SP_GROUP=$g"
   regs=$(make -s EXTRA="$flags" -B kubegpu_b200/lib/libkgpu.so 2>&1 | grep -A2 'score_pairs_sparseILb1ELb0ELb1' | grep -E 'Used|spill' | sed 's/ptxas info    : //; s/, used 1 barriers.*//; s/bytes stack frame, //' | tr '\n' ' ')
   echo "$flags :: $regs" | tee -a $out
