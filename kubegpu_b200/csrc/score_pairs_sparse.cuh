@@ -346,7 +346,7 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
             for (int k = 0; k < 9; k++) {
                 sOff[k] = acc;
                 for (int u = 0; u < SUB; u++) { const int c = sCnt[k * SUB + u]; sCnt[k * SUB + u] = acc; acc += c; }
-                sPad[k] = acc % SP_GROUP ? acc : -1;                 // position of k's dummy pod, if it needs one
+                sPad[k] = acc % SP_GROUP ? acc : -1;                 // position of k's first dummy pod, if it needs any
                 acc = (acc + SP_GROUP - 1) / SP_GROUP * SP_GROUP;
             }
             sOff[9] = acc;
@@ -368,13 +368,14 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
                 sTab[w][at / SP_GROUP].best[at % SP_GROUP] = INF32;          // warps skip the pods they cannot serve
             }
         }
-        if (SP_GROUP > 1 && tid < 9 && sPad[tid] >= 0) {                   // k's padding: a dummy pod
-            const int at = sPad[tid];
-            sIdx[at] = SP_DUMMY;
+        if (SP_GROUP > 1 && tid < 9 && sPad[tid] >= 0) {                   // k's padding: dummy pods up to the group boundary
+            for (int at = sPad[tid]; at % SP_GROUP != 0; at++) {
+                sIdx[at] = SP_DUMMY;
 #pragma unroll
-            for (int w = 0; w < SP_WARPS; w++) {
-                sTab[w][at / SP_GROUP].one[at % SP_GROUP] = MEM ? 0u : 1u;
-                sTab[w][at / SP_GROUP].best[at % SP_GROUP] = INF32;
+                for (int w = 0; w < SP_WARPS; w++) {
+                    sTab[w][at / SP_GROUP].one[at % SP_GROUP] = MEM ? 0u : 1u;
+                    sTab[w][at / SP_GROUP].best[at % SP_GROUP] = INF32;
+                }
             }
         }
         __syncthreads();

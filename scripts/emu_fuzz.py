@@ -26,9 +26,18 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=300)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--define", action="append", default=[], help="build knob for a private emulation build, e.g. KGPU_SP_GROUP=4")
     a = ap.parse_args()
-    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu")])
-    L = ctypes.CDLL(os.path.join(ROOT, "tests", "emu", "_build", "libkgpu_emu.so"))
+    emu_dir = os.path.join(ROOT, "tests", "emu")
+    if a.define:
+        lib = "/tmp/libkgpu_emu_%s.so" % "_".join(d.replace("=", "") for d in a.define)
+        subprocess.check_call(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread"] + ["-D" + d for d in a.define] +
+                              ["-I" + os.path.join(emu_dir, "stub"), "-I" + os.path.join(ROOT, "kubegpu_b200", "csrc"), "-o", lib,
+                               os.path.join(emu_dir, "emu_kernels.cc")])
+    else:
+        subprocess.check_call(["make", "-s", "-C", emu_dir])
+        lib = os.path.join(emu_dir, "_build", "libkgpu_emu.so")
+    L = ctypes.CDLL(lib)
     L.emu_score_sparse.restype = None
     L.emu_score_dense.restype = None
     L.emu_place_batch.restype = ctypes.c_int
