@@ -447,6 +447,36 @@ def main():
                       "note": "each pod sees the free masks left by the pods before it (no snapshot collapse); "
                               "bit-exact vs the CPU twin in tests/test_place_sequential.py"}
 
+    # ---- context: memory-aware pods (config C6: per-GPU memory classes, pods with min_mem) ----
+    memory_aware = None
+    if world == 1 and not args.no_variants and not push:
+        topo6, free6, mem6, pods6 = synth.gen_c6()
+        with Scorer((local_rank,)) as s6:
+            s6.set_variant(_lib.VARIANT_SPARSE)
+            s6.upload_nodes(topo6, free6)
+            s6.upload_gpu_memory(mem6)
+            d_pods6 = torch.from_numpy(pods6).to(dev)
+            d_keys6 = torch.empty(len(pods6), dtype=torch.int64, device=dev)
+            for _ in range(3):
+                s6.score_batch_device(d_pods6.data_ptr(), len(pods6), d_keys6.data_ptr(), sptr)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(5):
+                s6.score_batch_device(d_pods6.data_ptr(), len(pods6), d_keys6.data_ptr(), sptr)
+            b.record(stream)
+            torch.cuda.synchronize()
+            snap_ms = a.elapsed_time(b) / 5
+            s6.place_batch(pods6[:256])
+            s6.upload_nodes(topo6, free6)
+            s6.upload_gpu_memory(mem6)
+            s6.place_batch(pods6)
+            seq6_ms = s6.last_kernel_ms
+        memory_aware = {"workload": "C6: 100k heterogeneous nodes with per-GPU memory classes x 10k pods, k in 1..8, 4 of 7 pods with min_mem",
+                        "snapshot_ms_per_batch": snap_ms, "snapshot_value": len(pods6) / (snap_ms * 1e-3),
+                        "sequential_ms_per_batch": seq6_ms, "sequential_value": len(pods6) / (seq6_ms * 1e-3), "unit": UNIT,
+                        "note": "K1s + K1m launches / place_init + place_sequential with one table set per distinct min_mem; "
+                                "parity in tests/test_memory_aware.py and tests/test_place_sequential.py"}
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         k1_s = (k1_total_ms / K) * 1e-3
@@ -475,6 +505,8 @@ def main():
             line["variants"] = variants
         if sequential:
             line["stateful_sequential"] = sequential
+        if memory_aware:
+            line["memory_aware"] = memory_aware
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(topo, free, pods)
         elif world == 1:
