@@ -67,7 +67,7 @@ __device__ __forceinline__ uint32_t node_key_kf(const PairCosts &C, const PipeCo
 constexpr int SP_GROUP = KGPU_SP_GROUP;
 static_assert(SP_GROUP == 1 || SP_GROUP == 2 || SP_GROUP == 4, "KGPU_SP_GROUP must be 1, 2 or 4");
 constexpr int SP_POS = SP_CHUNK + 10 * (SP_GROUP - 1);          // positions of a chunk in bucket order, dummies included
-constexpr int SP_TAB = (SP_POS + SP_GROUP - 1) / SP_GROUP;      // groups
+constexpr int SP_TAB = (SP_POS + SP_GROUP - 1) / SP_GROUP + 1;  // groups (+1: the prefetch build reads one past the last)
 constexpr uint16_t SP_DUMMY = 0xFFFFu;
 constexpr int SP_MEM_SUB = 4;        // MEM launch: pods of one k are sub-bucketed by a hash of min_mem, so equal requirements sit together
 struct alignas(8 * KGPU_SP_GROUP) SpEnt {
@@ -96,6 +96,21 @@ __device__ __forceinline__ uint32_t sp_warp_key(uint32_t key, const SpFmt f, uin
     return ((key * thirty_two) & 0xFFFFE000u) | ((key & 0xFFu) | f.lane_hi);
 }
 
+#ifndef KGPU_SP_PREFETCH
+#define KGPU_SP_PREFETCH 0       // 1: load the next group's multipliers one trip ahead (reads one group past a bucket's end)
+#endif
+__device__ __forceinline__ void sp_load_ones(const SpEnt *ent, uint32_t (&ones)[SP_GROUP]) {
+    if (SP_GROUP == 4) {
+        const uint4 o = *reinterpret_cast<const uint4 *>(ent->one);          // one LDS.128
+        ones[0] = o.x; ones[1 % SP_GROUP] = o.y; ones[2 % SP_GROUP] = o.z; ones[3 % SP_GROUP] = o.w;
+    } else if (SP_GROUP == 2) {
+        const uint2 o = *reinterpret_cast<const uint2 *>(ent->one);          // one LDS.64
+        ones[0] = o.x; ones[1 % SP_GROUP] = o.y;
+    } else {
+        ones[0] = ent->one[0];
+    }
+}
+
 // One (K, F) loop: all pods of the chunk that want K GPUs, enumerating positions 0..F-1.
 template <int K, int F, bool PER_PAIR, bool MEM, bool BYTE_KEYS>
 __device__ __forceinline__ void sp_bucket(const PairCosts &C, const PipeConsts pc, uint32_t nfree, bool valid,
@@ -108,21 +123,23 @@ __device__ __forceinline__ void sp_bucket(const PairCosts &C, const PipeConsts p
     int32_t last_need = -1;                        // MEM: the requirement C2 / elig were last built for
     uint32_t elig = 0;
     PairCosts C2 = C;
+#if KGPU_SP_PREFETCH
+    uint32_t nxt[SP_GROUP];
+    sp_load_ones(reinterpret_cast<SpEnt *>(reinterpret_cast<char *>(tab) + (uint32_t)begin * 8u), nxt);
+#endif
     KGPU_UNROLL((sp_unroll(K, F)))
     // byte offsets (8 bytes per position, begin and end are whole groups): uniform, because begin and end
     // come from shared memory, so the loop runs on the uniform datapath and the group address is tab + offset
     for (uint32_t off = (uint32_t)begin * 8u; off != (uint32_t)end * 8u; off += (uint32_t)sizeof(SpEnt)) {
         SpEnt *const ent = reinterpret_cast<SpEnt *>(reinterpret_cast<char *>(tab) + off);
         uint32_t ones[SP_GROUP], v[SP_GROUP];
-        if (SP_GROUP == 4) {
-            const uint4 o = *reinterpret_cast<const uint4 *>(ent->one);      // one LDS.128
-            ones[0] = o.x; ones[1 % SP_GROUP] = o.y; ones[2 % SP_GROUP] = o.z; ones[3 % SP_GROUP] = o.w;
-        } else if (SP_GROUP == 2) {
-            const uint2 o = *reinterpret_cast<const uint2 *>(ent->one);      // one LDS.64
-            ones[0] = o.x; ones[1 % SP_GROUP] = o.y;
-        } else {
-            ones[0] = ent->one[0];
-        }
+#if KGPU_SP_PREFETCH
+#pragma unroll
+        for (int g = 0; g < SP_GROUP; g++) ones[g] = nxt[g];
+        sp_load_ones(ent + 1, nxt);                // next trip's multipliers: their LDS latency overlaps this trip
+#else
+        sp_load_ones(ent, ones);
+#endif
 #pragma unroll
         for (int g = 0; g < SP_GROUP; g++) {
             PipeConsts pcl = pc;
