@@ -248,6 +248,11 @@ def main():
     ap.add_argument("--impl", default="kgpu", choices=["kgpu", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "allreduce", "push"],
+                    help="multi-GPU key exchange: NCCL all-gather + K2 (default, measured in round 1) or the "
+                         "(round-2 prep, untested) peer-memory push kernel of kgpu_score_batch_exchange")
+    ap.add_argument("--graph", action="store_true",
+                    help="(round-2 prep, untested) replay the step (memset + K1s + all-gather + K2) as one CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -255,7 +260,7 @@ def main():
     import torch
     import torch.distributed as dist
     from kubegpu_b200 import _lib, synth
-    from kubegpu_b200.distributed import shard_range
+    from kubegpu_b200.distributed import all_reduce_min_keys, shard_range
     from kubegpu_b200.scorer import Scorer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -294,21 +299,46 @@ def main():
     torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
 
+    push = args.exchange == "push"
+    if push and args.graph:
+        raise SystemExit("--exchange push cannot be captured in a graph (the epoch is a kernel argument)")
+    if push:                                        # every rank maps every rank's result array (CUDA IPC)
+        mine = scorer.exchange_init(world, rank, N_PODS)
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, mine)
+        else:
+            handles = [mine]
+        scorer.exchange_connect(handles)
+    wrapped = {}
+
+    class _DeviceKeys:                              # zero-copy view of the handle-owned result array
+        def __init__(self, ptr):
+            self.__cuda_array_interface__ = {"shape": (N_PODS,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
     def step_device():
-        """pods already in HBM -> final keys in HBM (all ranks hold the answer)."""
+        """pods already in HBM -> final keys in HBM (all ranks hold the answer); returns the tensor holding them."""
+        sptr = torch.cuda.current_stream().cuda_stream          # the capture stream while a graph is recorded
+        if push:
+            ptr = scorer.score_batch_exchange(d_pods.data_ptr(), N_PODS, sptr, _lib.BATCH_NO_MIN_MEM)
+            if ptr not in wrapped:
+                wrapped[ptr] = torch.as_tensor(_DeviceKeys(ptr), device=dev)
+            return wrapped[ptr]
         scorer.score_batch_device(d_pods.data_ptr(), N_PODS, d_local.data_ptr(), sptr, _lib.BATCH_NO_MIN_MEM)
+        if world > 1 and args.exchange == "allreduce":          # one collective, no K2 (round-2 experiment)
+            return all_reduce_min_keys(d_local)
         if world > 1:
             dist.all_gather_into_tensor(d_gather.view(-1), d_local)
             scorer.reduce_shards_device(d_gather.data_ptr(), world, N_PODS, d_final.data_ptr(), sptr)
+        return d_final
 
     def step_e2e():
         """host pods -> host keys through the public call."""
-        if world == 1:
+        if world == 1 and not push:
             scorer.score_batch_ptr(h_pods.data_ptr(), N_PODS, h_keys.data_ptr())   # kgpu_score_batch: H2D + K1 + D2H
         else:
             d_pods.copy_(h_pods, non_blocking=True)
-            step_device()
-            h_keys.copy_(d_final, non_blocking=True)
+            h_keys.copy_(step_device(), non_blocking=True)
             stream.synchronize()
 
     def barrier():
@@ -320,6 +350,11 @@ def main():
     for _ in range(W):
         flush.zero_()
         step_device()
+    graph = None
+    if args.graph:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            step_device()
     barrier()
     launches0 = scorer.kernel_launches
     sampler = ClockSampler(local_rank)
@@ -332,11 +367,20 @@ def main():
         if world > 1:
             dist.all_reduce(sync_token)                # device-side rendezvous so no rank times another's flush
         ev[i][0].record(stream)
-        scorer.score_batch_device(d_pods.data_ptr(), N_PODS, d_local.data_ptr(), sptr, _lib.BATCH_NO_MIN_MEM)
-        ev[i][1].record(stream)                        # K1 only: roofline numerator
-        if world > 1:
-            dist.all_gather_into_tensor(d_gather.view(-1), d_local)
-            scorer.reduce_shards_device(d_gather.data_ptr(), world, N_PODS, d_final.data_ptr(), sptr)
+        if graph is not None:
+            graph.replay()
+            ev[i][1].record(stream)                    # (no K1-only split inside a graph replay)
+        elif push:
+            step_device()
+            ev[i][1].record(stream)                    # (K1 and the push/sync kernel are one call)
+        else:
+            scorer.score_batch_device(d_pods.data_ptr(), N_PODS, d_local.data_ptr(), sptr, _lib.BATCH_NO_MIN_MEM)
+            ev[i][1].record(stream)                    # K1 only: roofline numerator
+            if world > 1 and args.exchange == "allreduce":
+                all_reduce_min_keys(d_local)
+            elif world > 1:
+                dist.all_gather_into_tensor(d_gather.view(-1), d_local)
+                scorer.reduce_shards_device(d_gather.data_ptr(), world, N_PODS, d_final.data_ptr(), sptr)
         ev[i][2].record(stream)
     barrier()
     clocks = sampler.finish()
@@ -366,7 +410,7 @@ def main():
 
     # ---- context lines: the other K1 variants (few steps, rank-local, N=1 only) ---------
     variants = {}
-    if world == 1 and not args.no_variants:
+    if world == 1 and not args.no_variants and not push:
         for name, var, reps in (("lane_per_node_dense_all_C8k_subsets", _lib.VARIANT_LANE_PER_NODE, 5),
                                 ("warp_per_pair_north_star_mapping", _lib.VARIANT_WARP_PER_PAIR, 3),
                                 ("tile_memo_not_headline", _lib.VARIANT_TILE_MEMO, 10),
@@ -403,6 +447,36 @@ def main():
                       "note": "each pod sees the free masks left by the pods before it (no snapshot collapse); "
                               "bit-exact vs the CPU twin in tests/test_place_sequential.py"}
 
+    # ---- context: memory-aware pods (config C6: per-GPU memory classes, pods with min_mem) ----
+    memory_aware = None
+    if world == 1 and not args.no_variants and not push:
+        topo6, free6, mem6, pods6 = synth.gen_c6()
+        with Scorer((local_rank,)) as s6:
+            s6.set_variant(_lib.VARIANT_SPARSE)
+            s6.upload_nodes(topo6, free6)
+            s6.upload_gpu_memory(mem6)
+            d_pods6 = torch.from_numpy(pods6).to(dev)
+            d_keys6 = torch.empty(len(pods6), dtype=torch.int64, device=dev)
+            for _ in range(3):
+                s6.score_batch_device(d_pods6.data_ptr(), len(pods6), d_keys6.data_ptr(), sptr)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(5):
+                s6.score_batch_device(d_pods6.data_ptr(), len(pods6), d_keys6.data_ptr(), sptr)
+            b.record(stream)
+            torch.cuda.synchronize()
+            snap_ms = a.elapsed_time(b) / 5
+            s6.place_batch(pods6[:256])
+            s6.upload_nodes(topo6, free6)
+            s6.upload_gpu_memory(mem6)
+            s6.place_batch(pods6)
+            seq6_ms = s6.last_kernel_ms
+        memory_aware = {"workload": "C6: 100k heterogeneous nodes with per-GPU memory classes x 10k pods, k in 1..8, 4 of 7 pods with min_mem",
+                        "snapshot_ms_per_batch": snap_ms, "snapshot_value": len(pods6) / (snap_ms * 1e-3),
+                        "sequential_ms_per_batch": seq6_ms, "sequential_value": len(pods6) / (seq6_ms * 1e-3), "unit": UNIT,
+                        "note": "K1s + K1m launches / place_init + place_sequential with one table set per distinct min_mem; "
+                                "parity in tests/test_memory_aware.py and tests/test_place_sequential.py"}
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         k1_s = (k1_total_ms / K) * 1e-3
@@ -412,7 +486,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "nodes": N_NODES, "pods": N_PODS,
-                       "parallelism": "node list sharded over %d GPU(s), 1 NCCL all-gather + K2" % world if world > 1 else "1 GPU, no collective",
+                       "parallelism": ("node list sharded over %d GPU(s), " % world + ("peer-memory push + flag barrier (1 kernel)" if push else "1 NCCL all-reduce(min)" if args.exchange == "allreduce" else "1 NCCL all-gather + K2")) if world > 1 else "1 GPU, no collective",
                        "kernel": "score_pairs_sparse (per pair: every k-subset of the node's free-GPU positions)",
                        "l2": "flushed between timed iterations (256 MiB write); node array is 26 MB < L2"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -431,6 +505,8 @@ def main():
             line["variants"] = variants
         if sequential:
             line["stateful_sequential"] = sequential
+        if memory_aware:
+            line["memory_aware"] = memory_aware
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(topo, free, pods)
         elif world == 1:

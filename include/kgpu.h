@@ -150,8 +150,9 @@ int kgpu_score_pairs(kgpu_t *h, const int64_t *node_idx, const int32_t *k, const
 /* Stateful sequential placement (what TakePodResources would make of a scheduling cycle;
  * a no-op in the reference, gpu_scheduler.go:57-63).  Pods are placed IN ORDER; each one gets
  * the best (cost, node, mask) under the free masks left by the pods before it and then takes
- * those GPUs: the handle's device-side free masks are updated.  Host buffers, synchronous,
- * single-device handles only. */
+ * those GPUs: the handle's device-side free masks are updated.  min_mem_mib is honoured like
+ * in kgpu_score_batch; one batch may carry at most 7 distinct positive min_mem_mib values
+ * (KGPU_ERR_INVALID otherwise).  Host buffers, synchronous, single-device handles only. */
 int kgpu_place_batch(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_keys);
 /* Copy the current free masks (n = kgpu_num_nodes entries) back to the host. */
 int kgpu_get_free_masks(kgpu_t *h, int32_t *out_free_mask, int64_t n);
@@ -160,6 +161,22 @@ int kgpu_get_free_masks(kgpu_t *h, int32_t *out_free_mask, int64_t n);
  * every shard's keys), enqueued on `stream`. */
 int kgpu_reduce_shards_device(kgpu_t *h, const uint64_t *d_gathered, int G, int64_t P,
                               uint64_t *d_out, void *stream);
+
+/* Peer-memory key exchange for the one-process-per-GPU launch (EXPERIMENTAL; replaces the all-gather +
+ * kgpu_reduce_shards_device pair; no reference counterpart).  Every rank:
+ *   kgpu_exchange_init(h, world, rank, max_pods, handle)   allocate the rank's result/flag memory, export it
+ *   <all-gather the KGPU_IPC_HANDLE_BYTES-byte handles through the launcher, e.g. torch.distributed>
+ *   kgpu_exchange_connect(h, handles)                      map every peer's memory (handles = [world][64])
+ *   kgpu_score_batch_exchange(h, d_pods, P, &d_final, stream)   per step: K1 on the local shard, then one
+ *       kernel pushes the P bests into every rank's result array (64-bit atomic min over NVLink) and meets
+ *       the other ranks at a flag barrier in peer memory.  *d_final (device memory owned by the handle,
+ *       valid until the next-but-one call) then holds the global per-pod keys on every rank.
+ * All ranks must make the same sequence of kgpu_score_batch_exchange calls.  Single-device handles only. */
+#define KGPU_IPC_HANDLE_BYTES 64
+int kgpu_exchange_init(kgpu_t *h, int world, int rank, int64_t max_pods, unsigned char *out_handle);
+int kgpu_exchange_connect(kgpu_t *h, const unsigned char *handles);
+int kgpu_score_batch_exchange(kgpu_t *h, const int32_t *d_pods, int64_t P, const uint64_t **d_final_keys,
+                              void *stream, int batch_flags);
 
 /* Number of CUDA kernels this handle has launched so far (bench bookkeeping). */
 int64_t kgpu_kernel_launches(kgpu_t *h);

@@ -13,12 +13,13 @@ SYMBOLS = [
     "kgpu_version", "kgpu_create", "kgpu_destroy", "kgpu_last_error", "kgpu_set_weights",
     "kgpu_get_weights", "kgpu_set_variant", "kgpu_upload_nodes", "kgpu_update_node",
     "kgpu_set_free_mask", "kgpu_remove_node", "kgpu_upload_gpu_memory", "kgpu_update_gpu_memory", "kgpu_num_nodes", "kgpu_score_batch",
-    "kgpu_score_batch_device", "kgpu_score_batch_device_ex", "kgpu_score_pairs", "kgpu_place_batch", "kgpu_get_free_masks", "kgpu_reduce_shards_device", "kgpu_kernel_launches",
+    "kgpu_score_batch_device", "kgpu_score_batch_device_ex", "kgpu_score_pairs", "kgpu_place_batch", "kgpu_get_free_masks", "kgpu_reduce_shards_device", "kgpu_exchange_init", "kgpu_exchange_connect", "kgpu_score_batch_exchange", "kgpu_kernel_launches",
     "kgpu_last_kernel_ms",
 ]
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_COMM, ERR_STATE = 0, -1, -2, -3, -4, -5
 NO_FIT = 0xFFFFFFFFFFFFFFFF
+IPC_HANDLE_BYTES = 64
 VARIANT_AUTO, VARIANT_WARP_PER_PAIR, VARIANT_LANE_PER_NODE, VARIANT_MEMO_BY_K, VARIANT_TILE_MEMO = 0, 1, 2, 3, 4
 VARIANT_SPARSE = 5
 BATCH_NO_MIN_MEM = 1
@@ -80,6 +81,12 @@ def load() -> ctypes.CDLL:
     L.kgpu_get_free_masks.argtypes = [vp, i32p, i64]
     L.kgpu_reduce_shards_device.restype = ci
     L.kgpu_reduce_shards_device.argtypes = [vp, vp, ci, i64, vp, vp]
+    L.kgpu_exchange_init.restype = ci
+    L.kgpu_exchange_init.argtypes = [vp, ci, ci, i64, vp]
+    L.kgpu_exchange_connect.restype = ci
+    L.kgpu_exchange_connect.argtypes = [vp, vp]
+    L.kgpu_score_batch_exchange.restype = ci
+    L.kgpu_score_batch_exchange.argtypes = [vp, vp, i64, ctypes.POINTER(vp), vp, ci]
     L.kgpu_kernel_launches.restype = i64
     L.kgpu_kernel_launches.argtypes = [vp]
     L.kgpu_last_kernel_ms.restype = ctypes.c_double

@@ -35,47 +35,77 @@ def y(i, j):
 
 
 class Body:
+    """Running min (or max) over the folded terms in NACC independent accumulators.  An accumulator is
+    created from its first three terms (one 3-input min), so no instruction is spent on an identity
+    element; `finish` merges the live accumulators."""
+
     def __init__(self, op3="MIN3"):
-        self.lines, self.pending, self.op3, self.turn = [], [], op3, 0
-        init = "0xFFFFFFFFu" if op3 == "MIN3" else "0u"
-        self.w("uint32_t " + ", ".join("b%d = %s" % (i, init) for i in range(NACC)) + ";")
+        self.lines, self.pending, self.op3 = [], [], op3
+        self.op2 = "min" if op3 == "MIN3" else "max"
+        self.live, self.turn, self.declared = [], 0, set()
 
     def w(self, s):
         self.lines.append("    " + s)
 
-    def acc(self):
-        a = "b%d" % (self.turn % NACC)
-        self.turn += 1
-        return a
+    def _assign(self, name, expr):
+        self.declared.add(name)
+        self.w("%s = %s;" % (name, expr))
 
     def fold(self, expr):
         self.pending.append(expr)
-        if len(self.pending) == 2:
-            a = self.acc()
-            self.w("%s = %s(%s, %s, %s);" % (a, self.op3, a, self.pending[0], self.pending[1]))
+        if len(self.live) < NACC:                      # still creating accumulators: wait for three terms
+            if len(self.pending) == 3:
+                name = "b%d" % len(self.live)
+                self._assign(name, "%s(%s, %s, %s)" % (self.op3, *self.pending))
+                self.live.append(name)
+                self.pending = []
+        elif len(self.pending) == 2:
+            a = self.live[self.turn % NACC]
+            self.turn += 1
+            self._assign(a, "%s(%s, %s, %s)" % (self.op3, a, *self.pending))
             self.pending = []
 
     def addfold(self, x, yv):
-        a = self.acc()
-        self.w("%s = %s(%s, %s, %s);" % (a, "ADDMIN" if self.op3 == "MIN3" else "ADDMAX", x, yv, a))
+        """acc = min/max(acc, x + yv) in one instruction (VIADDMNMX)."""
+        op = "ADDMIN" if self.op3 == "MIN3" else "ADDMAX"
+        if len(self.live) < NACC:
+            name = "b%d" % len(self.live)
+            self._assign(name, "(%s) + (%s)" % (x, yv))
+            self.live.append(name)
+        else:
+            a = self.live[self.turn % NACC]
+            self.turn += 1
+            self._assign(a, "%s(%s, %s, %s)" % (op, x, yv, a))
 
     def flush(self):
-        if self.pending:
-            a = self.acc()
-            self.w("%s = %s(%s, %s);" % (a, "min" if self.op3 == "MIN3" else "max", a, self.pending[0]))
-            self.pending = []
+        """Scope boundary: pending terms refer to temporaries that are about to go out of scope."""
+        if not self.pending:
+            return
+        if not self.live:
+            expr = self.pending[0] if len(self.pending) == 1 else "%s(%s, %s)" % (self.op2, *self.pending)
+            self._assign("b0", expr)
+            self.live.append("b0")
+        else:
+            a = self.live[self.turn % len(self.live)]
+            self.turn += 1
+            if len(self.pending) == 1:
+                self._assign(a, "%s(%s, %s)" % (self.op2, a, self.pending[0]))
+            else:
+                self._assign(a, "%s(%s, %s, %s)" % (self.op3, a, *self.pending))
+        self.pending = []
 
     def finish(self):
         self.flush()
-        accs = ["b%d" % i for i in range(NACC)]
+        accs = list(self.live)
         while len(accs) > 1:
             if len(accs) >= 3:
                 self.w("%s = %s(%s, %s, %s);" % (accs[0], self.op3, accs[0], accs[1], accs[2]))
                 accs = [accs[0]] + accs[3:]
             else:
-                self.w("%s = %s(%s, %s);" % (accs[0], "min" if self.op3 == "MIN3" else "max", accs[0], accs[1]))
+                self.w("%s = %s(%s, %s);" % (accs[0], self.op2, accs[0], accs[1]))
                 accs = [accs[0]]
-        self.w("const uint32_t best = b0;")
+        self.w("const uint32_t best = %s;" % accs[0])
+        self.lines.insert(0, "    uint32_t %s;" % ", ".join(sorted(self.declared)))
 
 
 def dep_sum(terms):
@@ -103,15 +133,13 @@ def gen_direct(K, F):
         for a, bb in itertools.combinations(range(F), 2):
             if bb > F - 3:
                 continue
-            b.w("{")
+            g = "%d%d" % (a, bb)                       # temporaries are named per (a, b) so folds can span groups
             for x in range(bb + 1, F):
-                b.w("    const uint32_t q%d = F2(%s, %s);" % (x, c(a, x), c(bb, x)))
+                b.w("const uint32_t q%s_%d = F2(%s, %s);" % (g, x, c(a, x), c(bb, x)))
             for d in range(bb + 1, F - 1):
-                b.w("    const uint32_t t%d = F2(%s, q%d);" % (d, y(a, bb), d))
+                b.w("const uint32_t t%s_%d = F2(%s, q%s_%d);" % (g, d, y(a, bb), g, d))
                 for e in range(d + 1, F):
-                    b.fold("A3(t%d, q%d, %s)" % (d, e, y(d, e)))
-            b.flush()
-            b.w("}")
+                    b.fold("A3(t%s_%d, q%s_%d, %s)" % (g, d, g, e, y(d, e)))
     b.finish()
     b.w("return best;")
     return b.lines
@@ -130,7 +158,7 @@ def gen_complement(K, F):
         b.w("const uint32_t r%d = %s;" % (i, dep_sum([c(i, j) for j in range(F) if j != i])))
     b.w("const uint32_t tm = (%s >> 1) + 0x%02xu;" % (dep_sum(["r%d" % i for i in range(F)]), (1 << F) - 1))
     for i in range(F):
-        b.w("const uint32_t q%d = r%d + 0x%02xu;" % (i, i, 1 << i))
+        b.w("const uint32_t q%d = F2(r%d, 0x%02xu);" % (i, i, 1 << i))      # an IMAD, not an ALU add
     if comp == 1:
         for a in range(F):
             b.fold("q%d" % a)
@@ -141,12 +169,9 @@ def gen_complement(K, F):
         for a, bb in itertools.combinations(range(F), 2):
             if bb > F - 2:
                 continue
-            b.w("{")
-            b.w("    const uint32_t h = F2(F2N(%s, q%d), q%d);" % (c(a, bb), bb, a))
+            b.w("const uint32_t h%d%d = F2(F2N(%s, q%d), q%d);" % (a, bb, c(a, bb), bb, a))
             for d in range(bb + 1, F):
-                b.fold("A3(h, q%d, 0u - F2(%s, %s))" % (d, c(a, d), c(bb, d)))
-            b.flush()
-            b.w("}")
+                b.fold("A3(h%d%d, q%d, 0u - F2(%s, %s))" % (a, bb, d, c(a, d), c(bb, d)))
     b.finish()
     b.w("return tm - best;")
     return b.lines

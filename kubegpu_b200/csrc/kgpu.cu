@@ -15,6 +15,8 @@
 
 #include "multi_device.h"
 #include "place_sequential.cuh"
+#include "sparse_work.h"
+#include "peer_exchange.cuh"
 #include "score_pairs.cuh"
 #include "score_pairs_sparse.cuh"
 
@@ -51,8 +53,12 @@ struct kgpu_shard {
     unsigned long long *d_keys = nullptr;    // [pcap]
     unsigned long long *d_gather = nullptr;  // [ndev][pcap] (multi-device only)
     unsigned long long *d_bestk = nullptr;   // [9] memo variant
-    uint32_t *d_nodebest = nullptr;          // [9][Npad]  K3 tables
-    unsigned long long *d_tilebest = nullptr;   // [9][T]
+    std::vector<uint8_t> tile_class;         // K1s: max free-GPU count per 128-slot tile of the order (host copy)
+    std::vector<kgpu::SparseWorkItem> h_work;   // K1s work list for work_P pods (sparse_work.h)
+    int4 *d_work = nullptr;
+    int64_t work_cap = 0, work_P = -1;
+    uint32_t *d_nodebest = nullptr;          // [views][9][Npad]  K3 tables
+    unsigned long long *d_tilebest = nullptr;   // [views][9][T]
     int64_t place_cap = 0;
     int64_t pcap = 0;
 };
@@ -68,6 +74,17 @@ struct kgpu_ctx {
     double last_kernel_ms = 0.0;
     bool subsets_uploaded = false;
     kgpu::MultiDevice *multi = nullptr;   // NCCL communicator set, ndev > 1 only
+    // peer-memory key exchange (kgpu_exchange_*): one allocation per rank, mapped by every peer:
+    //   results[2][max_pods] uint64 | flags[PEER_MAX_WORLD] uint32 | ticket uint32 ;  local[] is private
+    struct {
+        int world = 0, rank = 0;
+        int64_t max_pods = 0;
+        void *base = nullptr;
+        void *peer_base[kgpu::PEER_MAX_WORLD] = {};
+        unsigned long long *local = nullptr;
+        uint32_t epoch = 0;
+        bool connected = false;
+    } xch;
 };
 
 namespace {
@@ -192,14 +209,39 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
                 s.compact_dirty = false;
             }
             const int4 *cpair4 = reinterpret_cast<const int4 *>(s.d_cpair);
-            kgpu::score_pairs_sparse<true, false><<<grid, kgpu::SP_THREADS, 0, st>>>(
-                cpair4, s.d_perm, s.d_free, s.d_mem, s.d_order, s.d_flag, s.node_id_base, pods4, P, (int)per, PC, d_keys);
+            // Work list instead of the plain grid: auto = for small shards (few tiles per resident block), where
+            // equal pod ranges are either too few or too short; KGPU_SP_WORKLIST=0/1 forces it off/on.
+            static const int worklist_mode = [] { const char *e = getenv("KGPU_SP_WORKLIST"); return e ? atoi(e) : -1; }();
+            const bool use_work = worklist_mode >= 0 ? worklist_mode != 0 : tiles * 4 < resident;
+            const int4 *d_work = nullptr;
+            if (use_work) {
+                if (s.work_P != P) {
+                    kgpu::build_sparse_work(s.tile_class, P, resident, s.h_work);
+                    if ((int64_t)s.h_work.size() > s.work_cap) {
+                        if (s.d_work) cudaFree(s.d_work);
+                        s.d_work = nullptr; s.work_cap = 0;
+                        KGPU_CUDA(h, cudaMalloc(&s.d_work, s.h_work.size() * sizeof(int4)));
+                        s.work_cap = (int64_t)s.h_work.size();
+                    }
+                    static_assert(sizeof(kgpu::SparseWorkItem) == sizeof(int4), "work item layout");
+                    KGPU_CUDA(h, cudaMemcpyAsync(s.d_work, s.h_work.data(), s.h_work.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+                    s.work_P = P;
+                }
+                d_work = s.d_work;
+                grid = dim3((unsigned)s.h_work.size(), 1);
+            }
+            bool byte_keys = true;       // every cost < 2^16 <=> 28 * max weight < 65536
+            for (int i = 0; i < 16; i++) byte_keys = byte_keys && h->W[i] <= 2340;
+#define KGPU_LAUNCH_SPARSE(MEMF, BK)                                                                          \
+    kgpu::score_pairs_sparse<true, MEMF, BK><<<grid, kgpu::SP_THREADS, 0, st>>>(                              \
+        cpair4, s.d_perm, s.d_free, s.d_mem, s.d_order, s.d_flag, s.node_id_base, pods4, P, (int)per, d_work, PC, d_keys)
+            if (byte_keys) KGPU_LAUNCH_SPARSE(false, true); else KGPU_LAUNCH_SPARSE(false, false);
             h->launches++;
             if (has_mem != 0) {
-                kgpu::score_pairs_sparse<true, true><<<grid, kgpu::SP_THREADS, 0, st>>>(
-                    cpair4, s.d_perm, s.d_free, s.d_mem, s.d_order, s.d_flag, s.node_id_base, pods4, P, (int)per, PC, d_keys);
+                if (byte_keys) KGPU_LAUNCH_SPARSE(true, true); else KGPU_LAUNCH_SPARSE(true, false);
                 h->launches++;
             }
+#undef KGPU_LAUNCH_SPARSE
         } else if (has_mem != 0) {   // K1m: the memory-constrained pods (its blocks exit at once if the flag is 0)
             kgpu::score_pairs_lane_per_node<true, true><<<grid, kgpu::LPN_THREADS, 0, st>>>(
                 topo4, s.d_free, mem4, s.d_flag, s.n, s.node_id_base, pods4, P, (int)per, W, PC, d_keys);
@@ -244,6 +286,7 @@ void free_shard(kgpu_shard &s) {
     if (s.d_bestk) cudaFree(s.d_bestk);
     if (s.d_nodebest) cudaFree(s.d_nodebest);
     if (s.d_tilebest) cudaFree(s.d_tilebest);
+    if (s.d_work) cudaFree(s.d_work);
     if (s.ev0) cudaEventDestroy(s.ev0);
     if (s.ev1) cudaEventDestroy(s.ev1);
     if (s.stream) cudaStreamDestroy(s.stream);
@@ -322,6 +365,12 @@ int kgpu_destroy(kgpu_t *h) {
         if (s.dev >= 0) { cudaSetDevice(s.dev); cudaStreamSynchronize(s.stream); }
     }
     delete h->multi;
+    if (h->xch.base) {
+        for (int r = 0; r < h->xch.world; r++)
+            if (h->xch.connected && r != h->xch.rank && h->xch.peer_base[r]) cudaIpcCloseMemHandle(h->xch.peer_base[r]);
+        cudaFree(h->xch.base);
+        cudaFree(h->xch.local);
+    }
     for (auto &s : h->shards) free_shard(s);
     delete h;
     return KGPU_OK;
@@ -411,6 +460,14 @@ int kgpu_upload_nodes(kgpu_t *h, const int32_t *topo, const int32_t *free_mask, 
                 s.order_cap = (int64_t)order.size();
             }
             s.n_slots = (int64_t)order.size();
+            s.tile_class.assign(order.size() / kgpu::SP_THREADS, 0);
+            for (size_t sl = 0; sl < order.size(); sl++)
+                if (order[sl] >= 0) {
+                    const uint8_t f = (uint8_t)__builtin_popcount((unsigned)free_mask[off + order[sl]] & 0xFFu);
+                    uint8_t &tc = s.tile_class[sl / kgpu::SP_THREADS];
+                    tc = std::max(tc, f);
+                }
+            s.work_P = -1;
             if (!order.empty()) {
                 KGPU_CUDA(h, cudaMemcpyAsync(s.d_order, order.data(), order.size() * 4, cudaMemcpyHostToDevice, s.stream));
                 KGPU_CUDA(h, cudaStreamSynchronize(s.stream));   // `order` is a local
@@ -551,8 +608,20 @@ int kgpu_place_batch(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_ke
     if (h->shards.size() != 1) return fail(h, KGPU_ERR_STATE, "kgpu_place_batch: needs a single-device handle");
     if (P < 0 || (P > 0 && (!pods || !out_keys))) return fail(h, KGPU_ERR_INVALID, "kgpu_place_batch: bad arguments");
     if (P == 0) return KGPU_OK;
-    for (int64_t p = 0; p < P; p++)
-        if (pods[4 * p + 3] > 0) return fail(h, KGPU_ERR_INVALID, "kgpu_place_batch: pod %lld has min_mem > 0 (not supported by the sequential path yet)", (long long)p);
+    // the batch's distinct memory requirements are the views the sequential kernels keep tables for
+    kgpu::PlaceViews views;
+    memset(&views, 0, sizeof views);
+    views.n = 1;
+    for (int64_t p = 0; p < P; p++) {
+        const int32_t need = pods[4 * p + 3];
+        if (need <= 0 || pods[4 * p] < 0 || pods[4 * p] > 8) continue;
+        bool seen = false;
+        for (int j = 1; j < views.n; j++) seen = seen || views.min_mem[j] == need;
+        if (seen) continue;
+        if (views.n == kgpu::PLACE_MAX_VIEWS)
+            return fail(h, KGPU_ERR_INVALID, "kgpu_place_batch: more than %d distinct min_mem values in one batch", kgpu::PLACE_MAX_VIEWS - 1);
+        views.min_mem[views.n++] = need;
+    }
     kgpu_shard &s = h->shards[0];
     int rc = ensure_pod_capacity(h, s, P);
     if (rc != KGPU_OK) return rc;
@@ -562,22 +631,23 @@ int kgpu_place_batch(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_ke
         KGPU_CUDA(h, cudaMemsetAsync(s.d_keys, 0xFF, (size_t)P * 8, s.stream));
     } else {
         const int64_t T = (s.n + kgpu::PLACE_TILE - 1) / kgpu::PLACE_TILE, Npad = T * kgpu::PLACE_TILE;
-        if (Npad > s.place_cap) {
+        if (Npad * views.n > s.place_cap) {
             if (s.d_nodebest) cudaFree(s.d_nodebest);
             if (s.d_tilebest) cudaFree(s.d_tilebest);
             s.d_nodebest = nullptr; s.d_tilebest = nullptr; s.place_cap = 0;
-            KGPU_CUDA(h, cudaMalloc(&s.d_nodebest, (size_t)Npad * 9 * 4));
-            KGPU_CUDA(h, cudaMalloc(&s.d_tilebest, (size_t)T * 9 * 8));
-            s.place_cap = Npad;
+            KGPU_CUDA(h, cudaMalloc(&s.d_nodebest, (size_t)Npad * views.n * 9 * 4));
+            KGPU_CUDA(h, cudaMalloc(&s.d_tilebest, (size_t)T * views.n * 9 * 8));
+            s.place_cap = Npad * views.n;
         }
         kgpu::Weights W;
         memcpy(W.w, h->W, sizeof W.w);
         KGPU_CUDA(h, cudaEventRecord(s.ev0, s.stream));
-        kgpu::place_init<<<(unsigned)T, kgpu::PLACE_TILE, 0, s.stream>>>(reinterpret_cast<const int4 *>(s.d_topo), s.d_free, s.n, Npad,
-                                                                        s.node_id_base, W, PC, s.d_nodebest, s.d_tilebest, T);
-        kgpu::place_sequential<<<1, kgpu::PLACE_THREADS, 0, s.stream>>>(s.d_topo, s.d_free, s.n, Npad, s.node_id_base,
-                                                                        reinterpret_cast<const int4 *>(s.d_pods), P, W, s.d_nodebest,
-                                                                        s.d_tilebest, T, s.d_keys);
+        kgpu::place_init<<<dim3((unsigned)T, (unsigned)views.n), kgpu::PLACE_TILE, 0, s.stream>>>(
+            reinterpret_cast<const int4 *>(s.d_topo), s.d_free, s.d_mem, s.n, Npad, s.node_id_base, W, PC, views, s.d_nodebest,
+            s.d_tilebest, T);
+        kgpu::place_sequential<<<1, kgpu::PLACE_THREADS, 0, s.stream>>>(s.d_topo, s.d_free, s.d_mem, s.n, Npad, s.node_id_base,
+                                                                        reinterpret_cast<const int4 *>(s.d_pods), P, W, views,
+                                                                        s.d_nodebest, s.d_tilebest, T, s.d_keys);
         h->launches += 2;
         s.compact_dirty = true;          // the free masks have changed on the device
         KGPU_CUDA(h, cudaGetLastError());
@@ -674,6 +744,84 @@ int kgpu_score_batch_device_ex(kgpu_t *h, const int32_t *d_pods, int64_t P, uint
     kgpu_shard &s = h->shards[0];
     return launch_score(h, s, d_pods, P, reinterpret_cast<unsigned long long *>(d_keys), (cudaStream_t)stream,
                         (batch_flags & KGPU_BATCH_NO_MIN_MEM) ? 0 : -1);
+}
+
+namespace {
+size_t xch_bytes(int64_t max_pods) { return (size_t)max_pods * 16 + kgpu::PEER_MAX_WORLD * 4 + 16; }
+unsigned long long *xch_results(void *base, int64_t max_pods, int buf) { return reinterpret_cast<unsigned long long *>(base) + (int64_t)buf * max_pods; }
+uint32_t *xch_flags(void *base, int64_t max_pods) { return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(base) + (size_t)max_pods * 16); }
+}  // namespace
+
+int kgpu_exchange_init(kgpu_t *h, int world, int rank, int64_t max_pods, unsigned char *out_handle) {
+    if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_exchange_init: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    static_assert(sizeof(cudaIpcMemHandle_t) == KGPU_IPC_HANDLE_BYTES, "IPC handle size");
+    if (h->shards.size() != 1) return fail(h, KGPU_ERR_STATE, "kgpu_exchange_init: needs a single-device handle");
+    if (world < 1 || world > kgpu::PEER_MAX_WORLD || rank < 0 || rank >= world || max_pods < 1 || !out_handle)
+        return fail(h, KGPU_ERR_INVALID, "kgpu_exchange_init: bad arguments (world <= %d)", kgpu::PEER_MAX_WORLD);
+    if (h->xch.base) return fail(h, KGPU_ERR_STATE, "kgpu_exchange_init: already initialised");
+    kgpu_shard &s = h->shards[0];
+    KGPU_CUDA(h, cudaSetDevice(s.dev));
+    KGPU_CUDA(h, cudaMalloc(&h->xch.base, xch_bytes(max_pods)));
+    KGPU_CUDA(h, cudaMalloc(&h->xch.local, (size_t)max_pods * 8));
+    KGPU_CUDA(h, cudaMemset(h->xch.base, 0xFF, (size_t)max_pods * 16));                                   // both result buffers: NO_FIT
+    KGPU_CUDA(h, cudaMemset(xch_flags(h->xch.base, max_pods), 0, kgpu::PEER_MAX_WORLD * 4 + 16));         // flags, ticket
+    KGPU_CUDA(h, cudaDeviceSynchronize());
+    cudaIpcMemHandle_t ipc;
+    KGPU_CUDA(h, cudaIpcGetMemHandle(&ipc, h->xch.base));
+    memcpy(out_handle, &ipc, sizeof ipc);
+    h->xch.world = world; h->xch.rank = rank; h->xch.max_pods = max_pods; h->xch.epoch = 0; h->xch.connected = false;
+    return KGPU_OK;
+}
+
+int kgpu_exchange_connect(kgpu_t *h, const unsigned char *handles) {
+    if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_exchange_connect: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->xch.base) return fail(h, KGPU_ERR_STATE, "kgpu_exchange_connect: call kgpu_exchange_init first");
+    if (!handles) return fail(h, KGPU_ERR_INVALID, "kgpu_exchange_connect: NULL handles");
+    if (h->xch.connected) return fail(h, KGPU_ERR_STATE, "kgpu_exchange_connect: already connected");
+    KGPU_CUDA(h, cudaSetDevice(h->shards[0].dev));
+    for (int r = 0; r < h->xch.world; r++) {
+        if (r == h->xch.rank) { h->xch.peer_base[r] = h->xch.base; continue; }
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, handles + (size_t)r * KGPU_IPC_HANDLE_BYTES, sizeof ipc);
+        KGPU_CUDA(h, cudaIpcOpenMemHandle(&h->xch.peer_base[r], ipc, cudaIpcMemLazyEnablePeerAccess));
+    }
+    h->xch.connected = true;
+    return KGPU_OK;
+}
+
+int kgpu_score_batch_exchange(kgpu_t *h, const int32_t *d_pods, int64_t P, const uint64_t **d_final_keys, void *stream,
+                              int batch_flags) {
+    if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_score_batch_exchange: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->xch.connected) return fail(h, KGPU_ERR_STATE, "kgpu_score_batch_exchange: exchange not connected");
+    if (P < 0 || P > h->xch.max_pods || (P > 0 && !d_pods) || !d_final_keys)
+        return fail(h, KGPU_ERR_INVALID, "kgpu_score_batch_exchange: bad arguments (P <= max_pods of kgpu_exchange_init)");
+    kgpu_shard &s = h->shards[0];
+    cudaStream_t st = (cudaStream_t)stream;
+    KGPU_CUDA(h, cudaSetDevice(s.dev));
+    const uint32_t epoch = ++h->xch.epoch;
+    const int buf = (int)(epoch & 1u);
+    const int64_t mp = h->xch.max_pods;
+    *d_final_keys = reinterpret_cast<const uint64_t *>(xch_results(h->xch.base, mp, buf));
+    if (P == 0) return KGPU_OK;
+    // the other buffer is what peers push into NEXT epoch: clean it before this rank can reach this epoch's barrier
+    // (all max_pods entries: the next batch may be longer than this one)
+    KGPU_CUDA(h, cudaMemsetAsync(xch_results(h->xch.base, mp, buf ^ 1), 0xFF, (size_t)mp * 8, st));
+    const int rc = launch_score(h, s, d_pods, P, h->xch.local, st, (batch_flags & KGPU_BATCH_NO_MIN_MEM) ? 0 : -1);
+    if (rc != KGPU_OK) return rc;
+    kgpu::PeerTable tab;
+    memset(&tab, 0, sizeof tab);
+    for (int r = 0; r < h->xch.world; r++) {
+        tab.results[r] = xch_results(h->xch.peer_base[r], mp, buf);
+        tab.flags[r] = xch_flags(h->xch.peer_base[r], mp);
+    }
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(xch_flags(h->xch.base, mp) + kgpu::PEER_MAX_WORLD);
+    kgpu::push_and_sync<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(h->xch.local, P, tab, h->xch.rank, h->xch.world, epoch, ticket);
+    h->launches++;
+    KGPU_CUDA(h, cudaGetLastError());
+    return KGPU_OK;
 }
 
 int kgpu_reduce_shards_device(kgpu_t *h, const uint64_t *d_gathered, int G, int64_t P, uint64_t *d_out, void *stream) {

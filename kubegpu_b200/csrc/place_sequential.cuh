@@ -1,19 +1,30 @@
-// place_sequential.cuh -- K3: stateful sequential placement.
+// place_sequential.cuh -- K3: stateful sequential placement, memory-aware.
 //
 // Semantics (bit-exact against the CPU twin used by the tests):
 //   for p = 0 .. P-1, in order:
-//       key_p = min over nodes of (cost<<40 | node_id<<8 | S)   given the CURRENT free masks
+//       key_p = min over nodes of (cost<<40 | node_id<<8 | S)   given the CURRENT free masks, where
+//               only GPUs with at least the pod's min_mem MiB count as free for that pod
 //       if key_p != NO_FIT:  free_mask[node] &= ~S              (the pod takes those GPUs)
 // This is what TakePodResources would make of a scheduling cycle if the reference's plugin
 // tracked usage (it is a no-op there: gpuschedulerplugin/gpu_scheduler.go:57-63), and it has no
 // snapshot-scoring collapse: every placement changes the state the next pod sees.
 //
-// Device data:  nodebest[9][Npad] uint32  (cost<<8 | S) of every node for k = 0..8, INF32 = no fit
-//               tilebest[9][T]    uint64  min over each 128-node tile of (cost<<40|node_id<<8|S)
-// place_init       : one block per tile: full enumeration for all 9 k (lane per node) -> both tables
-// place_sequential : ONE persistent block of 1024 threads walks the pods: argmin over tilebest[k]
-//                    (coalesced 8-byte loads + block reduction), commit, re-enumerate the winner
-//                    node for all 9 k (warp per k, lane per subset), refresh its tile's 9 minima.
+// Views.  The distinct min_mem values of a batch (at most PLACE_MAX_VIEWS - 1, the host checks) define
+// VIEWS of the cluster: view 0 sees every free GPU, view v only the free GPUs with >= min_mem[v] MiB.
+// GPU memory never changes, so a view is the same computation with (free & ok_v) as the free mask,
+// and every table below exists once per view.
+//
+// Device data (v = view, k = 0..8 GPUs wanted):
+//   nodebest[v][k][Npad] uint32  (cost<<8 | S) of every node, INF32 = no fit                      (global)
+//   tilebest[v][k][T]    uint64  min over each 128-node tile of (cost<<40 | node_id<<8 | S)      (global)
+//   super[v][k][ST]      uint64  min over each supertile (super_tiles tiles)                     (SHARED)
+// place_init       : grid (tiles, views): full enumeration for all 9 k (lane per node) -> nodebest, tilebest
+// place_sequential : ONE persistent block walks the pods.  Per pod: argmin over super[v][k] in shared
+//                    memory (the winning key already names node and subset), one barrier; commit; then
+//                    each warp takes (view, k) tasks on its own: re-enumerate the winner node (lane per
+//                    subset), refresh the minimum of its tile and of its supertile -- the global loads of
+//                    a task (topology row, node-key row of the tile, tile minima of the supertile) do not
+//                    depend on each other, so a pod costs one round trip to L2; one barrier.
 #pragma once
 #include "score_pairs.cuh"
 
@@ -21,9 +32,24 @@ namespace kgpu {
 
 constexpr int PLACE_TILE = 128;
 #ifndef KGPU_PLACE_THREADS
-#define KGPU_PLACE_THREADS 512      // 16 warps: cheaper barriers than 1024, still >= 9 warps (one per k)
+#define KGPU_PLACE_THREADS 512      // 16 warps: cheap barriers, 9 of them busy per view in the refresh
 #endif
 constexpr int PLACE_THREADS = KGPU_PLACE_THREADS;
+constexpr int PLACE_WARPS = PLACE_THREADS / 32;
+constexpr int PLACE_MAX_VIEWS = 8;
+constexpr int PLACE_SUPER_CAP = 4608;       // uint64 entries of static shared memory (36 KB) for super[][][]
+
+struct PlaceViews {
+    int32_t n;                              // 1 .. PLACE_MAX_VIEWS
+    int32_t min_mem[PLACE_MAX_VIEWS];       // min_mem[0] = 0
+};
+
+// host + device: tiles per supertile (a multiple of 32) such that views * 9 * ceil(T / super_tiles) fits
+__host__ __device__ inline int64_t place_super_tiles(int64_t T, int views) {
+    int64_t st = 32;
+    while ((int64_t)views * 9 * ((T + st - 1) / st) > PLACE_SUPER_CAP) st *= 2;
+    return st;
+}
 
 __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
 #pragma unroll
@@ -35,10 +61,20 @@ __device__ __forceinline__ unsigned long long wide_key(uint32_t nk, unsigned lon
     return nk == INF32 ? ~0ull : (((unsigned long long)(nk >> 8) << 40) | (node_id << 8) | (nk & 0xFFu));
 }
 
+// GPUs of `node` that view `need` may use (gpu_mem == nullptr: unlimited memory)
+__device__ __forceinline__ uint32_t view_ok_mask(const int32_t *__restrict__ gpu_mem, int64_t node, int32_t need) {
+    if (gpu_mem == nullptr || need <= 0) return 0xFFu;
+    uint32_t ok = 0;
+#pragma unroll
+    for (int g = 0; g < 8; g++)
+        if (__ldg(gpu_mem + node * 8 + g) >= need) ok |= 1u << g;
+    return ok;
+}
+
 __global__ void __launch_bounds__(PLACE_TILE)
-place_init(const int4 *__restrict__ topo4, const int32_t *__restrict__ free_mask, int64_t N, int64_t Npad,
-           int64_t node_id_base, Weights W, PipeConsts pc, uint32_t *__restrict__ nodebest,
-           unsigned long long *__restrict__ tilebest, int64_t T) {
+place_init(const int4 *__restrict__ topo4, const int32_t *__restrict__ free_mask, const int32_t *__restrict__ gpu_mem,
+           int64_t N, int64_t Npad, int64_t node_id_base, Weights W, PipeConsts pc, PlaceViews views,
+           uint32_t *__restrict__ nodebest, unsigned long long *__restrict__ tilebest, int64_t T) {
     __shared__ int32_t sW[16];
     __shared__ unsigned long long sRed[9][PLACE_TILE / 32];
     const int tid = threadIdx.x;
@@ -48,16 +84,21 @@ place_init(const int4 *__restrict__ topo4, const int32_t *__restrict__ free_mask
     }
     __syncthreads();
     const int64_t tile = blockIdx.x;
+    const int v = blockIdx.y;
+    int32_t need = 0;
+#pragma unroll
+    for (int i = 0; i < PLACE_MAX_VIEWS; i++)
+        if (i == v) need = views.min_mem[i];
     const int64_t node = tile * PLACE_TILE + tid;
     const bool valid = node < N;
     PairCosts C;
     uint32_t free;
-    stage_node(topo4, free_mask, node, valid, sW, C, free);
+    stage_node(topo4, free_mask, node, valid, sW, C, free, valid ? view_ok_mask(gpu_mem, node, need) : 0xFFu);
 #pragma unroll 1
     for (int k = 0; k <= 8; k++) {
         uint32_t key = node_key(k, C, pc, free, valid);
         if (key >= PEN) key = INF32;
-        nodebest[(int64_t)k * Npad + node] = key;
+        nodebest[((int64_t)v * 9 + k) * Npad + node] = key;
         const unsigned long long w = warp_min_u64(wide_key(key, (unsigned long long)(node_id_base + node)));
         if ((tid & 31) == 0) sRed[k][tid >> 5] = w;
     }
@@ -66,96 +107,151 @@ place_init(const int4 *__restrict__ topo4, const int32_t *__restrict__ free_mask
         unsigned long long b = ~0ull;
 #pragma unroll
         for (int w = 0; w < PLACE_TILE / 32; w++) b = min(b, sRed[tid][w]);
-        tilebest[(int64_t)tid * T + tile] = b;
+        tilebest[((int64_t)v * 9 + tid) * T + tile] = b;
+    }
+}
+
+// Subset costs of one node from half tables.  With the 8 GPUs split into halves lo = GPUs 0..3, hi = GPUs 4..7,
+//   cost(S) = A[S_lo] + B[S_hi] + sum over i in S_lo of R[i][S_hi]
+// A, B: link cost inside a half (16 entries each); R[i][h]: links from GPU i of the low half to the GPUs of
+// h (4 x 16 entries).  The warp builds the 96 entries once per placement (three per lane, a handful of adds
+// each); a subset then costs two loads and at most four predicated load-adds instead of 28 tests.
+constexpr int PLACE_HALF = 96;
+__device__ __forceinline__ void build_half_tables(const int32_t *sCost, int32_t *half, int lane) {
+    {
+        const int m = lane & 15, base = lane < 16 ? 0 : 4;
+        int32_t a = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = i + 1; j < 4; j++)
+                if (((m >> i) & 1) && ((m >> j) & 1)) a += sCost[(base + i) * 8 + base + j];
+        half[lane] = a;                                   // A at [0,16), B at [16,32)
+    }
+#pragma unroll
+    for (int e = lane; e < 64; e += 32) {                 // R[i][h] at [32 + 16 i + h]
+        const int i = e >> 4, h = e & 15;
+        int32_t r = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if ((h >> j) & 1) r += sCost[i * 8 + 4 + j];
+        half[32 + e] = r;
     }
 }
 
 // (cost<<8 | S) of one node for k GPUs, computed by a whole warp: lane per candidate subset.
-// sCost = the node's weight-mapped 8x8 matrix in shared memory.
-__device__ __forceinline__ uint32_t node_key_warp(int k, const int32_t *sCost, uint32_t fm, int lane) {
+__device__ __forceinline__ uint32_t node_key_warp(int k, const int32_t *half, uint32_t fm, int lane) {
     if (k == 0) return 0u;
     const int nsub = c_nsub[k];
     uint32_t key = INF32;
     for (int s = lane; s < nsub; s += 32) {
         const uint32_t S = c_subsets[k][s];
         if (S & ~fm) continue;
-        uint32_t cost = 0;
+        const uint32_t lo = S & 15u, hi = S >> 4;
+        uint32_t cost = (uint32_t)half[lo] + (uint32_t)half[16 + hi];
 #pragma unroll
-        for (int i = 0; i < 8; i++)
-#pragma unroll
-            for (int j = i + 1; j < 8; j++)
-                if ((S & ((1u << i) | (1u << j))) == ((1u << i) | (1u << j))) cost += (uint32_t)sCost[i * 8 + j];
+        for (int i = 0; i < 4; i++)
+            if ((lo >> i) & 1u) cost += (uint32_t)half[32 + 16 * i + hi];
         key = min(key, (cost << 8) | S);
     }
     return __reduce_min_sync(0xFFFFFFFFu, key);
 }
 
 __global__ void __launch_bounds__(PLACE_THREADS, 1)
-place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_mask, int64_t N, int64_t Npad,
-                 int64_t node_id_base, const int4 *__restrict__ pods4, int64_t P, Weights W,
-                 uint32_t *__restrict__ nodebest, unsigned long long *__restrict__ tilebest, int64_t T,
+place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_mask, const int32_t *__restrict__ gpu_mem,
+                 int64_t N, int64_t Npad, int64_t node_id_base, const int4 *__restrict__ pods4, int64_t P, Weights W,
+                 PlaceViews views, uint32_t *__restrict__ nodebest, unsigned long long *__restrict__ tilebest, int64_t T,
                  unsigned long long *__restrict__ keys) {
     __shared__ int32_t sW[16];
-    __shared__ int32_t sCost[64];
-    __shared__ unsigned long long sRed[PLACE_THREADS / 32];
-    __shared__ unsigned long long sWin;
-    __shared__ uint32_t sFree;
+    __shared__ int32_t sViewMin[PLACE_MAX_VIEWS];                 // static indexing of the kernel parameter only
+    __shared__ int32_t sCost[PLACE_WARPS][64];                    // per warp: the winner node's cost matrix
+    __shared__ int32_t sHalf[PLACE_WARPS][PLACE_HALF];            // per warp: its half tables (node_key_warp)
+    __shared__ unsigned long long sRed[2][PLACE_WARPS];           // double buffered by pod parity
+    __shared__ unsigned long long sSuper[PLACE_SUPER_CAP];        // super[v][k][ST]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int V = views.n;
+    const int64_t super_tiles = place_super_tiles(T, V);
+    const int64_t ST = (T + super_tiles - 1) / super_tiles;
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < 16; i++) sW[i] = W.w[i];
+#pragma unroll
+        for (int i = 0; i < PLACE_MAX_VIEWS; i++) sViewMin[i] = views.min_mem[i];
+    }
+    // supertile minima from the tile minima place_init left in memory
+    for (int64_t idx = tid; idx < (int64_t)V * 9 * ST; idx += PLACE_THREADS) {
+        const int64_t vk = idx / ST, st = idx % ST;
+        const int64_t t1 = min(T, (st + 1) * super_tiles);
+        unsigned long long b = ~0ull;
+        for (int64_t t = st * super_tiles; t < t1; t++) b = min(b, tilebest[vk * T + t]);
+        sSuper[idx] = b;
     }
     __syncthreads();
 
     for (int64_t p = 0; p < P; p++) {
-        const int k = __ldg(pods4 + p).x;                 // block-uniform
+        const int4 req = __ldg(pods4 + p);                // block-uniform
+        const int k = req.x;
         if (k < 0 || k > 8) {
             if (tid == 0) keys[p] = ~0ull;
             continue;
         }
-        // 1. best tile for this k
-        const unsigned long long *tb = tilebest + (int64_t)k * T;
+        int v = 0;                                        // the pod's view: the one with its min_mem
+        for (int j = 1; j < V; j++)
+            if (req.w == sViewMin[j]) v = j;
+        // 1. best supertile of (v, k): its minimum is the winning (cost, node, subset) itself
+        const unsigned long long *sp = sSuper + ((int64_t)v * 9 + k) * ST;
         unsigned long long best = ~0ull;
-        for (int64_t t = tid; t < T; t += PLACE_THREADS) best = min(best, tb[t]);
+        for (int64_t s = tid; s < ST; s += PLACE_THREADS) best = min(best, sp[s]);
         best = warp_min_u64(best);
-        if (lane == 0) sRed[warp] = best;
+        unsigned long long *red = sRed[p & 1];
+        if (lane == 0) red[warp] = best;
         __syncthreads();
-        if (warp == 0) {
-            unsigned long long b = warp_min_u64(lane < PLACE_THREADS / 32 ? sRed[lane] : ~0ull);
-            if (lane == 0) sWin = b;
-        }
-        __syncthreads();
-        const unsigned long long win = sWin;
+        const unsigned long long win = warp_min_u64(lane < PLACE_WARPS ? red[lane] : ~0ull);   // every warp for itself
         if (tid == 0) keys[p] = win;
-        if (win == ~0ull || k == 0) {                      // nothing fits / nothing to take
-            __syncthreads();
-            continue;
-        }
-        // 2. commit: the pod takes GPUs S of that node
+        if (win == ~0ull || k == 0) continue;             // nothing fits / nothing to take (block-uniform)
+
+        // 2. commit and refresh, warp by warp.  The new free mask is old & ~S whether a warp reads the
+        // mask before or after warp 0 has written it back.
         const int64_t node = (int64_t)((win >> 8) & 0xFFFFFFFFull) - node_id_base;
         const uint32_t S = (uint32_t)(win & 0xFFull);
-        if (tid < 64) sCost[tid] = sW[topo[node * 64 + tid] & 15];
-        if (tid == 64) {
+        const int64_t tile = node / PLACE_TILE, st = tile / super_tiles;
+        if (warp < min(PLACE_WARPS, V * 9)) {
+            int32_t *cost = sCost[warp];
+            cost[lane] = sW[__ldg(topo + node * 64 + lane) & 15];
+            cost[lane + 32] = sW[__ldg(topo + node * 64 + lane + 32) & 15];
             const uint32_t fm = ((uint32_t)free_mask[node] & 0xFFu) & ~S;
-            free_mask[node] = (int32_t)fm;
-            sFree = fm;
-        }
-        __syncthreads();
-        // 3+4. warp w handles k = w: re-enumerate the node (lane per subset), then refresh the minimum of the
-        // node's tile for that k with the fresh value (the other 127 entries are unchanged in memory).
-        if (warp <= 8) {
-            const uint32_t nk = node_key_warp(warp, sCost, sFree, lane);
-            if (lane == 0) nodebest[(int64_t)warp * Npad + node] = nk;
-            const int64_t tile = node / PLACE_TILE;
-            unsigned long long b = ~0ull;
+            const int32_t my_mem = (gpu_mem != nullptr && lane < 8) ? __ldg(gpu_mem + node * 8 + lane) : 0x7FFFFFFF;
+            __syncwarp();
+            int32_t *half = sHalf[warp];
+            build_half_tables(cost, half, lane);
+            __syncwarp();
+            if (warp == 0 && lane == 0) free_mask[node] = (int32_t)fm;
+            for (int task = warp; task < V * 9; task += PLACE_WARPS) {
+                const int tv = task / 9, tk = task % 9;
+                const int64_t vk = task;
+                // independent global loads first: the tile's node keys, the supertile's tile minima
+                uint32_t nb[PLACE_TILE / 32];
 #pragma unroll
-            for (int j = 0; j < PLACE_TILE / 32; j++) {
-                const int64_t n = tile * PLACE_TILE + lane + 32 * j;
-                const uint32_t v = n == node ? nk : nodebest[(int64_t)warp * Npad + n];
-                b = min(b, wide_key(v, (unsigned long long)(node_id_base + n)));
+                for (int j = 0; j < PLACE_TILE / 32; j++) nb[j] = nodebest[vk * Npad + tile * PLACE_TILE + lane + 32 * j];
+                unsigned long long sb = ~0ull;
+                for (int64_t t = st * super_tiles + lane; t < min(T, (st + 1) * super_tiles); t += 32)
+                    if (t != tile) sb = min(sb, tilebest[vk * T + t]);
+                const uint32_t ok = tv == 0 ? 0xFFu : (__ballot_sync(0xFFFFFFFFu, my_mem >= sViewMin[tv]) & 0xFFu);
+                const uint32_t nk = node_key_warp(tk, half, fm & ok, lane);
+                if (lane == 0) nodebest[vk * Npad + node] = nk;
+                unsigned long long tb = ~0ull;
+#pragma unroll
+                for (int j = 0; j < PLACE_TILE / 32; j++) {
+                    const int64_t n = tile * PLACE_TILE + lane + 32 * j;
+                    tb = min(tb, wide_key(n == node ? nk : nb[j], (unsigned long long)(node_id_base + n)));
+                }
+                tb = warp_min_u64(tb);
+                sb = warp_min_u64(min(sb, tb));
+                if (lane == 0) {
+                    tilebest[vk * T + tile] = tb;
+                    sSuper[vk * ST + st] = sb;
+                }
             }
-            b = warp_min_u64(b);
-            if (lane == 0) tilebest[(int64_t)warp * T + tile] = b;
         }
         __syncthreads();
     }

@@ -20,7 +20,10 @@
 
 namespace kgpu {
 
-constexpr int SP_THREADS = 128;
+#ifndef KGPU_SP_THREADS
+#define KGPU_SP_THREADS 128          // threads per block; 256 halves the per-pod block flushes (set KGPU_SP_MINBLOCKS 4 with it)
+#endif
+constexpr int SP_THREADS = KGPU_SP_THREADS;
 constexpr int SP_WARPS = SP_THREADS / 32;
 constexpr int SP_CHUNK = 512;       // pods per shared-memory chunk; sIdx packs (position | k << 9) in 16 bits
 constexpr int SP_ROW = 29;          // padded row of 28 pair costs per lane in shared memory
@@ -30,9 +33,19 @@ constexpr int SP_ROW = 29;          // padded row of 28 pair costs per lane in s
 #ifndef KGPU_SP_UNROLL
 #define KGPU_SP_UNROLL 1          // pods per trip of a (K,F) bucket loop
 #endif
+#ifndef KGPU_SP_UNROLL_SMALL
+#define KGPU_SP_UNROLL_SMALL KGPU_SP_UNROLL   // the same for the loops that enumerate <= KGPU_SP_SMALL subsets
+#endif
+#ifndef KGPU_SP_SMALL
+#define KGPU_SP_SMALL 6
+#endif
 #define KGPU_PRAGMA(x) _Pragma(#x)
 #define KGPU_UNROLL(n) KGPU_PRAGMA(unroll n)
 
+__host__ __device__ constexpr int sp_choose(int n, int k) { return k == 0 ? 1 : sp_choose(n - 1, k - 1) * n / k; }
+__host__ __device__ constexpr int sp_unroll(int K, int F) {
+    return (K <= 1 || sp_choose(F, K) <= KGPU_SP_SMALL) ? KGPU_SP_UNROLL_SMALL : KGPU_SP_UNROLL;
+}
 __host__ __device__ constexpr int sp_pidx(int i, int j) { return 7 * i - i * (i - 1) / 2 + (j - i - 1); }  // i<j
 
 template <int K, int F>
@@ -42,57 +55,144 @@ __device__ __forceinline__ uint32_t node_key_kf(const PairCosts &C, const PipeCo
     return best_kf<(K < 2 ? 2 : K), (F < 2 ? 2 : F)>(C, pc);
 }
 
-// One (K, F) loop: all pods of the chunk that want K GPUs, enumerating positions 0..F-1.
-template <int K, int F, bool PER_PAIR, bool MEM>
-__device__ __forceinline__ void sp_bucket(const PairCosts &C, const PipeConsts pc, uint32_t nfree, bool valid,
-                                          const int32_t (&mem)[8], uint32_t lane_field, const uint16_t *sIdx,
-                                          const uint8_t *sK, const int32_t *sMin, int begin, int end, uint32_t *sBestW) {
-    KGPU_UNROLL(KGPU_SP_UNROLL)
-    for (int i = begin; i < end; i++) {
-        const uint32_t word = sIdx[i];             // chunk position (9 bits) | the pod's k << 9
-        const int p = (int)(word & (SP_CHUNK - 1));
-        PipeConsts pcl = pc;
-        if (PER_PAIR && !MEM) {                    // un-hoistable per-pair work: see score_pairs.cuh
-            pcl.one = (word >> 9) - (uint32_t)(K - 1);
-            pcl.minus_one = 0u - pcl.one;
-        }
-        uint32_t key;
-        if (MEM) {
-            const int32_t need = sMin[p];
-            uint32_t pen[8], elig = 0;
-#pragma unroll
-            for (int g = 0; g < 8; g++) {
-                const bool lt = mem[g] < need;
-                pen[g] = lt ? PEN : 0u;
-                if (!lt && (uint32_t)g < nfree) elig |= 1u << g;      // position g: free and big enough
-            }
-            if (K == 0) key = valid ? 0u : INF32;
-            else if (K == 1) key = elig ? (elig & (0u - elig)) : INF32;
-            else {
-                PairCosts C2;
-                apply_pens(C, C2, pen);
-                key = best_kf<(K < 2 ? 2 : K), (F < 2 ? 2 : F)>(C2, pcl);
-            }
-        } else {
-            key = node_key_kf<K, F>(C, pcl, nfree, valid);
-        }
-        const uint32_t v = key >= PEN ? INF32 : (((key & ~0xFFu) << 5) | lane_field | (key & 0xFFu));
-        const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, v);
-        if (lane_field == 0) sBestW[p] = m;
+// Per-warp pod table of a chunk, in BUCKET order (pods grouped by k): the per-pod multiplier the
+// enumeration runs on (see score_pairs.cuh: it makes every instruction of the enumeration depend on
+// per-pod data) next to the slot the warp's result for that pod goes to.  Pods sit in groups of
+// SP_GROUP; a bucket loop handles one group per trip: one LDS of the multipliers, the enumerations, one
+// STS of the results, loop control once.  Buckets are padded to whole groups with dummy pods
+// (multiplier 1, result never read: sIdx marks them).
+#ifndef KGPU_SP_GROUP
+#define KGPU_SP_GROUP 2          // pods per trip of a bucket loop: 1, 2 or 4
+#endif
+constexpr int SP_GROUP = KGPU_SP_GROUP;
+static_assert(SP_GROUP == 1 || SP_GROUP == 2 || SP_GROUP == 4, "KGPU_SP_GROUP must be 1, 2 or 4");
+constexpr int SP_POS = SP_CHUNK + 10 * (SP_GROUP - 1);          // positions of a chunk in bucket order, dummies included
+constexpr int SP_TAB = (SP_POS + SP_GROUP - 1) / SP_GROUP + 1;  // groups (+1: the prefetch build reads one past the last)
+constexpr uint16_t SP_DUMMY = 0xFFFFu;
+constexpr int SP_MEM_SUB = 4;        // MEM launch: pods of one k are sub-bucketed by a hash of min_mem, so equal requirements sit together
+struct alignas(8 * KGPU_SP_GROUP) SpEnt {
+    uint32_t one[SP_GROUP];     // MEM: the pods' min_mem instead (the MEM loops derive `one` from K)
+    uint32_t best[SP_GROUP];    // warp key of the best (node, subset) of this warp for the pod, INF32 = none
+};
+
+// Warp key.  BYTE_KEYS (every cost < 2^16, i.e. every weight <= 2340): cost<<16 | lane<<8 | S, built
+// from the lane key (cost<<8 | S) with ONE PRMT whose selector also encodes "this lane cannot serve
+// k = K" (nfree < K, loop invariant): it then picks four 0xFF bytes = INF32.  Otherwise:
+// cost<<13 | lane<<8 | S with an IMAD for the shift and two LOP3.
+struct SpFmt {
+    uint32_t lane_hi;   // BYTE_KEYS: lane<<8 | 0xFFFF0000          else: feasible ? lane<<8 : 0xFFFFFFFF
+    uint32_t sel;       // BYTE_KEYS: feasible ? 0x2150 : 0x7777     else: unused
+};
+template <bool BYTE_KEYS>
+__device__ __forceinline__ SpFmt sp_fmt(uint32_t lane_field, bool feasible) {
+    SpFmt f;
+    if (BYTE_KEYS) { f.lane_hi = lane_field | 0xFFFF0000u; f.sel = feasible ? 0x2150u : 0x7777u; }
+    else           { f.lane_hi = feasible ? lane_field : 0xFFFFFFFFu; f.sel = 0u; }
+    return f;
+}
+template <bool BYTE_KEYS>
+__device__ __forceinline__ uint32_t sp_warp_key(uint32_t key, const SpFmt f, uint32_t thirty_two) {
+    if (BYTE_KEYS) return __byte_perm(key, f.lane_hi, f.sel);
+    return ((key * thirty_two) & 0xFFFFE000u) | ((key & 0xFFu) | f.lane_hi);
+}
+
+#ifndef KGPU_SP_PREFETCH
+#define KGPU_SP_PREFETCH 0       // 1: load the next group's multipliers one trip ahead (reads one group past a bucket's end)
+#endif
+__device__ __forceinline__ void sp_load_ones(const SpEnt *ent, uint32_t (&ones)[SP_GROUP]) {
+    if (SP_GROUP == 4) {
+        const uint4 o = *reinterpret_cast<const uint4 *>(ent->one);          // one LDS.128
+        ones[0] = o.x; ones[1 % SP_GROUP] = o.y; ones[2 % SP_GROUP] = o.z; ones[3 % SP_GROUP] = o.w;
+    } else if (SP_GROUP == 2) {
+        const uint2 o = *reinterpret_cast<const uint2 *>(ent->one);          // one LDS.64
+        ones[0] = o.x; ones[1 % SP_GROUP] = o.y;
+    } else {
+        ones[0] = ent->one[0];
     }
 }
 
-template <int K, bool PER_PAIR, bool MEM>
+// One (K, F) loop: all pods of the chunk that want K GPUs, enumerating positions 0..F-1.
+template <int K, int F, bool PER_PAIR, bool MEM, bool BYTE_KEYS>
+__device__ __forceinline__ void sp_bucket(const PairCosts &C, const PipeConsts pc, uint32_t nfree, bool valid,
+                                          const int32_t (&mem)[8], uint32_t lane_field, SpEnt *tab, int begin, int end) {
+    // (begin >> 30) is 0; tying the test to this chunk's bucket offset keeps the compiler from hoisting the
+    // nine per-K selectors to the top of the kernel, where they cost nine registers for the whole run.
+    const uint32_t need_free = (uint32_t)K + ((uint32_t)begin >> 30);
+    const SpFmt fmt = sp_fmt<BYTE_KEYS>(lane_field, MEM ? true : (valid && nfree >= need_free));
+    const uint32_t thirty_two = pc.one << 5;       // a register, so that the shift is an IMAD (kernel parameter: opaque)
+    int32_t last_need = -1;                        // MEM: the requirement C2 / elig were last built for
+    uint32_t elig = 0;
+    PairCosts C2 = C;
+#if KGPU_SP_PREFETCH
+    uint32_t nxt[SP_GROUP];
+    sp_load_ones(reinterpret_cast<SpEnt *>(reinterpret_cast<char *>(tab) + (uint32_t)begin * 8u), nxt);
+#endif
+    KGPU_UNROLL((sp_unroll(K, F)))
+    // byte offsets (8 bytes per position, begin and end are whole groups): uniform, because begin and end
+    // come from shared memory, so the loop runs on the uniform datapath and the group address is tab + offset
+    for (uint32_t off = (uint32_t)begin * 8u; off != (uint32_t)end * 8u; off += (uint32_t)sizeof(SpEnt)) {
+        SpEnt *const ent = reinterpret_cast<SpEnt *>(reinterpret_cast<char *>(tab) + off);
+        uint32_t ones[SP_GROUP], v[SP_GROUP];
+#if KGPU_SP_PREFETCH
+#pragma unroll
+        for (int g = 0; g < SP_GROUP; g++) ones[g] = nxt[g];
+        sp_load_ones(ent + 1, nxt);                // next trip's multipliers: their LDS latency overlaps this trip
+#else
+        sp_load_ones(ent, ones);
+#endif
+#pragma unroll
+        for (int g = 0; g < SP_GROUP; g++) {
+            PipeConsts pcl = pc;
+            if (MEM) {
+                const int32_t need = (int32_t)ones[g];
+                if (need != last_need) {               // warp-uniform; rare: the sort puts equal requirements together
+                    last_need = need;
+                    uint32_t pen[8];
+                    elig = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const bool lt = mem[q] < need;
+                        pen[q] = lt ? PEN : 0u;
+                        if (!lt && (uint32_t)q < nfree) elig |= 1u << q;      // position q: free and big enough
+                    }
+                    if (K >= 2) apply_pens(C, C2, pen);
+                }
+                uint32_t key;
+                if (K == 0) key = valid ? 0u : INF32;
+                else if (K == 1) key = elig ? (elig & (0u - elig)) : INF32;
+                else key = best_kf<(K < 2 ? 2 : K), (F < 2 ? 2 : F)>(C2, pcl);
+                v[g] = key >= PEN ? INF32 : sp_warp_key<BYTE_KEYS>(key, fmt, thirty_two);
+            } else {
+                if (PER_PAIR) {                        // un-hoistable per-pair work: see score_pairs.cuh
+                    pcl.one = ones[g];
+                    if (K >= 5) pcl.minus_one = 0u - pcl.one;
+                }
+                // lanes that cannot serve K (fmt says so) compute a key like the others and drop it
+                const uint32_t key = K == 0 ? 0u : K == 1 ? pcl.one : best_kf<(K < 2 ? 2 : K), (F < 2 ? 2 : F)>(C, pcl);
+                v[g] = sp_warp_key<BYTE_KEYS>(key, fmt, thirty_two);
+            }
+        }
+        uint32_t m[SP_GROUP];
+#pragma unroll
+        for (int g = 0; g < SP_GROUP; g++) m[g] = __reduce_min_sync(0xFFFFFFFFu, v[g]);
+        if (lane_field == 0) {
+            if (SP_GROUP == 4) *reinterpret_cast<uint4 *>(ent->best) = make_uint4(m[0], m[1 % SP_GROUP], m[2 % SP_GROUP], m[3 % SP_GROUP]);
+            else if (SP_GROUP == 2) *reinterpret_cast<uint2 *>(ent->best) = make_uint2(m[0], m[1 % SP_GROUP]);   // one STS.64
+            else ent->best[0] = m[0];
+        }
+    }
+}
+
+template <int K, bool PER_PAIR, bool MEM, bool BYTE_KEYS>
 __device__ __forceinline__ void sp_run_k(int F, const PairCosts &C, const PipeConsts pc, uint32_t nfree, bool valid,
-                                         const int32_t (&mem)[8], uint32_t lane_field, const uint16_t *sIdx,
-                                         const uint8_t *sK, const int32_t *sMin, int begin, int end, uint32_t *sBestW) {
+                                         const int32_t (&mem)[8], uint32_t lane_field, SpEnt *tab, int begin, int end) {
     if (begin >= end || F < K) return;             // F < K: no lane of this warp has K free GPUs
 #define KGPU_SP_CASE(FF)                                                                                         \
     case FF:                                                                                                     \
-        if (FF >= K) sp_bucket<K, (FF >= K ? FF : K), PER_PAIR, MEM>(C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, begin, end, sBestW); \
+        if (FF >= K) sp_bucket<K, (FF >= K ? FF : K), PER_PAIR, MEM, BYTE_KEYS>(C, pc, nfree, valid, mem, lane_field, tab, begin, end); \
         break;
     if (K <= 1) {                                  // F does not matter for k = 0, 1
-        sp_bucket<K, 8, PER_PAIR, MEM>(C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, begin, end, sBestW);
+        sp_bucket<K, 8, PER_PAIR, MEM, BYTE_KEYS>(C, pc, nfree, valid, mem, lane_field, tab, begin, end);
         return;
     }
     switch (F) {
@@ -166,35 +266,58 @@ compact_nodes(const int4 *__restrict__ topo4, const int32_t *__restrict__ free_m
         }
 }
 
-// grid = (slot tiles of 128, pod splits); block = 128 threads.  order[slot] = node index or -1 (padding).
-template <bool PER_PAIR, bool MEM>
+// grid = (work items) or (slot tiles, pod splits); block = SP_THREADS.  order[slot] = node index or -1 (padding).
+template <bool PER_PAIR, bool MEM, bool BYTE_KEYS>
 __global__ void __launch_bounds__(SP_THREADS, MEM ? 4 : KGPU_SP_MINBLOCKS)
 score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__ perm_in,
                    const int32_t *__restrict__ free_mask,
                    const int32_t *__restrict__ gpu_mem, const int32_t *__restrict__ order,
                    const int *__restrict__ mem_flag, int64_t node_id_base, const int4 *__restrict__ pods4, int64_t P,
-                   int pods_per_split, PipeConsts pc, unsigned long long *__restrict__ keys) {
+                   int pods_per_split, const int4 *__restrict__ work, PipeConsts pc, unsigned long long *__restrict__ keys) {
     if (MEM && *mem_flag == 0) return;
-    __shared__ int32_t sCnt[10], sOff[11];
+    constexpr int SUB = MEM ? SP_MEM_SUB : 1, NB = 9 * SUB + 1;     // sort buckets: (k, sub) for k = 0..8, then "not for this launch"
+    __shared__ int32_t sCnt[NB], sOff[11], sPad[9];
     __shared__ uint8_t sK[SP_CHUNK];
-    __shared__ uint16_t sIdx[SP_CHUNK];
-    __shared__ uint32_t sBest[SP_WARPS][SP_CHUNK];
-    __shared__ int32_t sMin[MEM ? SP_CHUNK : 1];
-    __shared__ uint32_t sPerm[SP_THREADS];             // position -> GPU index, 8 nibbles
+    __shared__ uint16_t sIdx[SP_POS];                  // bucket-order position -> chunk position (SP_DUMMY: padding)
+    __shared__ SpEnt sTab[SP_WARPS][SP_TAB];           // per warp, bucket order: multipliers | results
+    __shared__ uint32_t sHotLo[SP_THREADS], sHotHi[SP_THREADS];   // position g -> byte (1 << GPU index), g = 0..3 | 4..7
     __shared__ int32_t sNode[SP_THREADS];              // slot -> node index (-1 = padding)
 
     const int tid = threadIdx.x;
-    uint32_t *const sBestW = sBest[tid >> 5];
+    SpEnt *const tab = sTab[tid >> 5];
     const uint32_t lane_field = (uint32_t)(tid & 31) << 8;
 
     // ---- staging: the node's compacted pair costs (7 x 16 B), permutation and free count ----------
-    const int64_t slot = (int64_t)blockIdx.x * SP_THREADS + tid;
+    // which tile, which pods: a work item {tile, pod_begin, pod_end} of the host's list (sparse_work.h), or the
+    // plain grid (tile = blockIdx.x, equal pod ranges along blockIdx.y) when there is no list
+    int64_t tile_index = blockIdx.x, p_begin = (int64_t)blockIdx.y * pods_per_split, p_end = min(P, p_begin + pods_per_split);
+    if (work != nullptr) {
+        const int4 item = __ldg(work + blockIdx.x);
+        tile_index = item.x; p_begin = item.y; p_end = item.z;
+    }
+    const int64_t slot = tile_index * SP_THREADS + tid;
     const int32_t node = __ldg(order + slot);
     const bool valid = node >= 0;
     sNode[tid] = node;
     const uint32_t nfree = valid ? (uint32_t)__popc((uint32_t)__ldg(free_mask + node) & 0xFFu) : 0u;
     const uint32_t perm = valid ? __ldg(perm_in + node) : 0x76543210u;
-    sPerm[tid] = perm;
+    {
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            lo |= (1u << ((perm >> (4 * g)) & 7u)) << (8 * g);
+            hi |= (1u << ((perm >> (4 * g + 16)) & 7u)) << (8 * g);
+        }
+        sHotLo[tid] = lo;
+        sHotHi[tid] = hi;
+    }
+    // Are the tile's slots in increasing node id (one class, padding only at the end)?  Then (cost, warp, lane)
+    // order IS (cost, node) order and the flush can min the four warp keys directly.
+    bool ordered = false;
+    if (BYTE_KEYS) {
+        const int32_t prev = tid > 0 ? __ldg(order + slot - 1) : -1;
+        ordered = __syncthreads_and(tid == 0 || node < 0 || (prev >= 0 && prev < node)) != 0;
+    }
     PairCosts C;
     {
         uint32_t wds[28];
@@ -219,70 +342,105 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
     }
     const int F = (int)__reduce_max_sync(0xFFFFFFFFu, nfree);    // warp-uniform bound on usable positions
 
-    const int64_t p_begin = (int64_t)blockIdx.y * pods_per_split;
-    const int64_t p_end = min(P, p_begin + pods_per_split);
-
     for (int64_t c0 = p_begin; c0 < p_end; c0 += SP_CHUNK) {
         const int cn = (int)min((int64_t)SP_CHUNK, p_end - c0);
         __syncthreads();
-        if (tid < 10) sCnt[tid] = 0;
+        if (tid < NB) sCnt[tid] = 0;
         __syncthreads();
         for (int i = tid; i < cn; i += SP_THREADS) {
             const int4 req = __ldg(pods4 + c0 + i);
             const bool wants_mem = req.w > 0;
-            const int b = (req.x < 0 || req.x > 8 || wants_mem != MEM) ? 9 : req.x;
+            int b = 9 * SUB;
+            if (req.x >= 0 && req.x <= 8 && wants_mem == MEM)
+                b = req.x * SUB + (MEM ? (int)(((uint32_t)req.w * 0x9E3779B1u) >> 30) : 0);
             sK[i] = (uint8_t)b;
-            if (MEM) sMin[i] = req.w;
             atomicAdd(&sCnt[b], 1);
-#pragma unroll
-            for (int w = 0; w < SP_WARPS; w++) sBest[w][i] = INF32;      // warps skip the pods they cannot serve
         }
         __syncthreads();
-        if (tid == 0) {
+        if (tid == 0) {                            // sOff[k]: where k's pods start (a group boundary); sCnt: running positions
             int acc = 0;
-#pragma unroll
-            for (int b = 0; b < 10; b++) { sOff[b] = acc; acc += sCnt[b]; sCnt[b] = sOff[b]; }
-            sOff[10] = acc;
+#pragma unroll 1
+            for (int k = 0; k < 9; k++) {
+                sOff[k] = acc;
+                for (int u = 0; u < SUB; u++) { const int c = sCnt[k * SUB + u]; sCnt[k * SUB + u] = acc; acc += c; }
+                sPad[k] = acc % SP_GROUP ? acc : -1;                 // position of k's first dummy pod, if it needs any
+                acc = (acc + SP_GROUP - 1) / SP_GROUP * SP_GROUP;
+            }
+            sOff[9] = acc;
+            const int c9 = sCnt[9 * SUB];
+            sCnt[9 * SUB] = acc;
+            sOff[10] = acc + c9;
         }
         __syncthreads();
-        for (int i = tid; i < cn; i += SP_THREADS) sIdx[atomicAdd(&sCnt[sK[i]], 1)] = (uint16_t)(i | ((int)sK[i] << 9));
-        __syncthreads();
-
-        sp_run_k<0, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[0], sOff[1], sBestW);
-        sp_run_k<1, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[1], sOff[2], sBestW);
-        sp_run_k<2, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[2], sOff[3], sBestW);
-        sp_run_k<3, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[3], sOff[4], sBestW);
-        sp_run_k<4, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[4], sOff[5], sBestW);
-        sp_run_k<5, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[5], sOff[6], sBestW);
-        sp_run_k<6, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[6], sOff[7], sBestW);
-        sp_run_k<7, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[7], sOff[8], sBestW);
-        sp_run_k<8, PER_PAIR, MEM>(F, C, pc, nfree, valid, mem, lane_field, sIdx, sK, sMin, sOff[8], sOff[9], sBestW);
-        __syncthreads();
-
-        // block result per pod: min over the 4 warps of (cost, node id) -- a tile may hold warps of two
-        // adjacent classes, so node ids are compared explicitly -- then S' -> real GPU mask through the
-        // winner's permutation, and REDG.MIN.64 into keys[pod].
         for (int i = tid; i < cn; i += SP_THREADS) {
-            if (sK[i] == 9) continue;
-            unsigned long long best = ~0ull;       // cost<<40 | node_index<<8 | slot_in_tile... (slot kept aside)
-            int best_slot = -1;
-            uint32_t best_m = 0;
+            const int b = sK[i];
+            const int at = atomicAdd(&sCnt[b], 1);
+            sIdx[at] = (uint16_t)i;
+            // the per-pod multiplier: the pod's own k less what its bucket adds back (= 1 at run time)
+            const int4 req = __ldg(pods4 + c0 + i);
+            const uint32_t one = MEM ? (uint32_t)req.w : (uint32_t)(req.x - (b < 9 ? b - 1 : 0));
 #pragma unroll
             for (int w = 0; w < SP_WARPS; w++) {
-                const uint32_t m = sBest[w][i];
-                if (m == INF32) continue;
-                const int s = w * 32 + (int)((m >> 8) & 31u);
-                const unsigned long long cand = ((unsigned long long)(m >> 13) << 32) | (uint32_t)sNode[s];
-                if (cand < best) { best = cand; best_slot = s; best_m = m; }
+                sTab[w][at / SP_GROUP].one[at % SP_GROUP] = one;
+                sTab[w][at / SP_GROUP].best[at % SP_GROUP] = INF32;          // warps skip the pods they cannot serve
+            }
+        }
+        if (SP_GROUP > 1 && tid < 9 && sPad[tid] >= 0) {                   // k's padding: dummy pods up to the group boundary
+            for (int at = sPad[tid]; at % SP_GROUP != 0; at++) {
+                sIdx[at] = SP_DUMMY;
+#pragma unroll
+                for (int w = 0; w < SP_WARPS; w++) {
+                    sTab[w][at / SP_GROUP].one[at % SP_GROUP] = MEM ? 0u : 1u;
+                    sTab[w][at / SP_GROUP].best[at % SP_GROUP] = INF32;
+                }
+            }
+        }
+        __syncthreads();
+
+        sp_run_k<0, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[0], sOff[1]);
+        sp_run_k<1, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[1], sOff[2]);
+        sp_run_k<2, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[2], sOff[3]);
+        sp_run_k<3, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[3], sOff[4]);
+        sp_run_k<4, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[4], sOff[5]);
+        sp_run_k<5, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[5], sOff[6]);
+        sp_run_k<6, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[6], sOff[7]);
+        sp_run_k<7, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[7], sOff[8]);
+        sp_run_k<8, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[8], sOff[9]);
+        __syncthreads();
+
+        // block result per pod: min over the warps of (cost, node id), S' -> real GPU mask through the
+        // winner's one-hot bytes, REDG.MIN.64 into keys[pod].  Ordered tile + byte keys: the warp index goes
+        // into bits 13.. of the warp key (its lane byte has 3 spare bits) and plain 32-bit mins decide;
+        // otherwise (a tile of two classes) node ids are compared explicitly.
+        const int served = sOff[9];                // bucket 9 (not for this launch) sits at the end
+        for (int i = tid; i < served; i += SP_THREADS) {
+            if (SP_GROUP > 1 && sIdx[i] == SP_DUMMY) continue;
+            uint32_t best_m = INF32, cost = 0;
+            int best_slot = -1;
+            if (BYTE_KEYS && ordered) {
+#pragma unroll
+                for (int w = 0; w < SP_WARPS; w++) best_m = min(best_m, sTab[w][i / SP_GROUP].best[i % SP_GROUP] | ((uint32_t)w << 13));   // INF32 stays INF32
+                if (best_m != INF32) { best_slot = (int)((best_m >> 8) & (uint32_t)(SP_THREADS - 1)); cost = best_m >> 16; }
+            } else {
+                unsigned long long best = ~0ull;   // cost<<32 | node index
+#pragma unroll
+                for (int w = 0; w < SP_WARPS; w++) {
+                    const uint32_t m = sTab[w][i / SP_GROUP].best[i % SP_GROUP];
+                    if (m == INF32) continue;
+                    const int s = w * 32 + (int)((m >> 8) & 31u);
+                    const unsigned long long cand = ((unsigned long long)(m >> (BYTE_KEYS ? 16 : 13)) << 32) | (uint32_t)sNode[s];
+                    if (cand < best) { best = cand; best_slot = s; best_m = m; cost = (uint32_t)(best >> 32); }
+                }
             }
             if (best_slot >= 0) {
-                const uint32_t pm = sPerm[best_slot];
-                uint32_t S = 0;
-#pragma unroll
-                for (int g = 0; g < 8; g++)
-                    if ((best_m >> g) & 1u) S |= 1u << ((pm >> (4 * g)) & 7u);
-                const unsigned long long nid = (unsigned long long)(node_id_base + (long long)(best & 0xFFFFFFFFull));
-                atomicMin(&keys[c0 + i], ((best >> 32) << 40) | (nid << 8) | S);
+                // S' bit g set -> byte g of the one-hot words; OR the selected bytes together
+                const uint32_t sel_lo = (((best_m & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+                const uint32_t sel_hi = ((((best_m >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+                uint32_t t = (sHotLo[best_slot] & sel_lo) | (sHotHi[best_slot] & sel_hi);
+                t |= t >> 16;
+                const uint32_t S = (t | (t >> 8)) & 0xFFu;
+                const unsigned long long nid = (unsigned long long)(node_id_base + (long long)sNode[best_slot]);
+                atomicMin(&keys[c0 + sIdx[i]], ((unsigned long long)cost << 40) | (nid << 8) | S);
             }
         }
     }

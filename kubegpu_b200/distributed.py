@@ -30,3 +30,19 @@ def all_gather_keys(local_keys, group=None):
     out = torch.empty((world, local_keys.numel()), dtype=local_keys.dtype, device=local_keys.device)
     dist.all_gather_into_tensor(out.view(-1), local_keys.contiguous(), group=group)
     return out
+
+
+_SIGN = -(1 << 63)
+
+
+def all_reduce_min_keys(local_keys, group=None):
+    """One all-reduce instead of all-gather + K2: the per-pod minimum over the ranks' uint64 keys, given
+    and returned as their int64 view (in place).  Collectives reduce SIGNED integers, so the sign bit is
+    flipped around the reduction (an order-preserving map of uint64 onto int64; NO_FIT stays the largest)."""
+    import torch
+    import torch.distributed as dist
+    sign = torch.tensor(_SIGN, dtype=torch.int64, device=local_keys.device)
+    local_keys.bitwise_xor_(sign)
+    dist.all_reduce(local_keys, op=dist.ReduceOp.MIN, group=group)
+    local_keys.bitwise_xor_(sign)
+    return local_keys

@@ -168,6 +168,27 @@ class Scorer:
         self._check(self._L.kgpu_reduce_shards_device(self._h, d_gathered_addr, int(G), int(P), d_out_addr,
                                                       stream or None))
 
+    # ---- peer-memory key exchange (EXPERIMENTAL; one process per GPU) -------------------------
+    def exchange_init(self, world: int, rank: int, max_pods: int) -> bytes:
+        """Allocate this rank's result/flag memory; returns the 64-byte IPC handle to all-gather."""
+        buf = ctypes.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        self._check(self._L.kgpu_exchange_init(self._h, int(world), int(rank), int(max_pods), buf))
+        return bytes(buf.raw)
+
+    def exchange_connect(self, handles) -> None:
+        """handles: the world's IPC handles in rank order (list of 64-byte strings)."""
+        blob = b"".join(bytes(x) for x in handles)
+        if len(blob) % _lib.IPC_HANDLE_BYTES:
+            raise ValueError("every handle must be %d bytes" % _lib.IPC_HANDLE_BYTES)
+        self._check(self._L.kgpu_exchange_connect(self._h, ctypes.c_char_p(blob)))
+
+    def score_batch_exchange(self, d_pods_addr: int, P: int, stream: int = 0, batch_flags: int = 0) -> int:
+        """K1 on the local shard + push/sync over peer memory; returns the DEVICE address of the global keys
+        (uint64[P], owned by the handle, valid until the next-but-one call)."""
+        out = ctypes.c_void_p()
+        self._check(self._L.kgpu_score_batch_exchange(self._h, d_pods_addr, int(P), ctypes.byref(out), stream or None, int(batch_flags)))
+        return int(out.value or 0)
+
     @property
     def kernel_launches(self) -> int:
         return int(self._L.kgpu_kernel_launches(self._h))

@@ -263,6 +263,20 @@ void kgpu_oracle_place_batch_plain(const int32_t *topo, int32_t *free_mask, int6
     }
 }
 
+/* Memory-aware sequential placement: as above, each pod scored with kgpu_oracle_score_batch_mem
+ * (GPUs with less than the pod's min_mem MiB do not count as free for that pod). */
+void kgpu_oracle_place_batch_mem(const int32_t *topo, int32_t *free_mask, const int32_t *mem, int64_t N,
+                                 int64_t node_id_base, const int32_t *pods, int64_t P,
+                                 const int32_t *W, uint64_t *out_keys)
+{
+    for (int64_t p = 0; p < P; p++) {
+        kgpu_oracle_score_batch_mem(topo, free_mask, mem, N, node_id_base, pods + 4 * p, 1, W, out_keys + p);
+        if (out_keys[p] == KGPU_NO_FIT) continue;
+        int64_t n = (int64_t)((out_keys[p] >> 8) & 0xFFFFFFFFu) - node_id_base;
+        free_mask[n] = (int32_t)(((uint32_t)free_mask[n] & 0xFFu) & ~(uint32_t)(out_keys[p] & 0xFFu));
+    }
+}
+
 /* Same results with a per-node cache of the 9 node keys (only the chosen node changes). */
 void kgpu_oracle_place_batch(const int32_t *topo, int32_t *free_mask, int64_t N,
                              int64_t node_id_base, const int32_t *pods, int64_t P,

@@ -62,6 +62,8 @@ def lib() -> ctypes.CDLL:
         for fn in (L.kgpu_oracle_place_batch, L.kgpu_oracle_place_batch_plain):
             fn.restype = None
             fn.argtypes = [i32p, i32p, ctypes.c_int64, ctypes.c_int64, i32p, ctypes.c_int64, i32p, u64p]
+        L.kgpu_oracle_place_batch_mem.restype = None
+        L.kgpu_oracle_place_batch_mem.argtypes = [i32p, i32p, i32p, ctypes.c_int64, ctypes.c_int64, i32p, ctypes.c_int64, i32p, u64p]
         L.kgpu_oracle_reduce_shards.restype = None
         L.kgpu_oracle_reduce_shards.argtypes = [u64p, ctypes.c_int, ctypes.c_int64, u64p]
         _lib = L
@@ -108,12 +110,20 @@ def score_batch(topo, free_mask, pods, W=DEFAULT_WEIGHTS, node_id_base: int = 0,
     return out
 
 
-def place_batch(topo, free_mask, pods, W=DEFAULT_WEIGHTS, node_id_base: int = 0, plain: bool = False):
-    """K3 twin: sequential stateful placement.  Returns (keys[P], free_mask_after[N])."""
+def place_batch(topo, free_mask, pods, W=DEFAULT_WEIGHTS, node_id_base: int = 0, plain: bool = False, mem=None):
+    """K3 twin: sequential stateful placement.  Returns (keys[P], free_mask_after[N]).  With mem[N,8]
+    the pods' min_mem (pods[:,3]) is honoured (plain loop)."""
     topo, pods, W = _i32(topo), _i32(pods), _i32(W)
     free_after = np.array(free_mask, dtype=np.int32, copy=True)
     N, P = free_after.shape[0], pods.shape[0]
     out = np.empty(P, dtype=np.uint64)
+    if mem is not None:
+        mem = _i32(mem)
+        assert mem.size == 8 * N
+        lib().kgpu_oracle_place_batch_mem(_p(topo, ctypes.c_int32), _p(free_after, ctypes.c_int32), _p(mem, ctypes.c_int32), N,
+                                          int(node_id_base), _p(pods, ctypes.c_int32), P, _p(W, ctypes.c_int32),
+                                          _p(out, ctypes.c_uint64))
+        return out, free_after
     fn = lib().kgpu_oracle_place_batch_plain if plain else lib().kgpu_oracle_place_batch
     fn(_p(topo, ctypes.c_int32), _p(free_after, ctypes.c_int32), N, int(node_id_base), _p(pods, ctypes.c_int32), P,
        _p(W, ctypes.c_int32), _p(out, ctypes.c_uint64))

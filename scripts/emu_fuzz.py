@@ -2,7 +2,7 @@
 """Randomised CPU check of the kernel sources under the emulation harness (tests/emu) against the oracle:
     python scripts/emu_fuzz.py [--seconds 300] [--seed 1]
 Random node counts, pod counts, free-mask densities, weights (byte-key and general layouts), memory
-requirements, pod splits, sequential placement.  Prints the failing case and exits 1."""
+requirements, pod splits / work list, sequential placement with views.  Prints the failing case and exits 1."""
 import argparse
 import ctypes
 import os
@@ -26,12 +26,21 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=300)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--define", action="append", default=[], help="build knob for a private emulation build, e.g. KGPU_SP_GROUP=4")
     a = ap.parse_args()
-    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu")])
-    L = ctypes.CDLL(os.path.join(ROOT, "tests", "emu", "_build", "libkgpu_emu.so"))
+    emu_dir = os.path.join(ROOT, "tests", "emu")
+    if a.define:
+        lib = "/tmp/libkgpu_emu_%s.so" % "_".join(d.replace("=", "") for d in a.define)
+        subprocess.check_call(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread"] + ["-D" + d for d in a.define] +
+                              ["-I" + os.path.join(emu_dir, "stub"), "-I" + os.path.join(ROOT, "kubegpu_b200", "csrc"), "-o", lib,
+                               os.path.join(emu_dir, "emu_kernels.cc")])
+    else:
+        subprocess.check_call(["make", "-s", "-C", emu_dir])
+        lib = os.path.join(emu_dir, "_build", "libkgpu_emu.so")
+    L = ctypes.CDLL(lib)
     L.emu_score_sparse.restype = None
     L.emu_score_dense.restype = None
-    L.emu_place_batch.restype = None
+    L.emu_place_batch.restype = ctypes.c_int
     rng = np.random.default_rng(a.seed)
     t0, n_cases = time.time(), 0
     while time.time() - t0 < a.seconds:
@@ -70,7 +79,7 @@ def main():
         if use_mem:
             pods[:, 3] = rng.choice(np.array(synth.POD_MIN_MEM_CHOICES_MIB, dtype=np.int32), size=P)
         base = int(rng.choice([0, 5, 2**31 - 1000]))
-        splits = int(rng.choice([1, 2, 3, 7]))
+        splits = int(rng.choice([1, 2, 3, 7, -1, -16, -1184]))
         want = oracle_b.score_batch(topo, free, pods, W, node_id_base=base, mem=mem)
         case = dict(N=N, P=P, gen=int(gen), seed=seed, dens=str(dens), wkind=int(wkind), use_mem=use_mem, base=base, splits=splits)
         for name, fn in (("sparse", L.emu_score_sparse), ("dense", L.emu_score_dense)):
@@ -85,11 +94,10 @@ def main():
         if n_cases % 3 == 0 and P <= 400:            # sequential placement (slower under emulation)
             f = free.copy()
             keys = np.empty(P, dtype=np.uint64)
-            pz = pods.copy(); pz[:, 3] = 0
-            L.emu_place_batch(ptr(topo), ptr(f), ctypes.c_int64(N), ctypes.c_int64(base),
-                                   ptr(pz), ctypes.c_int64(P), ptr(W), ptr(keys, ctypes.c_uint64))
-            rc = 0
-            wk, wf = oracle_b.place_batch(topo, free.copy(), pz, W, node_id_base=base, plain=True)
+            rc = L.emu_place_batch(ptr(topo), ptr(f), None if mem is None else ptr(mem), ctypes.c_int64(N), ctypes.c_int64(base),
+                                   ptr(pods), ctypes.c_int64(P), ptr(W), ptr(keys, ctypes.c_uint64))
+            wk, wf = oracle_b.place_batch(topo, free.copy(), pods, W, node_id_base=base, mem=mem, plain=True) if mem is None else \
+                oracle_b.place_batch(topo, free.copy(), pods, W, node_id_base=base, mem=mem)
             if rc != 0 or not (keys == wk).all() or not (f == wf).all():
                 print("MISMATCH place", case, rc)
                 sys.exit(1)

@@ -15,7 +15,10 @@ ap.add_argument("--variants", default="2")
 ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--nodes", type=int, default=100_000)
 ap.add_argument("--pods", type=int, default=10_000)
+ap.add_argument("--lib", default=None, help="time this libkgpu build instead of kubegpu_b200/lib/libkgpu.so (sweeps)")
 a = ap.parse_args()
+if a.lib:
+    _lib.LIB_PATH = os.path.abspath(a.lib)
 mem = None
 if a.config == "c6":
     topo, free, mem, pods = synth.gen_c6(a.nodes, a.pods)

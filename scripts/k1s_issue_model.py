@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--pods", type=int, default=10_000)
     ap.add_argument("--issue", type=float, default=0.82, help="issue utilisation (measured: 0.82)")
     ap.add_argument("--ghz", type=float, default=1.9)
+    ap.add_argument("--group", type=int, default=1, help="pods per trip of a bucket loop (KGPU_SP_GROUP)")
     ap.add_argument("--extra", type=float, default=0.15, help="pod sort + flush share on top of the loops")
     a = ap.parse_args()
     name, loops = bucket_loops(a.lib, a.kernel)
@@ -64,8 +65,8 @@ def main():
             if f < k or (k <= 1 and f < k):
                 continue
             n, al = table[(k, 8)] if k <= 1 else table[(k, f)]
-            inst += pf[f] * n / len(ks)
-            alu += pf[f] * al / len(ks)
+            inst += pf[f] * n / len(ks) / a.group
+            alu += pf[f] * al / len(ks) / a.group
     warps = (a.nodes + 31) // 32
     total = inst * warps * a.pods * (1 + a.extra)
     cycles = total / (148 * 4 * a.issue)

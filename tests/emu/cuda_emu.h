@@ -29,6 +29,14 @@ struct int4 {
     int x, y, z, w;
 };
 inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+struct alignas(8) uint2 {
+    unsigned x, y;
+};
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+struct alignas(16) uint4 {
+    unsigned x, y, z, w;
+};
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 struct dim3 {
     unsigned x = 1, y = 1, z = 1;
     dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
@@ -132,6 +140,7 @@ inline int __syncthreads_or(int pred) {
     b.bar.arrive_and_wait();
     return b.or_flag.load();
 }
+inline int __syncthreads_and(int pred) { return !__syncthreads_or(!pred); }
 inline unsigned __reduce_min_sync(unsigned, unsigned v) { return emu::warp_all(v, [](unsigned a, unsigned b) { return a < b ? a : b; }); }
 inline unsigned __reduce_max_sync(unsigned, unsigned v) { return emu::warp_all(v, [](unsigned a, unsigned b) { return a > b ? a : b; }); }
 inline unsigned __ballot_sync(unsigned, int pred) {
@@ -158,6 +167,11 @@ inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v)
     while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
     return old;
 }
+
+inline unsigned long long atomicMin_system(unsigned long long *p, unsigned long long v) { return atomicMin(p, v); }
+inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 // ---- integer intrinsics ----------------------------------------------------------------------------------
 inline int __popc(unsigned x) { return __builtin_popcount(x); }

@@ -9,6 +9,9 @@
 #include "score_pairs.cuh"
 #include "score_pairs_sparse.cuh"
 #include "place_sequential.cuh"
+#include "sparse_work.h"
+#include "peer_exchange.cuh"
+
 
 namespace {
 
@@ -63,17 +66,52 @@ void emu_score_sparse(const int32_t *topo, const int32_t *free_mask, const int32
                 [&] { kgpu::compact_nodes(topo4, free_mask, n, Ws, cpair, perm); });
     int flag = 0;
     for (int64_t p = 0; p < P; p++) flag |= pods[4 * p + 3] > 0;
-    const dim3 grid((unsigned)(order.size() / kgpu::SP_THREADS), (unsigned)std::max(1, splits));
+    dim3 grid((unsigned)(order.size() / kgpu::SP_THREADS), (unsigned)std::max(1, splits));
     const int per = per_split(P, std::max(1, splits));
     const int4 *cpair4 = reinterpret_cast<const int4 *>(cpair);
-    emu::launch(grid, dim3(kgpu::SP_THREADS), [&] {
-        kgpu::score_pairs_sparse<true, false>(cpair4, perm, free_mask, mem, order.data(), &flag, node_id_base, pods4, P, per, kPC, keys);
-    });
-    if (flag)
-        emu::launch(grid, dim3(kgpu::SP_THREADS), [&] {
-            kgpu::score_pairs_sparse<true, true>(cpair4, perm, free_mask, mem, order.data(), &flag, node_id_base, pods4, P, per, kPC, keys);
-        });
+    // splits < 0: the work list of sparse_work.h for -splits resident blocks, as kgpu.cu builds it
+    std::vector<kgpu::SparseWorkItem> items;
+    const int4 *work = nullptr;
+    if (splits < 0) {
+        std::vector<uint8_t> tile_class(order.size() / kgpu::SP_THREADS, 0);
+        for (size_t sl = 0; sl < order.size(); sl++)
+            if (order[sl] >= 0)
+                tile_class[sl / kgpu::SP_THREADS] = std::max<uint8_t>(tile_class[sl / kgpu::SP_THREADS],
+                                                                      (uint8_t)__builtin_popcount((unsigned)free_mask[order[sl]] & 0xFFu));
+        kgpu::build_sparse_work(tile_class, P, -splits, items);
+        static_assert(sizeof(kgpu::SparseWorkItem) == sizeof(int4), "work item layout");
+        work = reinterpret_cast<const int4 *>(items.data());
+        grid = dim3((unsigned)items.size(), 1);
+    }
+    bool byte_keys = true;                               // kgpu.cu: every cost < 2^16
+    for (int i = 0; i < 16; i++) byte_keys = byte_keys && W[i] <= 2340;
+#define EMU_SPARSE(MEMF, BK)                                                                                   \
+    emu::launch(grid, dim3(kgpu::SP_THREADS), [&] {                                                            \
+        kgpu::score_pairs_sparse<true, MEMF, BK>(cpair4, perm, free_mask, mem, order.data(), &flag, node_id_base, pods4, P, per, work, kPC, keys); \
+    })
+    if (byte_keys) EMU_SPARSE(false, true); else EMU_SPARSE(false, false);
+    if (flag) { if (byte_keys) EMU_SPARSE(true, true); else EMU_SPARSE(true, false); }
+#undef EMU_SPARSE
     free(topo4); free(pods4); free(mem); free(cpair); free(perm);
+}
+
+// The peer-exchange kernel with world = 1 (the rank pushes into its own result array and passes its own
+// barrier): exercises the push, the last-block ticket and the flag protocol, not the cross-GPU part.
+void emu_push_and_sync(const unsigned long long *local, int64_t P, unsigned long long *result, uint32_t *flags,
+                       uint32_t epoch, unsigned int *ticket) {
+    kgpu::PeerTable tab;
+    std::memset(&tab, 0, sizeof tab);
+    tab.results[0] = result;
+    tab.flags[0] = flags;
+    emu::launch(dim3((unsigned)((P + 255) / 256)), dim3(256), [&] { kgpu::push_and_sync(local, P, tab, 0, 1, epoch, ticket); });
+}
+
+// The host-side work-list builder alone (sparse_work.h): items as int32[.][4], returns the count.
+int64_t emu_sparse_work(const uint8_t *tile_class, int64_t tiles, int64_t P, int64_t resident, int32_t *out, int64_t cap) {
+    std::vector<kgpu::SparseWorkItem> items;
+    kgpu::build_sparse_work(std::vector<uint8_t>(tile_class, tile_class + tiles), P, resident, items);
+    for (size_t i = 0; i < items.size() && (int64_t)i < cap; i++) std::memcpy(out + 4 * i, &items[i], 16);
+    return (int64_t)items.size();
 }
 
 // Dense K1 (+ K1m) as kgpu.cu launches them.
@@ -172,11 +210,24 @@ void emu_score_pair_list(const int32_t *topo, const int32_t *free_mask, const in
     free(topo4); free(mem);
 }
 
-// K3: place_init + place_sequential; free_mask is updated in place like the device copy.
-void emu_place_batch(const int32_t *topo, int32_t *free_mask, int64_t n, int64_t node_id_base, const int32_t *pods,
-                     int64_t P, const int32_t *W, unsigned long long *keys) {
+// K3: place_init + place_sequential as kgpu_place_batch launches them (views from the batch's distinct
+// min_mem values); free_mask is updated in place like the device copy.  Returns 0, or -1 for too many views.
+int emu_place_batch(const int32_t *topo, int32_t *free_mask, const int32_t *gpu_mem /*nullable*/, int64_t n,
+                    int64_t node_id_base, const int32_t *pods, int64_t P, const int32_t *W, unsigned long long *keys) {
     std::memset(keys, 0xFF, (size_t)P * 8);
-    if (n == 0 || P == 0) return;
+    if (n == 0 || P == 0) return 0;
+    kgpu::PlaceViews views;
+    std::memset(&views, 0, sizeof views);
+    views.n = 1;
+    for (int64_t p = 0; p < P; p++) {
+        const int32_t need = pods[4 * p + 3];
+        if (need <= 0 || pods[4 * p] < 0 || pods[4 * p] > 8) continue;
+        bool seen = false;
+        for (int j = 1; j < views.n; j++) seen = seen || views.min_mem[j] == need;
+        if (seen) continue;
+        if (views.n == kgpu::PLACE_MAX_VIEWS) return -1;
+        views.min_mem[views.n++] = need;
+    }
     for (int k = 0; k <= 8; k++) {
         int c = 0;
         for (unsigned S = 0; S < 256; S++)
@@ -187,17 +238,20 @@ void emu_place_batch(const int32_t *topo, int32_t *free_mask, int64_t n, int64_t
     std::memcpy(topo4, topo, (size_t)n * 256);
     int4 *pods4 = aligned_array<int4>((size_t)P);
     std::memcpy(pods4, pods, (size_t)P * 16);
+    int32_t *mem = aligned_array<int32_t>((size_t)n * 8);
+    if (gpu_mem) std::memcpy(mem, gpu_mem, (size_t)n * 32); else std::memset(mem, 0x7F, (size_t)n * 32);
     const int64_t T = (n + kgpu::PLACE_TILE - 1) / kgpu::PLACE_TILE, Npad = T * kgpu::PLACE_TILE;
-    uint32_t *nodebest = aligned_array<uint32_t>((size_t)Npad * 9);
-    unsigned long long *tilebest = aligned_array<unsigned long long>((size_t)T * 9);
+    uint32_t *nodebest = aligned_array<uint32_t>((size_t)Npad * 9 * views.n);
+    unsigned long long *tilebest = aligned_array<unsigned long long>((size_t)T * 9 * views.n);
     const kgpu::Weights Ws = weights_of(W);
-    emu::launch(dim3((unsigned)T), dim3(kgpu::PLACE_TILE),
-                [&] { kgpu::place_init(topo4, free_mask, n, Npad, node_id_base, Ws, kPC, nodebest, tilebest, T); });
+    emu::launch(dim3((unsigned)T, (unsigned)views.n), dim3(kgpu::PLACE_TILE),
+                [&] { kgpu::place_init(topo4, free_mask, mem, n, Npad, node_id_base, Ws, kPC, views, nodebest, tilebest, T); });
     emu::launch(dim3(1), dim3(kgpu::PLACE_THREADS), [&] {
-        kgpu::place_sequential(reinterpret_cast<const int32_t *>(topo4), free_mask, n, Npad, node_id_base, pods4, P, Ws, nodebest,
-                               tilebest, T, keys);
+        kgpu::place_sequential(reinterpret_cast<const int32_t *>(topo4), free_mask, mem, n, Npad, node_id_base, pods4, P, Ws, views,
+                               nodebest, tilebest, T, keys);
     });
-    free(topo4); free(pods4); free(nodebest); free(tilebest);
+    free(topo4); free(pods4); free(mem); free(nodebest); free(tilebest);
+    return 0;
 }
 
 }  // extern "C"

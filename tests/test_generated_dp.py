@@ -54,7 +54,7 @@ def functions(path):
         lines = []
         for ln in body.splitlines():
             ln = ln.strip()
-            if ln in ("{", "}") or not ln:
+            if ln in ("{", "}") or not ln or re.match(r"^uint32_t [\w, ]+;$", ln):   # braces, bare declarations
                 continue
             ln = re.sub(r"^(const )?uint32_t ", "", ln).rstrip(";")
             ln = re.sub(r"\b(0x[0-9a-fA-F]+|\d+)u\b", r"U32(\1)", ln)

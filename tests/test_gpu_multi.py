@@ -62,3 +62,28 @@ def test_torchrun_bench_keys_equal_single_gpu(tmp_path):
     assert one["n_gpus"] == 1 and two["n_gpus"] == 2
     assert one["keys_sha256_12"] == two["keys_sha256_12"]
     assert two["config"]["nodes"] == 100_000 and two["scaling"] == "strong"
+
+
+def test_torchrun_push_exchange_keys_equal_single_gpu():
+    """The peer-memory exchange (kgpu_score_batch_exchange: push with 64-bit atomic min over NVLink + flag
+    barrier, one kernel) must give the very same keys as one GPU and as the NCCL all-gather + K2 path."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if _ndev() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+
+    def line(cmd):
+        out = subprocess.run(cmd, cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        return json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+
+    one = line([sys.executable, "bench.py", "--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--no-variants"])
+    one_push = line([sys.executable, "bench.py", "--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--no-variants", "--exchange", "push"])
+    two = line([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                "--master-port", "29534", "bench.py", "--gpus", "2", "--steps", "5", "--warmup", "3", "--exchange", "push"])
+    assert one["keys_sha256_12"] == one_push["keys_sha256_12"] == two["keys_sha256_12"]
+    assert "push" in two["config"]["parallelism"]

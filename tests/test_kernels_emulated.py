@@ -113,19 +113,114 @@ def test_emulated_pair_list(emu, oracle_b):
         assert int(out[i]) == got, i
 
 
+def _place(emu, topo, free, pods, W, mem=None, base=0):
+    emu.emu_place_batch.restype = ctypes.c_int
+    f = np.ascontiguousarray(free, dtype=np.int32).copy()
+    pods = np.ascontiguousarray(pods, dtype=np.int32)
+    keys = np.empty(len(pods), dtype=np.uint64)
+    memp = None if mem is None else _p(np.ascontiguousarray(mem, dtype=np.int32))
+    rc = emu.emu_place_batch(_p(np.ascontiguousarray(topo, dtype=np.int32)), _p(f), memp, ctypes.c_int64(len(f)),
+                             ctypes.c_int64(base), _p(pods), ctypes.c_int64(len(pods)), _p(W), _p(keys, ctypes.c_uint64))
+    return rc, keys, f
+
+
 def test_emulated_sequential_placement(emu, oracle_b):
     """K3 (place_init + the persistent place_sequential block) against the stateful oracle."""
-    emu.emu_place_batch.restype = None
     W = np.ascontiguousarray(oracle_b.DEFAULT_WEIGHTS, dtype=np.int32)
     topo, free, pods = synth.gen_c4(N=300, P=120)
     pods[9, 0] = 0
-    f_emu = free.copy()
-    keys = np.empty(len(pods), dtype=np.uint64)
-    emu.emu_place_batch(_p(topo), _p(f_emu), ctypes.c_int64(len(free)), ctypes.c_int64(5), _p(pods), ctypes.c_int64(len(pods)),
-                        _p(W), _p(keys, ctypes.c_uint64))
+    pods[10, 0] = 12
+    rc, keys, f_emu = _place(emu, topo, free, pods, W, base=5)
     want_keys, want_free = oracle_b.place_batch(topo, free.copy(), pods, W, node_id_base=5)
-    assert (keys == want_keys).all()
-    assert (f_emu == want_free).all()
+    assert rc == 0 and (keys == want_keys).all() and (f_emu == want_free).all()
+
+
+def test_emulated_sequential_placement_many_tiles(emu, oracle_b):
+    """More than one supertile (33+ tiles) and a cluster that fills up: later pods find nothing."""
+    W = np.ascontiguousarray(oracle_b.DEFAULT_WEIGHTS, dtype=np.int32)
+    topo, free, _ = synth.gen_c2(N=128 * 34 + 17, P=0)
+    free[:] = 0
+    free[[5, 4300, 4368]] = [0x0F, 0xF0, 0xFF]           # three nodes with room, in different supertiles
+    pods = synth.make_pods(np.array([4, 4, 2, 8, 4, 2, 1, 1, 1, 1, 1], dtype=np.int32))
+    rc, keys, f_emu = _place(emu, topo, free, pods, W)
+    want_keys, want_free = oracle_b.place_batch(topo, free.copy(), pods, W)
+    assert rc == 0 and (keys == want_keys).all() and (f_emu == want_free).all()
+    assert (keys == np.uint64(0xFFFFFFFFFFFFFFFF)).any() and f_emu.sum() == 0
+
+
+def test_emulated_sequential_placement_memory_aware(emu, oracle_b):
+    """Pods with min_mem: one table set ("view") per distinct requirement; 4 requirements + the plain view."""
+    W = np.ascontiguousarray(oracle_b.DEFAULT_WEIGHTS, dtype=np.int32)
+    topo, free, mem, pods = synth.gen_c6(N=300, P=150)
+    assert len(set(pods[:, 3].tolist())) == 5
+    rc, keys, f_emu = _place(emu, topo, free, pods, W, mem=mem, base=9)
+    want_keys, want_free = oracle_b.place_batch(topo, free.copy(), pods, W, node_id_base=9, mem=mem)
+    assert rc == 0 and (keys == want_keys).all() and (f_emu == want_free).all()
+    plain_keys, _ = oracle_b.place_batch(topo, free.copy(), np.hstack([pods[:, :3], np.zeros((150, 1), np.int32)]), W, node_id_base=9)
+    assert (plain_keys != want_keys).any()
+    # without uploaded GPU memory the requirement excludes nothing (kgpu.h): same as the plain batch
+    rc, keys, _ = _place(emu, topo, free, pods, W, mem=None, base=9)
+    assert rc == 0 and (keys == plain_keys).all()
+    # eight distinct requirements are one too many
+    pods[:8, 3] = np.arange(1, 9) * 1000
+    assert _place(emu, topo, free, pods, W, mem=mem)[0] == -1
+
+
+@pytest.mark.parametrize("wmax", [2340, 2341])
+def test_emulated_sparse_warp_key_layouts(emu, oracle_b, wmax):
+    """2340 is the largest weight served by the byte-aligned warp key (cost < 2^16), 2341 the first that
+    takes the general layout; both with ragged free masks so warps mix lanes that can and cannot serve k."""
+    topo, free, pods = synth.gen_c4(N=400, P=90, seed=77)
+    W = np.array([wmax - i for i in range(16)], dtype=np.int32)
+    want = oracle_b.score_batch(topo, free, pods, W, node_id_base=3)
+    assert (_run(emu.emu_score_sparse, topo, free, pods, W, base=3, splits=3) == want).all()
+
+
+def test_emulated_sparse_work_list(emu, oracle_b):
+    """K1s driven by the work list (per-tile pod ranges of about equal work, heaviest first) instead of the
+    plain (tiles x splits) grid: same keys; every (tile, pod) covered exactly once."""
+    W = oracle_b.DEFAULT_WEIGHTS
+    topo, free, mem, pods = synth.gen_c6(N=900, P=700)
+    pods[5, 0], pods[6, 0] = 0, 9
+    want = oracle_b.score_batch(topo, free, pods, W, node_id_base=4, mem=mem)
+    for resident in (1, 16, 1184):
+        assert (_run(emu.emu_score_sparse, topo, free, pods, W, mem=mem, base=4, splits=-resident) == want).all(), resident
+
+
+@pytest.mark.parametrize("P", [1, 31, 32, 1000, 10_000])
+@pytest.mark.parametrize("resident", [1, 1184])
+def test_sparse_work_list_partitions_every_tile(emu, P, resident):
+    emu.emu_sparse_work.restype = ctypes.c_int64
+    rng = np.random.default_rng(P + resident)
+    tile_class = rng.integers(0, 9, size=57).astype(np.uint8)
+    out = np.zeros((200_000, 4), dtype=np.int32)
+    n = emu.emu_sparse_work(_p(tile_class, ctypes.c_uint8), ctypes.c_int64(57), ctypes.c_int64(P), ctypes.c_int64(resident),
+                            _p(out), ctypes.c_int64(len(out)))
+    items = out[:n]
+    assert 57 <= n <= len(out)
+    assert (np.diff(items[:, 3]) <= 0).all()                     # heaviest first
+    for t in range(57):
+        mine = items[items[:, 0] == t]
+        mine = mine[np.argsort(mine[:, 1])]
+        assert mine[0, 1] == 0 and mine[-1, 2] == P and (mine[1:, 1] == mine[:-1, 2]).all()   # a partition of [0, P)
+        assert (mine[:, 1] % 32 == 0).all() and (mine[:, 2] > mine[:, 1]).all()
+
+
+def test_emulated_sparse_single_class_tiles(emu, oracle_b):
+    """Tiles whose slots are one class in increasing node id take the flush's direct 32-bit min over the
+    warp keys (warp index in the key); C2's few shapes make cost ties across warps and nodes the rule."""
+    W = oracle_b.DEFAULT_WEIGHTS
+    topo, free, pods = synth.gen_c2(N=300, P=64)
+    free[:] = 0xFF
+    free[[7, 100, 299]] = [0x0F, 0x00, 0x3C]              # stragglers form small mixed tail tiles
+    pods = synth.make_pods(np.array([1, 2, 3, 4, 5, 6, 7, 8, 0] * 7, dtype=np.int32))
+    want = oracle_b.score_batch(topo, free, pods, W, node_id_base=40)
+    assert (_run(emu.emu_score_sparse, topo, free, pods, W, base=40, splits=2) == want).all()
+    # the same with every pod's cheapest nodes taken away one by one: winners move across warps and tiles
+    for taken in (0, 1, 2, 31, 32, 127, 128, 129):
+        free[taken] = 0
+        want = oracle_b.score_batch(topo, free, pods, W, node_id_base=40)
+        assert (_run(emu.emu_score_sparse, topo, free, pods, W, base=40) == want).all(), taken
 
 
 @pytest.mark.parametrize("kernel", ["sparse", "dense"])
@@ -141,3 +236,24 @@ def test_emulated_ragged_sizes(emu, oracle_b, kernel):
     none_free = np.zeros(5, dtype=np.int32)
     got = _run(fn, topo[:5], none_free, pods[:16], W)
     assert (got == oracle_b.score_batch(topo[:5], none_free, pods[:16], W)).all()
+
+
+def test_emulated_push_and_sync_single_rank(emu):
+    """peer_exchange.cuh with world = 1: pushes land (NO_FIT is not sent), the last block resets the ticket
+    and publishes the epoch; a second epoch into the same array keeps the minimum."""
+    emu.emu_push_and_sync.restype = None
+    P = 700
+    rng = np.random.default_rng(3)
+    local = rng.integers(1, 2**60, size=P, dtype=np.uint64)
+    local[::7] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    result = np.full(P, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)
+    flags = np.zeros(16, dtype=np.uint32)
+    ticket = np.zeros(1, dtype=np.uint32)
+    u64, u32 = ctypes.c_uint64, ctypes.c_uint32
+    emu.emu_push_and_sync(_p(local, u64), ctypes.c_int64(P), _p(result, u64), _p(flags, u32), 1, _p(ticket, u32))
+    assert (result == local).all() and flags[0] == 1 and ticket[0] == 0
+    lower = local.copy()
+    lower[5:50] = np.uint64(7)
+    lower[::7] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    emu.emu_push_and_sync(_p(lower, u64), ctypes.c_int64(P), _p(result, u64), _p(flags, u32), 2, _p(ticket, u32))
+    assert (result == np.minimum(local, lower)).all() and flags[0] == 2 and ticket[0] == 0

@@ -102,8 +102,10 @@ def test_gpu_memory_aware_parity(oracle_b, variant):
         bad[3, 3] = -1
         with pytest.raises(KgpuError):
             s.upload_gpu_memory(bad)
+        many = pods[:16].copy()
+        many[:8, 0], many[:8, 3] = 1, np.arange(1, 9) * 1000
         with pytest.raises(KgpuError):
-            s.place_batch(pods)            # sequential path: min_mem not supported yet, must say so
+            s.place_batch(many)            # sequential path: at most 7 distinct requirements per batch
 
 
 @pytest.mark.gpu

@@ -40,6 +40,10 @@ def _worker(rank, world, port, result_path):
     local = oracle_b.score_batch(topo, free, pods, node_id_base=lo)
     gathered = all_gather_keys(torch.from_numpy(local.view(np.int64)))
     final = oracle_b.reduce_shards(gathered.numpy().view(np.uint64))
+    # the one-collective alternative must agree (sign-flipped signed MIN == unsigned min, NO_FIT included)
+    from kubegpu_b200.distributed import all_reduce_min_keys
+    reduced = all_reduce_min_keys(torch.from_numpy(local.copy().view(np.int64))).numpy().view(np.uint64)
+    assert (reduced == final).all()
     if rank == 0:
         np.save(result_path, final)
     dist.barrier()

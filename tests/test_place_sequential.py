@@ -83,3 +83,27 @@ def test_place_batch_full_c2(oracle_b):
         got = s.place_batch(pods)
         assert (got == want_keys).all() and (s.get_free_masks() == want_free).all()
         print("K3 place_batch: %.3f ms for %d pods -> %.0f placements/s" % (s.last_kernel_ms, len(pods), len(pods) / s.last_kernel_ms * 1e3))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,P", [(300, 150), (20_000, 3000), (128 * 40 + 3, 2000)])
+def test_place_batch_memory_aware(oracle_b, N, P):
+    """Pods with min_mem placed sequentially: one table set per distinct requirement (4 + the plain one)."""
+    from kubegpu_b200.scorer import Scorer
+    topo, free, mem, pods = synth.gen_c6(N=N, P=P)
+    want_keys, want_free = oracle_b.place_batch(topo, free, pods, node_id_base=11, mem=mem)
+    plain = pods.copy()
+    plain[:, 3] = 0
+    plain_keys, plain_free = oracle_b.place_batch(topo, free, plain, node_id_base=11)
+    assert (plain_keys != want_keys).any()
+    with Scorer((0,)) as s:
+        s.upload_nodes(topo, free, node_id_base=11)
+        # no GPU memory uploaded: the requirement excludes nothing
+        assert (s.place_batch(pods) == plain_keys).all() and (s.get_free_masks() == plain_free).all()
+        s.upload_nodes(topo, free, node_id_base=11)
+        s.upload_gpu_memory(mem)
+        assert (s.place_batch(pods) == want_keys).all() and (s.get_free_masks() == want_free).all()
+        # next cycle continues on the reduced cluster, snapshot scoring sees it too
+        more_keys, more_free = oracle_b.place_batch(topo, want_free, pods[:100], node_id_base=11, mem=mem)
+        assert (s.place_batch(pods[:100]) == more_keys).all() and (s.get_free_masks() == more_free).all()
+        assert (s.score_batch(pods[:64]) == oracle_b.score_batch(topo, more_free, pods[:64], node_id_base=11, mem=mem)).all()
