@@ -216,3 +216,48 @@ def test_ten_million_nodes_sweep_point(scorer, oracle_b):
     k8 = keys[pods[:, 0] == 8]
     assert len(k8) and all(((int(k) >> 8) & 0xFFFFFFFF) == N - 1 and (int(k) >> 40) == 0 for k in k8)
     scorer.upload_nodes(topo[:1], free[:1])          # release the 2.5 GB before the next test
+
+
+def test_agree_set_on_gpu_against_reference_greedy(golden_dir):
+    """the chain GPU -> Oracle A -> reference goldens on hardware.  All 223 two-level
+    8-GPU shapes x k = 1..8 (1784 cases) go through kgpu_score_pairs; the GPU's optimal cost is compared
+    with the cost of the subset the reference's greedy tree fill picks (Oracle A, which reproduces
+    gpu_test.go:61-109): equal on 1759 cases, and the divergent set is exactly the committed 25
+    (tests/golden/agree_set.json), every one a case where the GPU is cheaper."""
+    import json
+    import sys
+    sys.path.insert(0, golden_dir)
+    import make_golden
+    from oracle import oracle_a as oa
+    from oracle import oracle_b as ob
+    from kubegpu_b200.scorer import Scorer
+    W = ob.DEFAULT_WEIGHTS
+    shapes = make_golden.two_level_shapes(8)
+    assert len(shapes) == 223
+    mats, trees = [], []
+    for shp in shapes:
+        tree = oa.add_to_node(None, oa.shape_to_resources([list(g) for g in shp]), "gpugrp", "cards", 1)
+        trees.append(tree)
+        mats.append(np.asarray(oa.tree_to_matrix(tree), dtype=np.int32).reshape(64))
+    topo = np.stack(mats)
+    free = np.full(len(shapes), 0xFF, dtype=np.int32)
+    idx = np.repeat(np.arange(len(shapes), dtype=np.int64), 8)
+    ks = np.tile(np.arange(1, 9, dtype=np.int32), len(shapes))
+    with Scorer((0,)) as s:
+        s.upload_nodes(topo, free)
+        got = s.score_pairs(idx, ks)
+    divergent = []
+    for i, k, nk in zip(idx, ks, got):
+        assert nk != 0xFFFFFFFF                       # all 8 GPUs are free: every k fits
+        greedy = oa.greedy_fill_mask(trees[i], int(k))
+        M = mats[i]
+        gcost = sum(int(W[M[a * 8 + b]]) for a in range(8) for b in range(a + 1, 8) if (greedy >> a) & 1 and (greedy >> b) & 1)
+        gpu_cost = int(nk) >> 8
+        assert gpu_cost <= gcost                      # the subset search is never worse than the greedy fill
+        if gpu_cost != gcost:
+            divergent.append({"shape": [list(g) for g in shapes[i]], "k": int(k), "greedy_cost": gcost, "optimal_cost": gpu_cost})
+    with open(os.path.join(golden_dir, "agree_set.json")) as f:
+        committed = json.load(f)
+    assert len(idx) == committed["cases"] == 1784
+    assert len(idx) - len(divergent) == committed["agree"] == 1759
+    assert divergent == [{k: d[k] for k in ("shape", "k", "greedy_cost", "optimal_cost")} for d in committed["divergent"]]
