@@ -117,6 +117,10 @@ int kgpu_update_gpu_memory(kgpu_t *h, int64_t idx, const int32_t mem_mib[8]);
 /* Overwrite one node (AddNode on an existing name / usage update). */
 int kgpu_update_node(kgpu_t *h, int64_t idx, const int32_t topo[64], int32_t free_mask);
 int kgpu_set_free_mask(kgpu_t *h, int64_t idx, int32_t free_mask);
+/* The same for n nodes in one call (a scheduling cycle's TakePodResources / ReturnPodResources,
+ * gpu_scheduler.go:57-63): one host-to-device copy and one kernel that stores the masks and refreshes the
+ * scorer's cached records of exactly those nodes.  A node listed twice gets its LAST mask. */
+int kgpu_set_free_masks(kgpu_t *h, const int64_t *idx, const int32_t *free_mask, int64_t n);
 /* RemoveNode: the slot stays, its GPUs become unschedulable (free_mask = 0). */
 int kgpu_remove_node(kgpu_t *h, int64_t idx);
 int64_t kgpu_num_nodes(kgpu_t *h);
@@ -147,6 +151,17 @@ int kgpu_score_batch_device_ex(kgpu_t *h, const int32_t *d_pods, int64_t P, uint
 int kgpu_score_pairs(kgpu_t *h, const int64_t *node_idx, const int32_t *k, const int32_t *min_mem_mib, int64_t n,
                      uint32_t *out_node_keys);
 
+/* The (node, k) fit table: for every node and k = 0..8 the (cost << 8) | gpu_mask of its cheapest k-subset of
+ * free GPUs (UINT32_MAX: does not fit), computed by one launch and kept as a host copy inside the handle.
+ * kgpu_fit_lookup reads that copy -- no launch, no copy: this is what serves PodFitsDevice, which the core calls
+ * once per (node, pod) pair (gpu_scheduler.go:34-44).  The table is built on first use and kept current by
+ * kgpu_update_node / kgpu_set_free_mask(s) (they refresh the rows of the nodes they touch); kgpu_upload_nodes,
+ * kgpu_set_weights and kgpu_place_batch invalidate it (rebuilt on the next lookup).  kgpu_build_fit_table
+ * forces the build (e.g. at the start of a scheduling cycle).  kgpu_score_pairs uses the same table for pairs
+ * without a memory requirement. */
+int kgpu_build_fit_table(kgpu_t *h);
+int kgpu_fit_lookup(kgpu_t *h, int64_t node_idx, int32_t k, uint32_t *out_node_key);
+
 /* Stateful sequential placement (what TakePodResources would make of a scheduling cycle;
  * a no-op in the reference, gpu_scheduler.go:57-63).  Pods are placed IN ORDER; each one gets
  * the best (cost, node, mask) under the free masks left by the pods before it and then takes
@@ -154,6 +169,11 @@ int kgpu_score_pairs(kgpu_t *h, const int64_t *node_idx, const int32_t *k, const
  * in kgpu_score_batch; one batch may carry at most 7 distinct positive min_mem_mib values
  * (KGPU_ERR_INVALID otherwise).  Host buffers, synchronous, single-device handles only. */
 int kgpu_place_batch(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_keys);
+/* Same with flags.  KGPU_PLACE_DRY_RUN: the pods are placed in order on a scratch copy of the free masks, so
+ * the keys are conflict-free PROPOSALS for the whole batch (no two pods share a GPU) while the handle's state
+ * is untouched; commit the accepted ones with kgpu_set_free_masks (TakePodResources). */
+#define KGPU_PLACE_DRY_RUN 1
+int kgpu_place_batch_ex(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_keys, int flags);
 /* Copy the current free masks (n = kgpu_num_nodes entries) back to the host. */
 int kgpu_get_free_masks(kgpu_t *h, int32_t *out_free_mask, int64_t n);
 
@@ -180,6 +200,9 @@ int kgpu_score_batch_exchange(kgpu_t *h, const int32_t *d_pods, int64_t P, const
 
 /* Number of CUDA kernels this handle has launched so far (bench bookkeeping). */
 int64_t kgpu_kernel_launches(kgpu_t *h);
+/* Wall-clock duration (ms) of the most recent kgpu_upload_nodes: host-to-device copies, the device-side
+ * value-domain check, the K1s order (counting sort by free-GPU count) and the compacted records. */
+double kgpu_last_upload_ms(kgpu_t *h);
 /* Device duration (ms, CUDA events on the launching stream) of the K1 launch(es)
  * of the most recent kgpu_score_batch call. */
 double kgpu_last_kernel_ms(kgpu_t *h);

@@ -12,8 +12,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libkgpu.so")
 SYMBOLS = [
     "kgpu_version", "kgpu_create", "kgpu_destroy", "kgpu_last_error", "kgpu_set_weights",
     "kgpu_get_weights", "kgpu_set_variant", "kgpu_upload_nodes", "kgpu_update_node",
-    "kgpu_set_free_mask", "kgpu_remove_node", "kgpu_upload_gpu_memory", "kgpu_update_gpu_memory", "kgpu_num_nodes", "kgpu_score_batch",
-    "kgpu_score_batch_device", "kgpu_score_batch_device_ex", "kgpu_score_pairs", "kgpu_place_batch", "kgpu_get_free_masks", "kgpu_reduce_shards_device", "kgpu_exchange_init", "kgpu_exchange_connect", "kgpu_score_batch_exchange", "kgpu_kernel_launches",
+    "kgpu_set_free_mask", "kgpu_set_free_masks", "kgpu_remove_node", "kgpu_build_fit_table", "kgpu_fit_lookup", "kgpu_last_upload_ms", "kgpu_upload_gpu_memory", "kgpu_update_gpu_memory", "kgpu_num_nodes", "kgpu_score_batch",
+    "kgpu_score_batch_device", "kgpu_score_batch_device_ex", "kgpu_score_pairs", "kgpu_place_batch", "kgpu_place_batch_ex", "kgpu_get_free_masks", "kgpu_reduce_shards_device", "kgpu_exchange_init", "kgpu_exchange_connect", "kgpu_score_batch_exchange", "kgpu_kernel_launches",
     "kgpu_last_kernel_ms",
 ]
 
@@ -23,6 +23,7 @@ IPC_HANDLE_BYTES = 64
 VARIANT_AUTO, VARIANT_WARP_PER_PAIR, VARIANT_LANE_PER_NODE, VARIANT_MEMO_BY_K, VARIANT_TILE_MEMO = 0, 1, 2, 3, 4
 VARIANT_SPARSE = 5
 BATCH_NO_MIN_MEM = 1
+PLACE_DRY_RUN = 1
 
 _lib = None
 
@@ -63,6 +64,14 @@ def load() -> ctypes.CDLL:
     L.kgpu_update_node.argtypes = [vp, i64, i32p, ctypes.c_int32]
     L.kgpu_set_free_mask.restype = ci
     L.kgpu_set_free_mask.argtypes = [vp, i64, ctypes.c_int32]
+    L.kgpu_set_free_masks.restype = ci
+    L.kgpu_set_free_masks.argtypes = [vp, ctypes.POINTER(i64), i32p, i64]
+    L.kgpu_build_fit_table.restype = ci
+    L.kgpu_build_fit_table.argtypes = [vp]
+    L.kgpu_fit_lookup.restype = ci
+    L.kgpu_fit_lookup.argtypes = [vp, i64, ctypes.c_int32, ctypes.POINTER(ctypes.c_uint32)]
+    L.kgpu_last_upload_ms.restype = ctypes.c_double
+    L.kgpu_last_upload_ms.argtypes = [vp]
     L.kgpu_remove_node.restype = ci
     L.kgpu_remove_node.argtypes = [vp, i64]
     L.kgpu_num_nodes.restype = i64
@@ -77,6 +86,8 @@ def load() -> ctypes.CDLL:
     L.kgpu_score_pairs.argtypes = [vp, ctypes.POINTER(i64), i32p, i32p, i64, ctypes.POINTER(ctypes.c_uint32)]
     L.kgpu_place_batch.restype = ci
     L.kgpu_place_batch.argtypes = [vp, vp, i64, vp]
+    L.kgpu_place_batch_ex.restype = ci
+    L.kgpu_place_batch_ex.argtypes = [vp, vp, i64, vp, ci]
     L.kgpu_get_free_masks.restype = ci
     L.kgpu_get_free_masks.argtypes = [vp, i32p, i64]
     L.kgpu_reduce_shards_device.restype = ci

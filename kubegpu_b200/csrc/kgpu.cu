@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -19,6 +20,7 @@
 #include "peer_exchange.cuh"
 #include "score_pairs.cuh"
 #include "score_pairs_sparse.cuh"
+#include "node_state.cuh"
 
 namespace {
 
@@ -42,11 +44,30 @@ struct kgpu_shard {
     int32_t *d_free = nullptr;       // [n]
     int32_t *d_mem = nullptr;        // [n][8] MiB per GPU (0x7F7F7F7F = unconstrained until uploaded)
     int *d_flag = nullptr;           // "batch has memory-constrained pods"
-    uint32_t *d_cpair = nullptr;     // K1s: [n][28] compacted scaled pair costs (see compact_nodes)
-    uint32_t *d_perm = nullptr;      // K1s: [n] position -> GPU index
-    bool compact_dirty = true;       // topology / free masks / weights changed since the cache was built
+    int4 *d_rec = nullptr;           // K1s: [tiles][7][SP_THREADS] compacted scaled pair costs, slot order (compact_nodes)
+    uint32_t *d_meta = nullptr;      // K1s: [n_slots] position -> GPU index (3-bit fields) | free count << 24
+    bool compact_dirty = true;       // topology / weights changed for every node since the cache was built
+    bool order_dirty = true;         // the order (slots by free count) must be rebuilt before the next K1s launch
+    int64_t stale_nodes = 0;         // nodes whose free count changed since the order was built (re-sort when many)
     int32_t *d_order = nullptr;      // K1s: slot -> node index, grouped by popcount(free), -1 = padding
-    int64_t n_slots = 0, order_cap = 0;
+    int32_t *d_slot_of = nullptr;    // K1s: node index -> slot
+    int32_t *d_ord_cnt = nullptr, *d_ord_off = nullptr;   // counting sort scratch [9][blocks]
+    long long *d_ord_meta = nullptr; // class counts [9], n_slots
+    int64_t ord_nb_cap = 0;
+    unsigned long long *d_bad = nullptr;   // validate_topo_dev: first out-of-domain element
+    int32_t *d_upd = nullptr;        // state-change scratch: [cap] node indices | [cap] masks
+    int64_t upd_cap = 0;
+    uint32_t *d_fit = nullptr;       // (node, k) fit table on the device [9][n] and, patches, [9][upd]
+    uint32_t *h_fit = nullptr;       // pinned host copy [9][n]: kgpu_fit_lookup / kgpu_score_pairs read it
+    int64_t fit_cap = 0;
+    bool fit_valid = false;
+    int4 *d_query = nullptr;         // kgpu_score_pairs with min_mem: {node lo, node hi, k, min_mem}
+    uint32_t *d_qout = nullptr;
+    int64_t query_cap = 0;
+    int32_t *d_free_scratch = nullptr;   // kgpu_place_batch_ex(KGPU_PLACE_DRY_RUN): the masks the dry run consumes
+    int64_t free_scratch_cap = 0;
+    int64_t class_count[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t n_slots = 0, slot_cap = 0;
     int64_t n = 0, cap = 0;
     int64_t node_id_base = 0;
     int32_t *d_pods = nullptr;       // [pcap][4]
@@ -73,6 +94,7 @@ struct kgpu_ctx {
     int64_t launches = 0;
     double last_kernel_ms = 0.0;
     bool subsets_uploaded = false;
+    double last_upload_ms = 0.0;
     kgpu::MultiDevice *multi = nullptr;   // NCCL communicator set, ndev > 1 only
     // peer-memory key exchange (kgpu_exchange_*): one allocation per rank, mapped by every peer:
     //   results[2][max_pods] uint64 | flags[PEER_MAX_WORLD] uint32 | ticket uint32 ;  local[] is private
@@ -142,6 +164,161 @@ int ensure_pod_capacity(kgpu_ctx *h, kgpu_shard &s, int64_t P) {
     return KGPU_OK;
 }
 
+// (Re)build the K1s order of shard s on the device: stable counting sort of the node indices by free-GPU
+// count (node_state.cuh).  One 80-byte read-back tells the host the class sizes (grid size, work list).
+int build_order(kgpu_ctx *h, kgpu_shard &s) {
+    KGPU_CUDA(h, cudaSetDevice(s.dev));
+    const int64_t need_slots = s.n + 9 * 32 + kgpu::SP_THREADS;
+    if (need_slots > s.slot_cap) {
+        if (s.d_order) cudaFree(s.d_order);
+        if (s.d_rec) cudaFree(s.d_rec);
+        if (s.d_meta) cudaFree(s.d_meta);
+        s.d_order = nullptr; s.d_rec = nullptr; s.d_meta = nullptr; s.slot_cap = 0;
+        const int64_t cap = (need_slots + kgpu::SP_THREADS - 1) / kgpu::SP_THREADS * kgpu::SP_THREADS;
+        KGPU_CUDA(h, cudaMalloc(&s.d_order, (size_t)cap * 4));
+        KGPU_CUDA(h, cudaMalloc(&s.d_meta, (size_t)cap * 4));
+        KGPU_CUDA(h, cudaMalloc(&s.d_rec, (size_t)cap * 112));
+        s.slot_cap = cap;
+    }
+    const int nb = (int)((s.n + kgpu::ORD_BLOCK - 1) / kgpu::ORD_BLOCK);
+    if (nb > s.ord_nb_cap) {
+        if (s.d_ord_cnt) cudaFree(s.d_ord_cnt);
+        if (s.d_ord_off) cudaFree(s.d_ord_off);
+        s.d_ord_cnt = nullptr; s.d_ord_off = nullptr; s.ord_nb_cap = 0;
+        KGPU_CUDA(h, cudaMalloc(&s.d_ord_cnt, (size_t)nb * 9 * 4));
+        KGPU_CUDA(h, cudaMalloc(&s.d_ord_off, (size_t)nb * 9 * 4));
+        s.ord_nb_cap = nb;
+    }
+    long long meta[kgpu::ORD_META] = {0};
+    if (s.n > 0) {
+        KGPU_CUDA(h, cudaMemsetAsync(s.d_order, 0xFF, (size_t)s.slot_cap * 4, s.stream));
+        kgpu::order_count<<<nb, kgpu::ORD_BLOCK, 0, s.stream>>>(s.d_free, s.n, s.d_ord_cnt, nb);
+        kgpu::order_scan<<<1, kgpu::ORD_BLOCK, 0, s.stream>>>(s.d_ord_cnt, nb, s.d_ord_off, s.d_ord_meta, kgpu::SP_THREADS);
+        kgpu::order_scatter<<<nb, kgpu::ORD_BLOCK, 0, s.stream>>>(s.d_free, s.n, s.d_ord_off, nb, s.d_order, s.d_slot_of);
+        h->launches += 3;
+        KGPU_CUDA(h, cudaGetLastError());
+        KGPU_CUDA(h, cudaMemcpyAsync(meta, s.d_ord_meta, sizeof meta, cudaMemcpyDeviceToHost, s.stream));
+        KGPU_CUDA(h, cudaStreamSynchronize(s.stream));
+    }
+    for (int c = 0; c < 9; c++) s.class_count[c] = meta[c];
+    s.n_slots = meta[9];
+    // max free count per tile, from the class layout: class c's nodes sit in [start, start + count)
+    s.tile_class.assign((size_t)(s.n_slots / kgpu::SP_THREADS), 0);
+    int64_t start = 0;
+    for (int c = 8; c >= 0; c--) {
+        const int64_t cnt = s.class_count[c];
+        if (cnt > 0)
+            for (int64_t t = start / kgpu::SP_THREADS; t <= (start + cnt - 1) / kgpu::SP_THREADS; t++)
+                s.tile_class[(size_t)t] = std::max<uint8_t>(s.tile_class[(size_t)t], (uint8_t)c);
+        start += (cnt + 31) / 32 * 32;
+    }
+    s.work_P = -1;
+    s.order_dirty = false;
+    s.stale_nodes = 0;
+    s.compact_dirty = true;            // records are stored in slot order
+    return KGPU_OK;
+}
+
+// Bring the K1s node cache of shard s up to date (order, compacted records); everything runs on s.stream and
+// has completed when this returns, so a following launch on any stream sees it.
+int ensure_node_cache(kgpu_ctx *h, kgpu_shard &s) {
+    if (!s.order_dirty && s.stale_nodes * 8 > s.n) s.order_dirty = true;     // many free counts changed: re-sort
+    if (!s.order_dirty && !s.compact_dirty) return KGPU_OK;
+    if (s.order_dirty) {
+        const int rc = build_order(h, s);
+        if (rc != KGPU_OK) return rc;
+    }
+    KGPU_CUDA(h, cudaSetDevice(s.dev));
+    if (s.compact_dirty && s.n_slots > 0) {
+        kgpu::Weights W;
+        memcpy(W.w, h->W, sizeof W.w);
+        kgpu::compact_nodes<<<(unsigned)(s.n_slots / kgpu::SP_THREADS), kgpu::SP_THREADS, 0, s.stream>>>(
+            reinterpret_cast<const int4 *>(s.d_topo), s.d_free, s.n_slots, W, s.d_order, s.d_slot_of, s.d_rec, s.d_meta);
+        h->launches++;
+        KGPU_CUDA(h, cudaGetLastError());
+    }
+    s.compact_dirty = false;
+    KGPU_CUDA(h, cudaStreamSynchronize(s.stream));
+    return KGPU_OK;
+}
+
+int ensure_upd_capacity(kgpu_ctx *h, kgpu_shard &s, int64_t m) {
+    if (m <= s.upd_cap) return KGPU_OK;
+    if (s.d_upd) cudaFree(s.d_upd);
+    s.d_upd = nullptr; s.upd_cap = 0;
+    const int64_t cap = std::max<int64_t>(256, m + m / 2);
+    KGPU_CUDA(h, cudaMalloc(&s.d_upd, (size_t)cap * 8));
+    s.upd_cap = cap;
+    return KGPU_OK;
+}
+
+// (node, k) fit table of shard s: fit_nodes over every node, one copy to the pinned host array.
+int build_fit_table(kgpu_ctx *h, kgpu_shard &s) {
+    KGPU_CUDA(h, cudaSetDevice(s.dev));
+    if (s.n > s.fit_cap) {
+        if (s.d_fit) cudaFree(s.d_fit);
+        if (s.h_fit) cudaFreeHost(s.h_fit);
+        s.d_fit = nullptr; s.h_fit = nullptr; s.fit_cap = 0;
+        KGPU_CUDA(h, cudaMalloc(&s.d_fit, (size_t)s.n * 36));
+        KGPU_CUDA(h, cudaMallocHost(&s.h_fit, (size_t)s.n * 36));
+        s.fit_cap = s.n;
+    }
+    if (s.n > 0) {
+        kgpu::Weights W;
+        memcpy(W.w, h->W, sizeof W.w);
+        kgpu::fit_nodes<<<(unsigned)((s.n + 127) / 128), 128, 0, s.stream>>>(reinterpret_cast<const int4 *>(s.d_topo), s.d_free,
+                                                                          nullptr, s.n, W, PC, s.d_fit);
+        h->launches++;
+        KGPU_CUDA(h, cudaGetLastError());
+        KGPU_CUDA(h, cudaMemcpyAsync(s.h_fit, s.d_fit, (size_t)s.n * 36, cudaMemcpyDeviceToHost, s.stream));
+        KGPU_CUDA(h, cudaStreamSynchronize(s.stream));
+    }
+    s.fit_valid = true;
+    return KGPU_OK;
+}
+
+// State change of m nodes of shard s (local indices idx, already distinct): masks != nullptr scatters the new
+// free masks; either way the compacted records of exactly those nodes are refreshed, and the fit table's rows
+// if it is valid.  One H2D copy, one or two kernels, one small D2H copy (fit rows), synchronous.
+int apply_node_updates(kgpu_ctx *h, kgpu_shard &s, const int32_t *idx, const int32_t *masks, int64_t m) {
+    if (m <= 0) return KGPU_OK;
+    KGPU_CUDA(h, cudaSetDevice(s.dev));
+    int rc = ensure_upd_capacity(h, s, m);
+    if (rc != KGPU_OK) return rc;
+    KGPU_CUDA(h, cudaMemcpyAsync(s.d_upd, idx, (size_t)m * 4, cudaMemcpyHostToDevice, s.stream));
+    if (masks) KGPU_CUDA(h, cudaMemcpyAsync(s.d_upd + s.upd_cap, masks, (size_t)m * 4, cudaMemcpyHostToDevice, s.stream));
+    kgpu::Weights W;
+    memcpy(W.w, h->W, sizeof W.w);
+    const int4 *topo4 = reinterpret_cast<const int4 *>(s.d_topo);
+    const bool cache_live = !s.order_dirty && !s.compact_dirty;
+    if (cache_live) {
+        kgpu::compact_nodes<<<(unsigned)((m + kgpu::SP_THREADS - 1) / kgpu::SP_THREADS), kgpu::SP_THREADS, 0, s.stream>>>(
+            topo4, s.d_free, m, W, s.d_order, s.d_slot_of, s.d_rec, s.d_meta, s.d_upd, masks ? s.d_upd + s.upd_cap : nullptr);
+        h->launches++;
+        s.stale_nodes += m;
+    } else if (masks) {
+        kgpu::scatter_masks<<<(unsigned)((m + 255) / 256), 256, 0, s.stream>>>(s.d_upd, s.d_upd + s.upd_cap, m, s.d_free);
+        h->launches++;
+    }
+    KGPU_CUDA(h, cudaGetLastError());
+    if (s.fit_valid) {
+        // rows of the changed nodes: fit_nodes over the list into d_fit's spare rows?  No: a private patch buffer
+        uint32_t *d_patch = nullptr;
+        KGPU_CUDA(h, cudaMallocAsync(&d_patch, (size_t)m * 36, s.stream));
+        kgpu::fit_nodes<<<(unsigned)((m + 127) / 128), 128, 0, s.stream>>>(topo4, s.d_free, s.d_upd, m, W, PC, d_patch);
+        h->launches++;
+        std::vector<uint32_t> rows((size_t)m * 9);
+        KGPU_CUDA(h, cudaMemcpyAsync(rows.data(), d_patch, (size_t)m * 36, cudaMemcpyDeviceToHost, s.stream));
+        KGPU_CUDA(h, cudaFreeAsync(d_patch, s.stream));
+        KGPU_CUDA(h, cudaStreamSynchronize(s.stream));
+        for (int k = 0; k < 9; k++)
+            for (int64_t i = 0; i < m; i++) s.h_fit[(int64_t)k * s.n + idx[i]] = rows[(size_t)((int64_t)k * m + i)];
+    } else {
+        KGPU_CUDA(h, cudaStreamSynchronize(s.stream));
+    }
+    return KGPU_OK;
+}
+
 // Enqueue K1 for P pods on shard s: d_keys[p] = best placement over this shard's nodes.
 // has_mem: 1 / 0 = the host knows whether some pod carries min_mem > 0; -1 = unknown (device buffers).
 int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, unsigned long long *d_keys,
@@ -161,6 +338,10 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
 
     const bool wpp = h->variant == KGPU_VARIANT_WARP_PER_PAIR;
     const bool sparse = h->variant == KGPU_VARIANT_SPARSE;
+    if (sparse) {                      // order + compacted records current?  (no-op unless nodes / masks / weights changed)
+        const int rc = ensure_node_cache(h, s);
+        if (rc != KGPU_OK) return rc;
+    }
     if (!wpp && has_mem != 0) {   // which pods go to K1m?  (flag read by its blocks; skipped when the host knows there are none)
         KGPU_CUDA(h, cudaMemsetAsync(s.d_flag, 0, sizeof(int), st));
         kgpu::any_mem_pod<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(pods4, P, s.d_flag);
@@ -202,13 +383,6 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
             h->launches++;
         }
         if (sparse) {
-            if (s.compact_dirty) {   // rebuild the compacted pair-cost cache (topology / masks / weights changed)
-                kgpu::compact_nodes<<<(unsigned)((s.n + kgpu::SP_THREADS - 1) / kgpu::SP_THREADS), kgpu::SP_THREADS, 0, st>>>(
-                    topo4, s.d_free, s.n, W, s.d_cpair, s.d_perm);
-                h->launches++;
-                s.compact_dirty = false;
-            }
-            const int4 *cpair4 = reinterpret_cast<const int4 *>(s.d_cpair);
             // Work list instead of the plain grid: auto = for small shards (few tiles per resident block), where
             // equal pod ranges are either too few or too short; KGPU_SP_WORKLIST=0/1 forces it off/on.
             static const int worklist_mode = [] { const char *e = getenv("KGPU_SP_WORKLIST"); return e ? atoi(e) : -1; }();
@@ -234,7 +408,7 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
             for (int i = 0; i < 16; i++) byte_keys = byte_keys && h->W[i] <= 2340;
 #define KGPU_LAUNCH_SPARSE(MEMF, BK)                                                                          \
     kgpu::score_pairs_sparse<true, MEMF, BK><<<grid, kgpu::SP_THREADS, 0, st>>>(                              \
-        cpair4, s.d_perm, s.d_free, s.d_mem, s.d_order, s.d_flag, s.node_id_base, pods4, P, (int)per, d_work, PC, d_keys)
+        s.d_rec, s.d_meta, s.d_mem, s.d_order, s.d_flag, s.node_id_base, pods4, P, (int)per, d_work, PC, d_keys)
             if (byte_keys) KGPU_LAUNCH_SPARSE(false, true); else KGPU_LAUNCH_SPARSE(false, false);
             h->launches++;
             if (has_mem != 0) {
@@ -278,8 +452,19 @@ void free_shard(kgpu_shard &s) {
     if (s.d_mem) cudaFree(s.d_mem);
     if (s.d_flag) cudaFree(s.d_flag);
     if (s.d_order) cudaFree(s.d_order);
-    if (s.d_cpair) cudaFree(s.d_cpair);
-    if (s.d_perm) cudaFree(s.d_perm);
+    if (s.d_rec) cudaFree(s.d_rec);
+    if (s.d_meta) cudaFree(s.d_meta);
+    if (s.d_slot_of) cudaFree(s.d_slot_of);
+    if (s.d_ord_cnt) cudaFree(s.d_ord_cnt);
+    if (s.d_ord_off) cudaFree(s.d_ord_off);
+    if (s.d_ord_meta) cudaFree(s.d_ord_meta);
+    if (s.d_bad) cudaFree(s.d_bad);
+    if (s.d_upd) cudaFree(s.d_upd);
+    if (s.d_fit) cudaFree(s.d_fit);
+    if (s.h_fit) cudaFreeHost(s.h_fit);
+    if (s.d_free_scratch) cudaFree(s.d_free_scratch);
+    if (s.d_query) cudaFree(s.d_query);
+    if (s.d_qout) cudaFree(s.d_qout);
     if (s.d_pods) cudaFree(s.d_pods);
     if (s.d_keys) cudaFree(s.d_keys);
     if (s.d_gather) cudaFree(s.d_gather);
@@ -297,7 +482,7 @@ void free_shard(kgpu_shard &s) {
 
 extern "C" {
 
-const char *kgpu_version(void) { return "0.1.0"; }
+const char *kgpu_version(void) { return "0.2.0"; }
 
 const char *kgpu_last_error(kgpu_t *h) {
     if (h) {
@@ -339,6 +524,8 @@ int kgpu_create(const int *dev_ids, int ndev, kgpu_t **out) {
         step(cudaEventCreate(&s.ev1), "cudaEventCreate");
         step(cudaMalloc(&s.d_bestk, 9 * 8), "cudaMalloc");
         step(cudaMalloc(&s.d_flag, sizeof(int)), "cudaMalloc");
+        step(cudaMalloc(&s.d_ord_meta, kgpu::ORD_META * sizeof(long long)), "cudaMalloc");
+        step(cudaMalloc(&s.d_bad, sizeof(unsigned long long)), "cudaMalloc");
     }
     if (rc == KGPU_OK && ndev > 1) {
         std::vector<int> devs(dev_ids, dev_ids + ndev);
@@ -383,7 +570,7 @@ int kgpu_set_weights(kgpu_t *h, const int32_t w[KGPU_NUM_LEVELS]) {
         if (w[i] < 0 || w[i] > KGPU_MAX_WEIGHT)
             return fail(h, KGPU_ERR_INVALID, "kgpu_set_weights: w[%d] = %d outside 0..%d", i, w[i], KGPU_MAX_WEIGHT);
     memcpy(h->W, w, sizeof h->W);
-    for (auto &s : h->shards) s.compact_dirty = true;
+    for (auto &s : h->shards) { s.compact_dirty = true; s.fit_valid = false; }
     return KGPU_OK;
 }
 
@@ -410,76 +597,83 @@ int kgpu_upload_nodes(kgpu_t *h, const int32_t *topo, const int32_t *free_mask, 
     if (n < 0 || (n > 0 && (!topo || !free_mask))) return fail(h, KGPU_ERR_INVALID, "kgpu_upload_nodes: bad arguments");
     if (node_id_base < 0 || node_id_base + n > 0xFFFFFFFFLL)
         return fail(h, KGPU_ERR_INVALID, "kgpu_upload_nodes: node ids must fit in 32 bits");
-    int rc = validate_topo(h, topo, n);
-    if (rc != KGPU_OK) return rc;
+    const auto t_begin = std::chrono::steady_clock::now();
     const int64_t G = (int64_t)h->shards.size();
     const int64_t per = (n + G - 1) / G;     // contiguous ranges: shard g holds [g*per, ...)
+    if (per > 0x7FFFFFFFLL - 4096) return fail(h, KGPU_ERR_INVALID, "kgpu_upload_nodes: more than 2^31 nodes per device");
+    // A failure below leaves the handle EMPTY (n = 0 everywhere), never half old / half new.
+    auto empty_all = [&]() {
+        for (auto &s : h->shards) { s.n = 0; s.n_slots = 0; s.order_dirty = true; s.compact_dirty = true; s.fit_valid = false; s.work_P = -1; }
+        h->n_total = 0;
+    };
+#define KGPU_UP(expr)                                                                                 \
+    do {                                                                                              \
+        cudaError_t e__ = (expr);                                                                     \
+        if (e__ != cudaSuccess) {                                                                     \
+            empty_all();                                                                              \
+            return fail(h, e__ == cudaErrorMemoryAllocation ? KGPU_ERR_NOMEM : KGPU_ERR_CUDA,          \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);  \
+        }                                                                                             \
+    } while (0)
     int64_t off = 0;
     for (auto &s : h->shards) {
         const int64_t cnt = std::max<int64_t>(0, std::min<int64_t>(per, n - off));
-        KGPU_CUDA(h, cudaSetDevice(s.dev));
+        KGPU_UP(cudaSetDevice(s.dev));
         if (cnt > s.cap) {
             if (s.d_topo) cudaFree(s.d_topo);
             if (s.d_free) cudaFree(s.d_free);
             if (s.d_mem) cudaFree(s.d_mem);
-            if (s.d_cpair) cudaFree(s.d_cpair);
-            if (s.d_perm) cudaFree(s.d_perm);
-            s.d_topo = nullptr; s.d_free = nullptr; s.d_mem = nullptr; s.d_cpair = nullptr; s.d_perm = nullptr; s.cap = 0;
-            KGPU_CUDA(h, cudaMalloc(&s.d_cpair, (size_t)cnt * 112));
-            KGPU_CUDA(h, cudaMalloc(&s.d_perm, (size_t)cnt * 4));
-            KGPU_CUDA(h, cudaMalloc(&s.d_topo, (size_t)cnt * 256));
-            KGPU_CUDA(h, cudaMalloc(&s.d_free, (size_t)cnt * 4));
-            KGPU_CUDA(h, cudaMalloc(&s.d_mem, (size_t)cnt * 32));
+            if (s.d_slot_of) cudaFree(s.d_slot_of);
+            s.d_topo = nullptr; s.d_free = nullptr; s.d_mem = nullptr; s.d_slot_of = nullptr; s.cap = 0; s.n = 0;
+            KGPU_UP(cudaMalloc(&s.d_topo, (size_t)cnt * 256));
+            KGPU_UP(cudaMalloc(&s.d_free, (size_t)cnt * 4));
+            KGPU_UP(cudaMalloc(&s.d_mem, (size_t)cnt * 32));
+            KGPU_UP(cudaMalloc(&s.d_slot_of, (size_t)cnt * 4));
             s.cap = cnt;
         }
-        // per-GPU memory is unconstrained (0x7F7F7F7F MiB) until kgpu_upload_gpu_memory says otherwise
-        if (cnt > 0) KGPU_CUDA(h, cudaMemsetAsync(s.d_mem, 0x7F, (size_t)cnt * 32, s.stream));
         if (cnt > 0) {
-            KGPU_CUDA(h, cudaMemcpyAsync(s.d_topo, topo + off * 64, (size_t)cnt * 256, cudaMemcpyHostToDevice, s.stream));
-            KGPU_CUDA(h, cudaMemcpyAsync(s.d_free, free_mask + off, (size_t)cnt * 4, cudaMemcpyHostToDevice, s.stream));
+            // per-GPU memory is unconstrained (0x7F7F7F7F MiB) until kgpu_upload_gpu_memory says otherwise
+            KGPU_UP(cudaMemsetAsync(s.d_mem, 0x7F, (size_t)cnt * 32, s.stream));
+            KGPU_UP(cudaMemcpyAsync(s.d_topo, topo + off * 64, (size_t)cnt * 256, cudaMemcpyHostToDevice, s.stream));
+            KGPU_UP(cudaMemcpyAsync(s.d_free, free_mask + off, (size_t)cnt * 4, cudaMemcpyHostToDevice, s.stream));
+            // value-domain check on the device (levels 0..15): one 8-byte read-back instead of an O(64 N) host pass
+            KGPU_UP(cudaMemsetAsync(s.d_bad, 0xFF, sizeof(unsigned long long), s.stream));
+            kgpu::validate_topo_dev<<<(unsigned)((cnt * 16 + 255) / 256), 256, 0, s.stream>>>(
+                reinterpret_cast<const int4 *>(s.d_topo), cnt * 16, s.d_bad);
+            h->launches++;
+            KGPU_UP(cudaGetLastError());
         }
         s.n = cnt;
-        s.compact_dirty = true;
         s.node_id_base = node_id_base + off;
-        // K1s order: nodes grouped by number of free GPUs (8 first), each class in increasing node
-        // index and padded to whole warps (32 slots), so the lanes of a warp share the bound F and are
-        // in increasing node id (tie-break order inside a warp; across warps the flush compares ids).
-        {
-            std::vector<int32_t> order;
-            order.reserve((size_t)cnt + 9 * 128);
-            for (int f = 8; f >= 0; f--) {
-                for (int64_t i = 0; i < cnt; i++)
-                    if (__builtin_popcount((unsigned)free_mask[off + i] & 0xFFu) == f) order.push_back((int32_t)i);
-                while (order.size() % 32) order.push_back(-1);
-            }
-            while (order.size() % kgpu::SP_THREADS) order.push_back(-1);
-            if ((int64_t)order.size() > s.order_cap) {
-                if (s.d_order) cudaFree(s.d_order);
-                s.d_order = nullptr; s.order_cap = 0;
-                KGPU_CUDA(h, cudaMalloc(&s.d_order, std::max<size_t>(1, order.size()) * 4));
-                s.order_cap = (int64_t)order.size();
-            }
-            s.n_slots = (int64_t)order.size();
-            s.tile_class.assign(order.size() / kgpu::SP_THREADS, 0);
-            for (size_t sl = 0; sl < order.size(); sl++)
-                if (order[sl] >= 0) {
-                    const uint8_t f = (uint8_t)__builtin_popcount((unsigned)free_mask[off + order[sl]] & 0xFFu);
-                    uint8_t &tc = s.tile_class[sl / kgpu::SP_THREADS];
-                    tc = std::max(tc, f);
-                }
-            s.work_P = -1;
-            if (!order.empty()) {
-                KGPU_CUDA(h, cudaMemcpyAsync(s.d_order, order.data(), order.size() * 4, cudaMemcpyHostToDevice, s.stream));
-                KGPU_CUDA(h, cudaStreamSynchronize(s.stream));   // `order` is a local
-            }
-        }
+        s.order_dirty = true;
+        s.compact_dirty = true;
+        s.fit_valid = false;
         off += cnt;
     }
-    for (auto &s : h->shards) {
-        KGPU_CUDA(h, cudaSetDevice(s.dev));
-        KGPU_CUDA(h, cudaStreamSynchronize(s.stream));
-    }
     h->n_total = n;
+    // all devices copy concurrently; then the verdicts, then the K1s order + compacted records (device side)
+    off = 0;
+    for (auto &s : h->shards) {
+        if (s.n > 0) {
+            unsigned long long bad = ~0ull;
+            KGPU_UP(cudaSetDevice(s.dev));
+            KGPU_UP(cudaMemcpyAsync(&bad, s.d_bad, sizeof bad, cudaMemcpyDeviceToHost, s.stream));
+            KGPU_UP(cudaStreamSynchronize(s.stream));
+            if (bad != ~0ull) {
+                const long long el = (long long)bad;
+                empty_all();
+                return fail(h, KGPU_ERR_INVALID, "topo[%lld][%d] = %d outside the link-level domain 0..15",
+                            (long long)(off + el / 64), (int)(el % 64), topo[(off + el / 64) * 64 + el % 64]);
+            }
+        }
+        off += s.n;
+    }
+#undef KGPU_UP
+    for (auto &s : h->shards) {
+        const int rc = ensure_node_cache(h, s);
+        if (rc != KGPU_OK) { empty_all(); return rc; }
+    }
+    h->last_upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     return KGPU_OK;
 }
 
@@ -524,24 +718,47 @@ int kgpu_update_node(kgpu_t *h, int64_t idx, const int32_t topo[64], int32_t fre
     int64_t local = 0;
     kgpu_shard *s = shard_of(h, idx, &local);
     KGPU_CUDA(h, cudaSetDevice(s->dev));
-    s->compact_dirty = true;
     KGPU_CUDA(h, cudaMemcpyAsync(s->d_topo + local * 64, topo, 256, cudaMemcpyHostToDevice, s->stream));
-    KGPU_CUDA(h, cudaMemcpyAsync(s->d_free + local, &free_mask, 4, cudaMemcpyHostToDevice, s->stream));
-    KGPU_CUDA(h, cudaStreamSynchronize(s->stream));
+    const int32_t li = (int32_t)local;
+    return apply_node_updates(h, *s, &li, &free_mask, 1);      // new mask + this node's record (and fit row) only
+}
+
+int kgpu_set_free_masks(kgpu_t *h, const int64_t *idx, const int32_t *free_mask, int64_t n) {
+    if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_set_free_masks: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (n < 0 || (n > 0 && (!idx || !free_mask))) return fail(h, KGPU_ERR_INVALID, "kgpu_set_free_masks: bad arguments");
+    for (int64_t i = 0; i < n; i++)
+        if (idx[i] < 0 || idx[i] >= h->n_total)
+            return fail(h, KGPU_ERR_INVALID, "kgpu_set_free_masks: index %lld out of range", (long long)idx[i]);
+    // per shard: local indices, the LAST entry wins when a node is listed more than once
+    int64_t off = 0;
+    for (auto &s : h->shards) {
+        std::vector<int32_t> li, lm;
+        if (n == 1) {
+            if (idx[0] >= off && idx[0] < off + s.n) { li.push_back((int32_t)(idx[0] - off)); lm.push_back(free_mask[0]); }
+        } else {
+            std::vector<std::pair<int32_t, int64_t>> ent;     // (local index, position in the call)
+            for (int64_t i = 0; i < n; i++)
+                if (idx[i] >= off && idx[i] < off + s.n) ent.emplace_back((int32_t)(idx[i] - off), i);
+            std::sort(ent.begin(), ent.end());
+            for (size_t e = 0; e < ent.size(); e++)
+                if (e + 1 == ent.size() || ent[e + 1].first != ent[e].first) { li.push_back(ent[e].first); lm.push_back(free_mask[ent[e].second]); }
+        }
+        off += s.n;
+        if (li.empty()) continue;
+        const int rc = apply_node_updates(h, s, li.data(), lm.data(), (int64_t)li.size());
+        if (rc != KGPU_OK) return rc;
+    }
     return KGPU_OK;
 }
 
 int kgpu_set_free_mask(kgpu_t *h, int64_t idx, int32_t free_mask) {
     if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_set_free_mask: NULL handle");
-    std::lock_guard<std::mutex> g(h->mu);
-    if (idx < 0 || idx >= h->n_total) return fail(h, KGPU_ERR_INVALID, "kgpu_set_free_mask: index %lld out of range", (long long)idx);
-    int64_t local = 0;
-    kgpu_shard *s = shard_of(h, idx, &local);
-    s->compact_dirty = true;
-    KGPU_CUDA(h, cudaSetDevice(s->dev));
-    KGPU_CUDA(h, cudaMemcpyAsync(s->d_free + local, &free_mask, 4, cudaMemcpyHostToDevice, s->stream));
-    KGPU_CUDA(h, cudaStreamSynchronize(s->stream));
-    return KGPU_OK;
+    {
+        std::lock_guard<std::mutex> g(h->mu);
+        if (idx < 0 || idx >= h->n_total) return fail(h, KGPU_ERR_INVALID, "kgpu_set_free_mask: index %lld out of range", (long long)idx);
+    }
+    return kgpu_set_free_masks(h, &idx, &free_mask, 1);
 }
 
 int kgpu_remove_node(kgpu_t *h, int64_t idx) { return kgpu_set_free_mask(h, idx, 0); }
@@ -603,6 +820,10 @@ int kgpu_score_batch(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_ke
 }
 
 int kgpu_place_batch(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_keys) {
+    return kgpu_place_batch_ex(h, pods, P, out_keys, 0);
+}
+
+int kgpu_place_batch_ex(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_keys, int flags) {
     if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_place_batch: NULL handle");
     std::lock_guard<std::mutex> g(h->mu);
     if (h->shards.size() != 1) return fail(h, KGPU_ERR_STATE, "kgpu_place_batch: needs a single-device handle");
@@ -627,6 +848,18 @@ int kgpu_place_batch(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_ke
     if (rc != KGPU_OK) return rc;
     KGPU_CUDA(h, cudaSetDevice(s.dev));
     KGPU_CUDA(h, cudaMemcpyAsync(s.d_pods, pods, (size_t)P * 16, cudaMemcpyHostToDevice, s.stream));
+    const bool dry = (flags & KGPU_PLACE_DRY_RUN) != 0;
+    int32_t *d_free = s.d_free;
+    if (dry && s.n > 0) {                  // place on a scratch copy of the masks: conflict-free proposals, nothing taken
+        if (s.n > s.free_scratch_cap) {
+            if (s.d_free_scratch) cudaFree(s.d_free_scratch);
+            s.d_free_scratch = nullptr; s.free_scratch_cap = 0;
+            KGPU_CUDA(h, cudaMalloc(&s.d_free_scratch, (size_t)s.n * 4));
+            s.free_scratch_cap = s.n;
+        }
+        KGPU_CUDA(h, cudaMemcpyAsync(s.d_free_scratch, s.d_free, (size_t)s.n * 4, cudaMemcpyDeviceToDevice, s.stream));
+        d_free = s.d_free_scratch;
+    }
     if (s.n == 0) {
         KGPU_CUDA(h, cudaMemsetAsync(s.d_keys, 0xFF, (size_t)P * 8, s.stream));
     } else {
@@ -643,13 +876,16 @@ int kgpu_place_batch(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out_ke
         memcpy(W.w, h->W, sizeof W.w);
         KGPU_CUDA(h, cudaEventRecord(s.ev0, s.stream));
         kgpu::place_init<<<dim3((unsigned)T, (unsigned)views.n), kgpu::PLACE_TILE, 0, s.stream>>>(
-            reinterpret_cast<const int4 *>(s.d_topo), s.d_free, s.d_mem, s.n, Npad, s.node_id_base, W, PC, views, s.d_nodebest,
+            reinterpret_cast<const int4 *>(s.d_topo), d_free, s.d_mem, s.n, Npad, s.node_id_base, W, PC, views, s.d_nodebest,
             s.d_tilebest, T);
-        kgpu::place_sequential<<<1, kgpu::PLACE_THREADS, 0, s.stream>>>(s.d_topo, s.d_free, s.d_mem, s.n, Npad, s.node_id_base,
+        kgpu::place_sequential<<<1, kgpu::PLACE_THREADS, 0, s.stream>>>(s.d_topo, d_free, s.d_mem, s.n, Npad, s.node_id_base,
                                                                         reinterpret_cast<const int4 *>(s.d_pods), P, W, views,
                                                                         s.d_nodebest, s.d_tilebest, T, s.d_keys);
         h->launches += 2;
-        s.compact_dirty = true;          // the free masks have changed on the device
+        if (!dry) {
+            s.order_dirty = true;        // the free masks have changed on the device: re-sort + recompact lazily
+            s.fit_valid = false;
+        }
         KGPU_CUDA(h, cudaGetLastError());
         KGPU_CUDA(h, cudaEventRecord(s.ev1, s.stream));
     }
@@ -679,6 +915,30 @@ int kgpu_get_free_masks(kgpu_t *h, int32_t *out_free_mask, int64_t n) {
     return KGPU_OK;
 }
 
+int kgpu_build_fit_table(kgpu_t *h) {
+    if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_build_fit_table: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    for (auto &s : h->shards) {
+        const int rc = build_fit_table(h, s);
+        if (rc != KGPU_OK) return rc;
+    }
+    return KGPU_OK;
+}
+
+int kgpu_fit_lookup(kgpu_t *h, int64_t node_idx, int32_t k, uint32_t *out_node_key) {
+    if (!h || !out_node_key) return fail(h, KGPU_ERR_INVALID, "kgpu_fit_lookup: NULL argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (node_idx < 0 || node_idx >= h->n_total) return fail(h, KGPU_ERR_INVALID, "kgpu_fit_lookup: node index %lld out of range", (long long)node_idx);
+    int64_t local = 0;
+    kgpu_shard *s = shard_of(h, node_idx, &local);
+    if (!s->fit_valid) {                          // built lazily, kept current by the state-change calls
+        const int rc = build_fit_table(h, *s);
+        if (rc != KGPU_OK) return rc;
+    }
+    *out_node_key = (k < 0 || k > 8) ? UINT32_MAX : s->h_fit[(int64_t)k * s->n + local];
+    return KGPU_OK;
+}
+
 int kgpu_score_pairs(kgpu_t *h, const int64_t *node_idx, const int32_t *k, const int32_t *min_mem_mib, int64_t n,
                      uint32_t *out_node_keys) {
     if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_score_pairs: NULL handle");
@@ -687,42 +947,52 @@ int kgpu_score_pairs(kgpu_t *h, const int64_t *node_idx, const int32_t *k, const
     for (int64_t i = 0; i < n; i++)
         if (node_idx[i] < 0 || node_idx[i] >= h->n_total)
             return fail(h, KGPU_ERR_INVALID, "kgpu_score_pairs: node index %lld out of range", (long long)node_idx[i]);
+    // Pairs without a memory requirement are answered from the (node, k) fit table's host copy: no launch,
+    // no copy per call (PodFitsDevice is called once per (node, pod) by the core: gpu_scheduler.go:34-44).
+    // The others go to the device in one packed copy, routed to the shard that holds their node.
     kgpu::Weights W;
     memcpy(W.w, h->W, sizeof W.w);
-    // route each pair to the shard that holds its node
     int64_t off = 0;
     for (auto &s : h->shards) {
-        std::vector<long long> idx;
-        std::vector<int32_t> kk, mm;
+        std::vector<int4> q;
         std::vector<int64_t> pos;
-        for (int64_t i = 0; i < n; i++)
-            if (node_idx[i] >= off && node_idx[i] < off + s.n) {
-                idx.push_back(node_idx[i] - off); kk.push_back(k[i]); mm.push_back(min_mem_mib ? min_mem_mib[i] : 0); pos.push_back(i);
+        for (int64_t i = 0; i < n; i++) {
+            if (node_idx[i] < off || node_idx[i] >= off + s.n) continue;
+            const int64_t local = node_idx[i] - off;
+            if (!min_mem_mib || min_mem_mib[i] <= 0) {
+                if (!s.fit_valid) {
+                    const int rc = build_fit_table(h, s);
+                    if (rc != KGPU_OK) return rc;
+                }
+                out_node_keys[i] = (k[i] < 0 || k[i] > 8) ? UINT32_MAX : s.h_fit[(int64_t)k[i] * s.n + local];
+            } else {
+                q.push_back(make_int4((int)(local & 0xFFFFFFFFLL), (int)(local >> 32), k[i], min_mem_mib[i]));
+                pos.push_back(i);
             }
+        }
         off += s.n;
-        if (idx.empty()) continue;
-        const size_t m = idx.size();
+        if (q.empty()) continue;
+        const int64_t m = (int64_t)q.size();
         KGPU_CUDA(h, cudaSetDevice(s.dev));
-        long long *d_idx = nullptr; int32_t *d_k = nullptr, *d_mm = nullptr; uint32_t *d_out = nullptr;
-        KGPU_CUDA(h, cudaMallocAsync(&d_idx, m * 8, s.stream));
-        KGPU_CUDA(h, cudaMallocAsync(&d_k, m * 4, s.stream));
-        KGPU_CUDA(h, cudaMallocAsync(&d_mm, m * 4, s.stream));
-        KGPU_CUDA(h, cudaMemcpyAsync(d_mm, mm.data(), m * 4, cudaMemcpyHostToDevice, s.stream));
-        KGPU_CUDA(h, cudaMallocAsync(&d_out, m * 4, s.stream));
-        KGPU_CUDA(h, cudaMemcpyAsync(d_idx, idx.data(), m * 8, cudaMemcpyHostToDevice, s.stream));
-        KGPU_CUDA(h, cudaMemcpyAsync(d_k, kk.data(), m * 4, cudaMemcpyHostToDevice, s.stream));
+        if (m > s.query_cap) {
+            if (s.d_free_scratch) cudaFree(s.d_free_scratch);
+    if (s.d_query) cudaFree(s.d_query);
+            if (s.d_qout) cudaFree(s.d_qout);
+            s.d_query = nullptr; s.d_qout = nullptr; s.query_cap = 0;
+            const int64_t cap = std::max<int64_t>(256, m + m / 2);
+            KGPU_CUDA(h, cudaMalloc(&s.d_query, (size_t)cap * 16));
+            KGPU_CUDA(h, cudaMalloc(&s.d_qout, (size_t)cap * 4));
+            s.query_cap = cap;
+        }
+        KGPU_CUDA(h, cudaMemcpyAsync(s.d_query, q.data(), (size_t)m * 16, cudaMemcpyHostToDevice, s.stream));
         kgpu::score_pair_list<<<(unsigned)((m + 127) / 128), 128, 0, s.stream>>>(
-            reinterpret_cast<const int4 *>(s.d_topo), s.d_free, s.d_mem, s.n, d_idx, d_k, d_mm, (int64_t)m, W, PC, d_out);
+            reinterpret_cast<const int4 *>(s.d_topo), s.d_free, s.d_mem, s.n, s.d_query, m, W, PC, s.d_qout);
         h->launches++;
         KGPU_CUDA(h, cudaGetLastError());
-        std::vector<uint32_t> res(m);
-        KGPU_CUDA(h, cudaMemcpyAsync(res.data(), d_out, m * 4, cudaMemcpyDeviceToHost, s.stream));
-        KGPU_CUDA(h, cudaFreeAsync(d_idx, s.stream));
-        KGPU_CUDA(h, cudaFreeAsync(d_k, s.stream));
-        KGPU_CUDA(h, cudaFreeAsync(d_mm, s.stream));
-        KGPU_CUDA(h, cudaFreeAsync(d_out, s.stream));
+        std::vector<uint32_t> res((size_t)m);
+        KGPU_CUDA(h, cudaMemcpyAsync(res.data(), s.d_qout, (size_t)m * 4, cudaMemcpyDeviceToHost, s.stream));
         KGPU_CUDA(h, cudaStreamSynchronize(s.stream));
-        for (size_t j = 0; j < m; j++) out_node_keys[pos[j]] = res[j];
+        for (int64_t j = 0; j < m; j++) out_node_keys[pos[(size_t)j]] = res[(size_t)j];
     }
     return KGPU_OK;
 }
@@ -842,6 +1112,12 @@ int64_t kgpu_kernel_launches(kgpu_t *h) {
     if (!h) return 0;
     std::lock_guard<std::mutex> g(h->mu);
     return h->launches;
+}
+
+double kgpu_last_upload_ms(kgpu_t *h) {
+    if (!h) return 0.0;
+    std::lock_guard<std::mutex> g(h->mu);
+    return h->last_upload_ms;
 }
 
 double kgpu_last_kernel_ms(kgpu_t *h) {

@@ -92,10 +92,10 @@ order_scan(const int32_t *__restrict__ cnt, int nb, int32_t *__restrict__ off, l
     if (tid == 0) meta[9] = ((long long)running + tile - 1) / tile * tile;
 }
 
-// pass 3: order[slot] = node, stable inside a class (order must be pre-set to -1)
+// pass 3: order[slot] = node and slot_of[node] = slot, stable inside a class (order must be pre-set to -1)
 __global__ void __launch_bounds__(ORD_BLOCK)
 order_scatter(const int32_t *__restrict__ free_mask, int64_t N, const int32_t *__restrict__ off, int nb,
-              int32_t *__restrict__ order) {
+              int32_t *__restrict__ order, int32_t *__restrict__ slot_of) {
     __shared__ int32_t sCnt[9][32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t node = (int64_t)blockIdx.x * ORD_BLOCK + tid;
@@ -111,7 +111,14 @@ order_scatter(const int32_t *__restrict__ free_mask, int64_t N, const int32_t *_
     if (f < 0) return;
     int before = 0;
     for (int w = 0; w < warp; w++) before += sCnt[f][w];
-    order[off[f * nb + blockIdx.x] + before + rank] = (int32_t)node;
+    const int32_t slot = off[f * nb + blockIdx.x] + before + rank;
+    order[slot] = (int32_t)node;
+    slot_of[node] = slot;
+}
+
+__global__ void scatter_masks(const int32_t *__restrict__ idx, const int32_t *__restrict__ mask, int64_t n, int32_t *free_mask) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) free_mask[idx[i]] = mask[i];
 }
 
 // fit[k * n + i] = (cost<<8 | S) of node list[i] (or node i) for k GPUs, INF32 = does not fit.

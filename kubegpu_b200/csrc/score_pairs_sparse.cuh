@@ -202,14 +202,26 @@ __device__ __forceinline__ void sp_run_k(int F, const PairCosts &C, const PipeCo
 #undef KGPU_SP_CASE
 }
 
-// Compacted pair-cost cache: for every node the 28 scaled pair costs in COMPACT position order
-// (free GPUs first, ascending; pairs touching a non-free position carry PEN) plus the permutation
-// position -> GPU index (8 nibbles).  Rebuilt by the host wrapper whenever topology, free masks or
-// weights changed since the last launch (kgpu.cu: compact_dirty), so K1s blocks stage a node with
-// seven 16-byte loads instead of redoing the gather in every pod split.
+// Compacted pair-cost cache, in SLOT order and tile-transposed, so that a K1s block stages its 128 nodes with
+// fully coalesced loads (what matters when few pods amortise the staging: the HBM-bound regime):
+//   rec  [tile][7][SP_THREADS] int4   word 4t+q of slot s = compacted scaled pair cost number 4t+q of the slot's
+//                                     node (free GPUs first, ascending; pairs touching a non-free position carry PEN)
+//   meta [slot] uint32                position -> GPU index as eight 3-bit fields | free count << 24
+// Padding slots (order[slot] < 0) hold PEN costs, the identity permutation and free count 0.
+// Built for every slot after an upload, a re-sort or a weight change (list == nullptr: item = slot), and for the
+// listed NODES only after a state change (kgpu_set_free_masks / kgpu_update_node: item -> node list[item] ->
+// slot_of[node]; `new_mask`, if given, is scattered into free_mask by the same threads).  A node keeps its slot
+// when its free count changes: the order is then stale, which costs speed (the warp's F is the max over its
+// lanes), never correctness; the host re-sorts when enough nodes have changed.
+__host__ __device__ constexpr int64_t sp_rec_index(int64_t slot, int t) {
+    return ((slot / SP_THREADS) * 7 + t) * SP_THREADS + slot % SP_THREADS;
+}
 __global__ void __launch_bounds__(SP_THREADS)
-compact_nodes(const int4 *__restrict__ topo4, const int32_t *__restrict__ free_mask, int64_t N, Weights W,
-              uint32_t *__restrict__ cpair /*[N][28]*/, uint32_t *__restrict__ perm_out /*[N]*/) {
+compact_nodes(const int4 *__restrict__ topo4, int32_t *free_mask, int64_t n_items, Weights W,
+              const int32_t *__restrict__ order /*[n_slots]*/, const int32_t *__restrict__ slot_of /*[N]*/,
+              int4 *__restrict__ rec, uint32_t *__restrict__ meta,
+              const int32_t *__restrict__ list = nullptr /*[n_items] node indices, or every slot*/,
+              const int32_t *__restrict__ new_mask = nullptr /*[n_items] with list: masks to store first*/) {
     __shared__ int32_t sW[16];
     __shared__ uint32_t sRow[SP_THREADS * SP_ROW];
     const int tid = threadIdx.x;
@@ -218,9 +230,19 @@ compact_nodes(const int4 *__restrict__ topo4, const int32_t *__restrict__ free_m
         for (int i = 0; i < 16; i++) sW[i] = W.w[i];
     }
     __syncthreads();
-    const int64_t node = (int64_t)blockIdx.x * SP_THREADS + tid;
-    if (node >= N) return;
-    const uint32_t free = (uint32_t)__ldg(free_mask + node) & 0xFFu;
+    const int64_t item = (int64_t)blockIdx.x * SP_THREADS + tid;
+    if (item >= n_items) return;
+    int64_t node, slot;
+    if (list) { node = __ldg(list + item); slot = __ldg(slot_of + node); }
+    else      { slot = item; node = __ldg(order + slot); }
+    if (node < 0) {                                   // padding slot
+#pragma unroll
+        for (int t = 0; t < 7; t++) rec[sp_rec_index(slot, t)] = make_int4((int)PEN, (int)PEN, (int)PEN, (int)PEN);
+        meta[slot] = 0xFAC688u;                       // identity permutation (7<<21 | 6<<18 | ... | 0), free count 0
+        return;
+    }
+    if (new_mask) free_mask[node] = __ldg(new_mask + item);
+    const uint32_t free = (uint32_t)(new_mask ? __ldg(new_mask + item) : free_mask[node]) & 0xFFu;
     uint32_t *row = sRow + tid * SP_ROW;
     {
         const int4 *src = topo4 + node * 16;
@@ -242,7 +264,7 @@ compact_nodes(const int4 *__restrict__ topo4, const int32_t *__restrict__ free_m
             }
     }
     const uint32_t nfree = (uint32_t)__popc(free);
-    uint32_t perm = 0;
+    uint32_t perm = 0;                                // nibbles here, 3-bit fields in meta
     {
         int pos = 0;
 #pragma unroll
@@ -252,8 +274,13 @@ compact_nodes(const int4 *__restrict__ topo4, const int32_t *__restrict__ free_m
         for (int g = 0; g < 8; g++)
             if (!((free >> g) & 1u)) { perm |= (uint32_t)g << (4 * pos); pos++; }
     }
-    perm_out[node] = perm;
-    uint32_t *dst = cpair + node * 28;
+    {
+        uint32_t p3 = 0;
+#pragma unroll
+        for (int g = 0; g < 8; g++) p3 |= ((perm >> (4 * g)) & 7u) << (3 * g);
+        meta[slot] = p3 | (nfree << 24);
+    }
+    uint32_t wds[28];
 #pragma unroll
     for (int i = 0; i < 8; i++)
 #pragma unroll
@@ -262,15 +289,17 @@ compact_nodes(const int4 *__restrict__ topo4, const int32_t *__restrict__ free_m
             const int lo = min(a, b), hi = max(a, b);
             uint32_t cst = row[7 * lo - ((lo * (lo - 1)) >> 1) + (hi - lo - 1)];
             if ((uint32_t)j >= nfree) cst += PEN;
-            dst[sp_pidx(i, j)] = cst;
+            wds[sp_pidx(i, j)] = cst;
         }
+#pragma unroll
+    for (int t = 0; t < 7; t++)
+        rec[sp_rec_index(slot, t)] = make_int4((int)wds[4 * t], (int)wds[4 * t + 1], (int)wds[4 * t + 2], (int)wds[4 * t + 3]);
 }
 
 // grid = (work items) or (slot tiles, pod splits); block = SP_THREADS.  order[slot] = node index or -1 (padding).
 template <bool PER_PAIR, bool MEM, bool BYTE_KEYS>
 __global__ void __launch_bounds__(SP_THREADS, MEM ? 4 : KGPU_SP_MINBLOCKS)
-score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__ perm_in,
-                   const int32_t *__restrict__ free_mask,
+score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ meta,
                    const int32_t *__restrict__ gpu_mem, const int32_t *__restrict__ order,
                    const int *__restrict__ mem_flag, int64_t node_id_base, const int4 *__restrict__ pods4, int64_t P,
                    int pods_per_split, const int4 *__restrict__ work, PipeConsts pc, unsigned long long *__restrict__ keys) {
@@ -296,17 +325,24 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
         tile_index = item.x; p_begin = item.y; p_end = item.z;
     }
     const int64_t slot = tile_index * SP_THREADS + tid;
+    // the slot's record: seven coalesced 16-byte loads, issued before anything waits on them
+    int4 rw[7];
+    {
+        const int4 *src = rec + tile_index * (7 * SP_THREADS) + tid;
+#pragma unroll
+        for (int t = 0; t < 7; t++) rw[t] = __ldg(src + t * SP_THREADS);
+    }
     const int32_t node = __ldg(order + slot);
+    const uint32_t pm = __ldg(meta + slot);             // eight 3-bit GPU indices | free count << 24
     const bool valid = node >= 0;
     sNode[tid] = node;
-    const uint32_t nfree = valid ? (uint32_t)__popc((uint32_t)__ldg(free_mask + node) & 0xFFu) : 0u;
-    const uint32_t perm = valid ? __ldg(perm_in + node) : 0x76543210u;
+    const uint32_t nfree = pm >> 24;                     // 0 for padding slots
     {
         uint32_t lo = 0, hi = 0;
 #pragma unroll
         for (int g = 0; g < 4; g++) {
-            lo |= (1u << ((perm >> (4 * g)) & 7u)) << (8 * g);
-            hi |= (1u << ((perm >> (4 * g + 16)) & 7u)) << (8 * g);
+            lo |= (1u << ((pm >> (3 * g)) & 7u)) << (8 * g);
+            hi |= (1u << ((pm >> (3 * g + 12)) & 7u)) << (8 * g);
         }
         sHotLo[tid] = lo;
         sHotHi[tid] = hi;
@@ -319,26 +355,15 @@ score_pairs_sparse(const int4 *__restrict__ cpair4, const uint32_t *__restrict__
         ordered = __syncthreads_and(tid == 0 || node < 0 || (prev >= 0 && prev < node)) != 0;
     }
     PairCosts C;
-    {
-        uint32_t wds[28];
-        if (valid) {
-            const int4 *src = cpair4 + (int64_t)node * 7;
-#pragma unroll
-            for (int t = 0; t < 7; t++) {
-                const int4 v = __ldg(src + t);
-                wds[4 * t + 0] = (uint32_t)v.x; wds[4 * t + 1] = (uint32_t)v.y;
-                wds[4 * t + 2] = (uint32_t)v.z; wds[4 * t + 3] = (uint32_t)v.w;
-            }
-        } else {
-#pragma unroll
-            for (int t = 0; t < 28; t++) wds[t] = PEN;
-        }
-        for_each_pair(C, [&](int i, int j) -> uint32_t { return wds[sp_pidx(i, j)]; });
-    }
+    for_each_pair(C, [&](int i, int j) -> uint32_t {
+        const int w = sp_pidx(i, j);
+        const int4 v = rw[w >> 2];
+        return (uint32_t)((w & 3) == 0 ? v.x : (w & 3) == 1 ? v.y : (w & 3) == 2 ? v.z : v.w);
+    });
     int32_t mem[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (MEM && valid) {
 #pragma unroll
-        for (int g = 0; g < 8; g++) mem[g] = __ldg(gpu_mem + (int64_t)node * 8 + ((perm >> (4 * g)) & 7u));
+        for (int g = 0; g < 8; g++) mem[g] = __ldg(gpu_mem + (int64_t)node * 8 + ((pm >> (3 * g)) & 7u));
     }
     const int F = (int)__reduce_max_sync(0xFFFFFFFFu, nfree);    // warp-uniform bound on usable positions
 

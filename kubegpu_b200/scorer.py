@@ -107,6 +107,28 @@ class Scorer:
     def set_free_mask(self, idx: int, free_mask: int) -> None:
         self._check(self._L.kgpu_set_free_mask(self._h, int(idx), int(free_mask)))
 
+    def set_free_masks(self, idx, free_masks) -> None:
+        """Batched state change (a cycle's Take/Return): one copy + one kernel; last entry wins on duplicates."""
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        fm = _i32(free_masks)
+        if idx.shape[0] != fm.shape[0]:
+            raise ValueError("idx and free_masks must have the same length")
+        self._check(self._L.kgpu_set_free_masks(self._h, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                                fm.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), idx.shape[0]))
+
+    def build_fit_table(self) -> None:
+        self._check(self._L.kgpu_build_fit_table(self._h))
+
+    def fit_lookup(self, node_idx: int, k: int) -> int:
+        """(cost << 8 | mask) of node node_idx for k GPUs from the handle's host-side (node, k) table, or 0xFFFFFFFF."""
+        out = ctypes.c_uint32()
+        self._check(self._L.kgpu_fit_lookup(self._h, int(node_idx), int(k), ctypes.byref(out)))
+        return int(out.value)
+
+    @property
+    def last_upload_ms(self) -> float:
+        return float(self._L.kgpu_last_upload_ms(self._h))
+
     def remove_node(self, idx: int) -> None:
         self._check(self._L.kgpu_remove_node(self._h, int(idx)))
 
@@ -124,13 +146,14 @@ class Scorer:
         self._check(self._L.kgpu_score_batch(self._h, pods.ctypes.data, P, out.ctypes.data))
         return out
 
-    def place_batch(self, pods, out: Optional[np.ndarray] = None) -> np.ndarray:
-        """Stateful sequential placement: pods in order, each takes its GPUs (device free masks change)."""
+    def place_batch(self, pods, out: Optional[np.ndarray] = None, dry_run: bool = False) -> np.ndarray:
+        """Stateful sequential placement: pods in order, each takes its GPUs (device free masks change).
+        dry_run: conflict-free proposals on a scratch copy of the masks, the handle's state is untouched."""
         pods = _i32(pods)
         P = pods.size // 4
         if out is None:
             out = np.empty(P, dtype=np.uint64)
-        self._check(self._L.kgpu_place_batch(self._h, pods.ctypes.data, P, out.ctypes.data))
+        self._check(self._L.kgpu_place_batch_ex(self._h, pods.ctypes.data, P, out.ctypes.data, _lib.PLACE_DRY_RUN if dry_run else 0))
         return out
 
     def get_free_masks(self) -> np.ndarray:

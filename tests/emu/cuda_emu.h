@@ -150,6 +150,10 @@ template <class T>
 inline T __shfl_sync(unsigned, T v, int src, int = 32) { return emu::warp_read(v, src); }
 template <class T>
 inline T __shfl_xor_sync(unsigned, T v, int lane_mask, int = 32) { return emu::warp_read(v, emu::ctx.lane ^ lane_mask); }
+template <class T>
+inline T __shfl_up_sync(unsigned, T v, int delta, int = 32) {      // lanes below delta keep their own value
+    return emu::warp_read(v, emu::ctx.lane >= delta ? emu::ctx.lane - delta : emu::ctx.lane);
+}
 
 // ---- memory ------------------------------------------------------------------------------------------
 template <class T>

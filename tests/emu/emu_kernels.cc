@@ -11,6 +11,7 @@
 #include "place_sequential.cuh"
 #include "sparse_work.h"
 #include "peer_exchange.cuh"
+#include "node_state.cuh"
 
 
 namespace {
@@ -40,44 +41,55 @@ T *aligned_array(size_t n) {
 
 extern "C" {
 
-// K1s (+ its MEM instantiation) exactly as kgpu.cu launches them: order by free count, compact cache, grid.
-void emu_score_sparse(const int32_t *topo, const int32_t *free_mask, const int32_t *gpu_mem /*nullable*/, int64_t n,
-                      int64_t node_id_base, const int32_t *pods, int64_t P, const int32_t *W, int splits,
-                      unsigned long long *keys) {
-    std::memset(keys, 0xFF, (size_t)P * 8);
-    if (n == 0 || P == 0) return;
-    std::vector<int32_t> order;
-    for (int f = 8; f >= 0; f--) {
-        for (int64_t i = 0; i < n; i++)
-            if (__builtin_popcount((unsigned)free_mask[i] & 0xFFu) == f) order.push_back((int32_t)i);
-        while (order.size() % 32) order.push_back(-1);
-    }
-    while (order.size() % kgpu::SP_THREADS) order.push_back(-1);
-    int4 *topo4 = aligned_array<int4>((size_t)n * 16);
-    std::memcpy(topo4, topo, (size_t)n * 256);
-    int4 *pods4 = aligned_array<int4>((size_t)P);
-    std::memcpy(pods4, pods, (size_t)P * 16);
-    int32_t *mem = aligned_array<int32_t>((size_t)n * 8);
-    if (gpu_mem) std::memcpy(mem, gpu_mem, (size_t)n * 32); else std::memset(mem, 0x7F, (size_t)n * 32);
-    uint32_t *cpair = aligned_array<uint32_t>((size_t)n * 28);
-    uint32_t *perm = aligned_array<uint32_t>((size_t)n);
-    const kgpu::Weights Ws = weights_of(W);
-    emu::launch(dim3((unsigned)((n + kgpu::SP_THREADS - 1) / kgpu::SP_THREADS)), dim3(kgpu::SP_THREADS),
-                [&] { kgpu::compact_nodes(topo4, free_mask, n, Ws, cpair, perm); });
+// The K1s node cache as kgpu.cu builds it (build_order + ensure_node_cache): device-side counting sort of the
+// nodes by free count, then the compacted slot-ordered records.
+struct EmuCache {
+    std::vector<int32_t> order, slot_of;
+    int4 *rec = nullptr;
+    uint32_t *meta = nullptr;
+    int64_t n_slots = 0;
+    long long class_count[9] = {0};
+    ~EmuCache() { free(rec); free(meta); }
+};
+
+void emu_build_order(const int32_t *free_mask, int64_t n, EmuCache &c) {
+    const int nb = (int)((n + kgpu::ORD_BLOCK - 1) / kgpu::ORD_BLOCK);
+    const int64_t cap = (n + 9 * 32 + 2 * kgpu::SP_THREADS) / kgpu::SP_THREADS * kgpu::SP_THREADS;
+    c.order.assign((size_t)cap, -1);
+    c.slot_of.assign((size_t)std::max<int64_t>(1, n), -1);
+    std::vector<int32_t> cnt((size_t)nb * 9), off((size_t)nb * 9);
+    long long meta[kgpu::ORD_META] = {0};
+    emu::launch(dim3((unsigned)nb), dim3(kgpu::ORD_BLOCK), [&] { kgpu::order_count(free_mask, n, cnt.data(), nb); });
+    emu::launch(dim3(1), dim3(kgpu::ORD_BLOCK), [&] { kgpu::order_scan(cnt.data(), nb, off.data(), meta, kgpu::SP_THREADS); });
+    emu::launch(dim3((unsigned)nb), dim3(kgpu::ORD_BLOCK),
+                [&] { kgpu::order_scatter(free_mask, n, off.data(), nb, c.order.data(), c.slot_of.data()); });
+    for (int k = 0; k < 9; k++) c.class_count[k] = meta[k];
+    c.n_slots = meta[9];
+}
+
+void emu_build_cache(const int4 *topo4, int32_t *free_mask, int64_t n, const kgpu::Weights &Ws, EmuCache &c) {
+    emu_build_order(free_mask, n, c);
+    c.rec = aligned_array<int4>((size_t)c.order.size() * 7);
+    c.meta = aligned_array<uint32_t>(c.order.size());
+    emu::launch(dim3((unsigned)(c.n_slots / kgpu::SP_THREADS)), dim3(kgpu::SP_THREADS),
+                [&] { kgpu::compact_nodes(topo4, free_mask, c.n_slots, Ws, c.order.data(), c.slot_of.data(), c.rec, c.meta); });
+}
+
+void emu_launch_sparse(const EmuCache &c, const int32_t *free_mask, const int32_t *mem, int64_t node_id_base, const int4 *pods4,
+                       const int32_t *pods, int64_t P, const int32_t *W, int splits, unsigned long long *keys) {
     int flag = 0;
     for (int64_t p = 0; p < P; p++) flag |= pods[4 * p + 3] > 0;
-    dim3 grid((unsigned)(order.size() / kgpu::SP_THREADS), (unsigned)std::max(1, splits));
+    dim3 grid((unsigned)(c.n_slots / kgpu::SP_THREADS), (unsigned)std::max(1, splits));
     const int per = per_split(P, std::max(1, splits));
-    const int4 *cpair4 = reinterpret_cast<const int4 *>(cpair);
     // splits < 0: the work list of sparse_work.h for -splits resident blocks, as kgpu.cu builds it
     std::vector<kgpu::SparseWorkItem> items;
     const int4 *work = nullptr;
     if (splits < 0) {
-        std::vector<uint8_t> tile_class(order.size() / kgpu::SP_THREADS, 0);
-        for (size_t sl = 0; sl < order.size(); sl++)
-            if (order[sl] >= 0)
-                tile_class[sl / kgpu::SP_THREADS] = std::max<uint8_t>(tile_class[sl / kgpu::SP_THREADS],
-                                                                      (uint8_t)__builtin_popcount((unsigned)free_mask[order[sl]] & 0xFFu));
+        std::vector<uint8_t> tile_class((size_t)(c.n_slots / kgpu::SP_THREADS), 0);
+        for (int64_t sl = 0; sl < c.n_slots; sl++)
+            if (c.order[(size_t)sl] >= 0)
+                tile_class[(size_t)(sl / kgpu::SP_THREADS)] = std::max<uint8_t>(tile_class[(size_t)(sl / kgpu::SP_THREADS)],
+                                                                            (uint8_t)__builtin_popcount((unsigned)free_mask[c.order[(size_t)sl]] & 0xFFu));
         kgpu::build_sparse_work(tile_class, P, -splits, items);
         static_assert(sizeof(kgpu::SparseWorkItem) == sizeof(int4), "work item layout");
         work = reinterpret_cast<const int4 *>(items.data());
@@ -87,12 +99,87 @@ void emu_score_sparse(const int32_t *topo, const int32_t *free_mask, const int32
     for (int i = 0; i < 16; i++) byte_keys = byte_keys && W[i] <= 2340;
 #define EMU_SPARSE(MEMF, BK)                                                                                   \
     emu::launch(grid, dim3(kgpu::SP_THREADS), [&] {                                                            \
-        kgpu::score_pairs_sparse<true, MEMF, BK>(cpair4, perm, free_mask, mem, order.data(), &flag, node_id_base, pods4, P, per, work, kPC, keys); \
+        kgpu::score_pairs_sparse<true, MEMF, BK>(c.rec, c.meta, mem, c.order.data(), &flag, node_id_base, pods4, P, per, work, kPC, keys); \
     })
     if (byte_keys) EMU_SPARSE(false, true); else EMU_SPARSE(false, false);
     if (flag) { if (byte_keys) EMU_SPARSE(true, true); else EMU_SPARSE(true, false); }
 #undef EMU_SPARSE
-    free(topo4); free(pods4); free(mem); free(cpair); free(perm);
+}
+
+// K1s (+ its MEM instantiation) exactly as kgpu.cu launches them: device-built order, compact cache, grid.
+void emu_score_sparse(const int32_t *topo, const int32_t *free_mask_in, const int32_t *gpu_mem /*nullable*/, int64_t n,
+                      int64_t node_id_base, const int32_t *pods, int64_t P, const int32_t *W, int splits,
+                      unsigned long long *keys) {
+    std::memset(keys, 0xFF, (size_t)P * 8);
+    if (n == 0 || P == 0) return;
+    std::vector<int32_t> free_mask(free_mask_in, free_mask_in + n);
+    int4 *topo4 = aligned_array<int4>((size_t)n * 16);
+    std::memcpy(topo4, topo, (size_t)n * 256);
+    int4 *pods4 = aligned_array<int4>((size_t)P);
+    std::memcpy(pods4, pods, (size_t)P * 16);
+    int32_t *mem = aligned_array<int32_t>((size_t)n * 8);
+    if (gpu_mem) std::memcpy(mem, gpu_mem, (size_t)n * 32); else std::memset(mem, 0x7F, (size_t)n * 32);
+    const kgpu::Weights Ws = weights_of(W);
+    EmuCache c;
+    emu_build_cache(topo4, free_mask.data(), n, Ws, c);
+    emu_launch_sparse(c, free_mask.data(), mem, node_id_base, pods4, pods, P, W, splits, keys);
+    free(topo4); free(pods4); free(mem);
+}
+
+// kgpu_upload_nodes + kgpu_set_free_masks + kgpu_score_batch: the cache is built for free_mask0, then the m listed
+// nodes get new masks through the incremental path (compact_nodes with a list; the order stays as it was, i.e.
+// stale), then K1s runs.  Must equal a fresh upload with the final masks.
+void emu_score_sparse_after_updates(const int32_t *topo, const int32_t *free_mask0, int64_t n, const int32_t *upd_idx,
+                                    const int32_t *upd_mask, int64_t m, const int32_t *pods, int64_t P, const int32_t *W,
+                                    int splits, unsigned long long *keys, int32_t *free_mask_out) {
+    std::memset(keys, 0xFF, (size_t)P * 8);
+    std::vector<int32_t> free_mask(free_mask0, free_mask0 + n);
+    int4 *topo4 = aligned_array<int4>((size_t)n * 16);
+    std::memcpy(topo4, topo, (size_t)n * 256);
+    int4 *pods4 = aligned_array<int4>((size_t)P);
+    std::memcpy(pods4, pods, (size_t)P * 16);
+    int32_t *mem = aligned_array<int32_t>((size_t)n * 8);
+    std::memset(mem, 0x7F, (size_t)n * 32);
+    const kgpu::Weights Ws = weights_of(W);
+    EmuCache c;
+    emu_build_cache(topo4, free_mask.data(), n, Ws, c);
+    if (m > 0)
+        emu::launch(dim3((unsigned)((m + kgpu::SP_THREADS - 1) / kgpu::SP_THREADS)), dim3(kgpu::SP_THREADS), [&] {
+            kgpu::compact_nodes(topo4, free_mask.data(), m, Ws, c.order.data(), c.slot_of.data(), c.rec, c.meta, upd_idx, upd_mask);
+        });
+    emu_launch_sparse(c, free_mask.data(), mem, 0, pods4, pods, P, W, splits, keys);
+    std::memcpy(free_mask_out, free_mask.data(), (size_t)n * 4);
+    free(topo4); free(pods4); free(mem);
+}
+
+// The device-built order alone: order[cap] (cap = n + 9*32 + 2*tile rounded down to tiles), slot_of[n], class counts.
+int64_t emu_order(const int32_t *free_mask, int64_t n, int32_t *order_out, int64_t cap, int32_t *slot_of_out, long long *class_count) {
+    EmuCache c;
+    emu_build_order(free_mask, n, c);
+    for (int64_t i = 0; i < cap; i++) order_out[i] = i < (int64_t)c.order.size() ? c.order[(size_t)i] : -1;
+    std::memcpy(slot_of_out, c.slot_of.data(), (size_t)n * 4);
+    for (int k = 0; k < 9; k++) class_count[k] = c.class_count[k];
+    return c.n_slots;
+}
+
+// fit_nodes (the (node, k) fit table), optionally over a list; out[k * m + i]
+void emu_fit_nodes(const int32_t *topo, const int32_t *free_mask, int64_t n, const int32_t *list /*nullable*/, int64_t m,
+                   const int32_t *W, uint32_t *out) {
+    int4 *topo4 = aligned_array<int4>((size_t)n * 16);
+    std::memcpy(topo4, topo, (size_t)n * 256);
+    const kgpu::Weights Ws = weights_of(W);
+    emu::launch(dim3((unsigned)((m + 127) / 128)), dim3(128), [&] { kgpu::fit_nodes(topo4, free_mask, list, m, Ws, kPC, out); });
+    free(topo4);
+}
+
+// validate_topo_dev: index of the first value outside 0..15, or -1
+long long emu_validate_topo(const int32_t *topo, int64_t n) {
+    int4 *topo4 = aligned_array<int4>((size_t)n * 16);
+    std::memcpy(topo4, topo, (size_t)n * 256);
+    unsigned long long bad = ~0ull;
+    emu::launch(dim3((unsigned)((n * 16 + 255) / 256)), dim3(256), [&] { kgpu::validate_topo_dev(topo4, n * 16, &bad); });
+    free(topo4);
+    return bad == ~0ull ? -1 : (long long)bad;
 }
 
 // The peer-exchange kernel with world = 1 (the rank pushes into its own result array and passes its own
@@ -196,7 +283,7 @@ void emu_reduce_shards(const unsigned long long *gathered, int G, int64_t P, uns
     emu::launch(dim3((unsigned)((P + 255) / 256)), dim3(256), [&] { kgpu::reduce_shards(gathered, G, P, out); });
 }
 
-// kgpu_score_pairs
+// kgpu_score_pairs (the min_mem path: packed queries)
 void emu_score_pair_list(const int32_t *topo, const int32_t *free_mask, const int32_t *gpu_mem, int64_t n,
                          const long long *node_idx, const int32_t *ks, const int32_t *min_mem, int64_t m, const int32_t *W,
                          uint32_t *out) {
@@ -204,10 +291,13 @@ void emu_score_pair_list(const int32_t *topo, const int32_t *free_mask, const in
     std::memcpy(topo4, topo, (size_t)n * 256);
     int32_t *mem = aligned_array<int32_t>((size_t)n * 8);
     if (gpu_mem) std::memcpy(mem, gpu_mem, (size_t)n * 32); else std::memset(mem, 0x7F, (size_t)n * 32);
+    int4 *q = aligned_array<int4>((size_t)m);
+    for (int64_t i = 0; i < m; i++)
+        q[i] = make_int4((int)(node_idx[i] & 0xFFFFFFFFLL), (int)(node_idx[i] >> 32), ks[i], min_mem ? min_mem[i] : 0);
     const kgpu::Weights Ws = weights_of(W);
     emu::launch(dim3((unsigned)((m + 127) / 128)), dim3(128),
-                [&] { kgpu::score_pair_list(topo4, free_mask, mem, n, node_idx, ks, min_mem, m, Ws, kPC, out); });
-    free(topo4); free(mem);
+                [&] { kgpu::score_pair_list(topo4, free_mask, mem, n, q, m, Ws, kPC, out); });
+    free(topo4); free(mem); free(q);
 }
 
 // K3: place_init + place_sequential as kgpu_place_batch launches them (views from the batch's distinct

@@ -257,3 +257,86 @@ def test_emulated_push_and_sync_single_rank(emu):
     lower[::7] = np.uint64(0xFFFFFFFFFFFFFFFF)
     emu.emu_push_and_sync(_p(lower, u64), ctypes.c_int64(P), _p(result, u64), _p(flags, u32), 2, _p(ticket, u32))
     assert (result == np.minimum(local, lower)).all() and flags[0] == 2 and ticket[0] == 0
+
+
+# ---- node_state.cuh: device-side order, incremental record refresh, fit table, value-domain check ---------
+def _host_order(free, tile=128):
+    order = []
+    for f in range(8, -1, -1):
+        order += [i for i in range(len(free)) if bin(int(free[i]) & 0xFF).count("1") == f]
+        while len(order) % 32:
+            order.append(-1)
+    while len(order) % tile:
+        order.append(-1)
+    return np.array(order, dtype=np.int32)
+
+
+@pytest.mark.parametrize("n", [1, 31, 1000, 1024, 1025, 3333])
+def test_emulated_device_order_is_the_stable_class_sort(emu, n):
+    """order_count / order_scan / order_scatter == the host's nine-pass stable sort by free count (classes 8..0,
+    padded to warps, total padded to tiles), slot_of is its inverse, class counts are right."""
+    free = synth.rand_below(0xABC0 + n, 1, n, 256).astype(np.int32)
+    if n == 1000:
+        free[:] = 0xFF                                  # one class only
+    want = _host_order(free)
+    cap = (n + 9 * 32 + 256) // 128 * 128
+    order = np.empty(cap, dtype=np.int32)
+    slot_of = np.empty(n, dtype=np.int32)
+    cc = np.zeros(9, dtype=np.int64)
+    emu.emu_order.restype = ctypes.c_int64
+    n_slots = emu.emu_order(_p(free), ctypes.c_int64(n), _p(order), ctypes.c_int64(cap), _p(slot_of), _p(cc, ctypes.c_longlong))
+    assert n_slots == len(want)
+    assert (order[:n_slots] == want).all() and (order[n_slots:] == -1).all()
+    assert (order[slot_of] == np.arange(n)).all()
+    assert cc.tolist() == [int((np.array([bin(int(x) & 0xFF).count("1") for x in free]) == c).sum()) for c in range(9)]
+
+
+def test_emulated_incremental_mask_updates_equal_fresh_upload(emu, oracle_b):
+    """kgpu_set_free_masks: records of the listed nodes are refreshed in place (stale order), K1s then gives the
+    keys of a fresh upload with the final masks -- including nodes whose free count crossed class boundaries
+    and a node that went from 0 to 8 free GPUs."""
+    W = oracle_b.DEFAULT_WEIGHTS
+    topo, free, pods = synth.gen_c4(N=520, P=90)
+    free0 = free.copy()
+    free0[7] = 0
+    upd_idx = np.array([7, 0, 100, 101, 102, 300, 519, 260], dtype=np.int32)
+    upd_mask = np.array([0xFF, 0x00, 0x0F, 0xF0, 0x81, 0xFF, 0x01, 0x3C], dtype=np.int32)
+    final = free0.copy()
+    final[upd_idx] = upd_mask
+    for splits in (1, 2):
+        keys = np.empty(len(pods), dtype=np.uint64)
+        out_free = np.empty_like(free0)
+        emu.emu_score_sparse_after_updates.restype = None
+        emu.emu_score_sparse_after_updates(_p(np.ascontiguousarray(topo, dtype=np.int32)), _p(free0), ctypes.c_int64(len(free0)),
+                                           _p(upd_idx), _p(upd_mask), ctypes.c_int64(len(upd_idx)), _p(pods), ctypes.c_int64(len(pods)),
+                                           _p(np.ascontiguousarray(W, dtype=np.int32)), splits, _p(keys, ctypes.c_uint64), _p(out_free))
+        assert (out_free == final).all()
+        assert (keys == oracle_b.score_batch(topo, final, pods, W)).all()
+
+
+def test_emulated_fit_table_rows(emu, oracle_b):
+    W = np.ascontiguousarray(oracle_b.DEFAULT_WEIGHTS, dtype=np.int32)
+    topo, free, _ = synth.gen_c4(N=200, P=1)
+    topo = np.ascontiguousarray(topo, dtype=np.int32)
+    emu.emu_fit_nodes.restype = None
+    out = np.empty(9 * 200, dtype=np.uint32)
+    emu.emu_fit_nodes(_p(topo), _p(free), ctypes.c_int64(200), None, ctypes.c_int64(200), _p(W), _p(out, ctypes.c_uint32))
+    for i in range(0, 200, 7):
+        for k in range(9):
+            assert int(out[k * 200 + i]) == oracle_b.node_key(topo[i], int(free[i]), k)
+    lst = np.array([199, 3, 50], dtype=np.int32)
+    out = np.empty(27, dtype=np.uint32)
+    emu.emu_fit_nodes(_p(topo), _p(free), ctypes.c_int64(200), _p(lst), ctypes.c_int64(3), _p(W), _p(out, ctypes.c_uint32))
+    for j, i in enumerate(lst):
+        for k in range(9):
+            assert int(out[k * 3 + j]) == oracle_b.node_key(topo[i], int(free[i]), k)
+
+
+def test_emulated_validate_topo(emu):
+    topo, _, _ = synth.gen_c4(N=100, P=1)
+    topo = np.ascontiguousarray(topo, dtype=np.int32)
+    emu.emu_validate_topo.restype = ctypes.c_longlong
+    assert emu.emu_validate_topo(_p(topo), ctypes.c_int64(100)) == -1
+    topo[40, 9] = 16
+    topo[77, 3] = -1
+    assert emu.emu_validate_topo(_p(topo), ctypes.c_int64(100)) == 40 * 64 + 9
