@@ -388,7 +388,8 @@ std::vector<GpuSlot> parseGpuSlots(const types::ResourceList &alloc) {
 }
 }  // namespace
 
-NvidiaGPUScheduler::NvidiaGPUScheduler(const std::vector<int> &devices) {
+NvidiaGPUScheduler::NvidiaGPUScheduler(const std::vector<int> &devices, bool groupSchedulerMode)
+    : groupSchedulerMode_(groupSchedulerMode) {
     if (devices.empty()) return;
     if (kgpu_create(devices.data(), (int)devices.size(), &handle_) != KGPU_OK) {
         lastError_ = kgpu_last_error(nullptr);
@@ -447,7 +448,7 @@ void NvidiaGPUScheduler::AddNode(const std::string &nodeName, types::NodeInfo *n
                                                                               : kLevelCross;
             }
     }
-    dirty_ = true;
+    if (fresh) dirty_ = true; else changed_.push_back(nodeName);
 }
 
 void NvidiaGPUScheduler::RemoveNode(const std::string &nodeName) {              // gpu_scheduler.go:30-32
@@ -455,7 +456,7 @@ void NvidiaGPUScheduler::RemoveNode(const std::string &nodeName) {              
     auto it = nodes_.find(nodeName);
     if (it != nodes_.end()) {
         it->second.removed = true;
-        dirty_ = true;
+        changed_.push_back(nodeName);
     }
 }
 
@@ -466,7 +467,7 @@ std::string NvidiaGPUScheduler::SetNodeTopology(const std::string &nodeName, con
         if (topo[i] < 0 || topo[i] >= KGPU_NUM_LEVELS) return lastError_ = "SetNodeTopology: link level outside 0..15";
     std::copy(topo, topo + 64, it->second.topo);
     it->second.explicitTopo = true;
-    dirty_ = true;
+    changed_.push_back(nodeName);
     return "";
 }
 
@@ -504,7 +505,23 @@ std::string NvidiaGPUScheduler::AddNodeFromGpusInfo(const std::string &nodeName,
 // Push the host-side node array to the device(s) if it changed since the last launch.
 std::string NvidiaGPUScheduler::flushNodes() {
     if (!handle_) return lastError_ = "no CUDA device: the kgpu scorer has no CPU path (" + lastError_ + ")";
-    if (!dirty_) return "";
+    if (!dirty_) {
+        // only existing nodes changed: one kgpu_update_node each (256-byte copy + a refresh of that node's records)
+        // instead of re-uploading the cluster
+        for (const std::string &name : changed_) {
+            const NodeRecord &rec = nodes_[name];
+            const int32_t fm = rec.removed ? 0 : (int32_t)(rec.presentMask & ~rec.usedMask);
+            if (kgpu_update_node(handle_, rec.index, rec.topo, fm) != KGPU_OK) return lastError_ = kgpu_last_error(handle_);
+            if (rec.hasMem) {
+                int32_t mem[8];
+                for (int g = 0; g < 8; g++) mem[g] = g < rec.nGpus ? rec.memMiB[g] : 0;
+                if (kgpu_update_gpu_memory(handle_, rec.index, mem) != KGPU_OK) return lastError_ = kgpu_last_error(handle_);
+            }
+        }
+        changed_.clear();
+        return "";
+    }
+    changed_.clear();
     const size_t n = indexToName_.size();
     std::vector<int32_t> topo(n * 64), freeMask(n);
     for (size_t i = 0; i < n; i++) {
@@ -528,15 +545,26 @@ std::string NvidiaGPUScheduler::flushNodes() {
 }
 
 std::string NvidiaGPUScheduler::ScoreBatch(const std::vector<const types::PodInfo *> &pods, std::vector<Placement> *out) {
-    return runBatch(pods, out, false);
+    return runBatch(pods, out, BatchMode::Snapshot);
 }
 
 std::string NvidiaGPUScheduler::PlaceBatch(const std::vector<const types::PodInfo *> &pods, std::vector<Placement> *out) {
-    return runBatch(pods, out, true);
+    return runBatch(pods, out, BatchMode::Sequential);
 }
 
+std::string NvidiaGPUScheduler::ProposeBatch(const std::vector<const types::PodInfo *> &pods, std::vector<Placement> *out) {
+    return runBatch(pods, out, BatchMode::DryRun);
+}
+
+namespace {
+int32_t minMemOf(const types::PodInfo &pod) {
+    const int64_t need = getOr0(pod.Requests, GPUMinMemoryMiB);
+    return (int32_t)std::max<int64_t>(0, std::min<int64_t>(need, std::numeric_limits<int32_t>::max()));
+}
+}  // namespace
+
 std::string NvidiaGPUScheduler::runBatch(const std::vector<const types::PodInfo *> &pods, std::vector<Placement> *out,
-                                         bool sequential) {
+                                         BatchMode mode) {
     std::string err = flushNodes();
     if (!err.empty()) return err;
     const size_t P = pods.size();
@@ -548,12 +576,12 @@ std::string NvidiaGPUScheduler::runBatch(const std::vector<const types::PodInfo 
         const int64_t k = PodGPUCount(copy);
         req[p * 4 + 0] = k > 8 ? 9 : (int32_t)k;           // > 8 GPUs never fits one node
         req[p * 4 + 1] = (int32_t)p;
-        const int64_t need = getOr0(pods[p]->Requests, GPUMinMemoryMiB);
-        req[p * 4 + 3] = (int32_t)std::max<int64_t>(0, std::min<int64_t>(need, std::numeric_limits<int32_t>::max()));
+        req[p * 4 + 3] = minMemOf(*pods[p]);
     }
     std::vector<uint64_t> keys(P, KGPU_NO_FIT);
-    const int rc = sequential ? kgpu_place_batch(handle_, req.data(), (int64_t)P, keys.data())
-                              : kgpu_score_batch(handle_, req.data(), (int64_t)P, keys.data());
+    const int rc = mode == BatchMode::Snapshot ? kgpu_score_batch(handle_, req.data(), (int64_t)P, keys.data())
+                                               : kgpu_place_batch_ex(handle_, req.data(), (int64_t)P, keys.data(),
+                                                                     mode == BatchMode::DryRun ? KGPU_PLACE_DRY_RUN : 0);
     if (rc != KGPU_OK) return lastError_ = kgpu_last_error(handle_);
     out->assign(P, Placement());
     for (size_t p = 0; p < P; p++) {
@@ -564,26 +592,48 @@ std::string NvidiaGPUScheduler::runBatch(const std::vector<const types::PodInfo 
             pl.cost = KGPU_KEY_COST(keys[p]);
             pl.gpuMask = KGPU_KEY_MASK(keys[p]);
             pl.nodeName = indexToName_[KGPU_KEY_NODE(keys[p])];
-            if (sequential) nodes_[pl.nodeName].usedMask |= pl.gpuMask;     // the device already took them
+            if (mode == BatchMode::Sequential) {            // the device already took them: TakePodResources is a no-op
+                nodes_[pl.nodeName].usedMask |= pl.gpuMask;
+                pl.committed = true;
+            }
         }
         if (!pods[p]->Name.empty()) lastPlacement_[pods[p]->Name] = pl;
     }
     return "";
 }
 
+// Which registered node is this?  The reference passes only the NodeInfo: its Name, else the pointer AddNode saw.
+const NvidiaGPUScheduler::NodeRecord *NvidiaGPUScheduler::recordOf(const types::NodeInfo *nodeInfo) const {
+    const NodeRecord *rec = nullptr;
+    if (!nodeInfo->Name.empty()) rec = node(nodeInfo->Name);
+    if (!rec) {
+        auto byPtr = infoToName_.find(nodeInfo);
+        if (byPtr != infoToName_.end()) rec = node(byPtr->second);
+    }
+    return (rec && !rec->removed) ? rec : nullptr;
+}
+
+// (cost<<8 | mask) of this node for k GPUs: the handle's (node, k) fit table (a host read, no launch) unless the
+// pod carries a memory requirement (one packed query launch).
 std::string NvidiaGPUScheduler::scoreOne(const NodeRecord &rec, int k, int32_t minMemMiB, uint32_t *nodeKey) {
     std::string err = flushNodes();
     if (!err.empty()) return err;
-    const int64_t idx = rec.index;
     const int32_t kk = k > 8 ? 9 : k;
+    if (minMemMiB <= 0) {
+        if (kgpu_fit_lookup(handle_, rec.index, kk, nodeKey) != KGPU_OK) return lastError_ = kgpu_last_error(handle_);
+        return "";
+    }
+    const int64_t idx = rec.index;
     if (kgpu_score_pairs(handle_, &idx, &kk, &minMemMiB, 1, nodeKey) != KGPU_OK) return lastError_ = kgpu_last_error(handle_);
     return "";
 }
 
-// gpu_scheduler.go:34-44.  fits / reasons as the reference; `score` is the new part:
-// 1 / (1 + link cost of the cheapest k-subset of THIS node's free GPUs), 0 when the GPUs do
-// not fit.  Higher is better, 1.0 = all requested GPUs on zero-cost (NVLink) links.
-bool NvidiaGPUScheduler::PodFitsDevice(types::NodeInfo *nodeInfo, types::PodInfo *podInfo, bool /*fillAllocateFrom*/,
+// gpu_scheduler.go:34-44.  fits / reasons as the reference, PLUS the device's verdict for this node's current free
+// GPUs; `score` is the new part: 1 / (1 + link cost of the cheapest k-subset of THIS node's free GPUs), 0 when the
+// GPUs do not fit.  Higher is better, 1.0 = all requested GPUs on zero-cost (NVLink) links.  The fits decision
+// does not depend on whether the caller asked for a score, and a device error is a "does not fit" with a reason
+// (the reference collapses errors to false as well, gpu_scheduler.go:35-42), never a silent "fits, score 0".
+bool NvidiaGPUScheduler::PodFitsDevice(types::NodeInfo *nodeInfo, types::PodInfo *podInfo, bool fillAllocateFrom,
                                        std::vector<kubedevice::devicescheduler::PredicateFailureReason> *reasons,
                                        double *score) {
     if (reasons) reasons->clear();
@@ -591,41 +641,67 @@ bool NvidiaGPUScheduler::PodFitsDevice(types::NodeInfo *nodeInfo, types::PodInfo
     bool found = false;
     const std::string err = TranslatePodGPUResources(cache_, *nodeInfo, *podInfo, &found);
     if (!err.empty() || !found) return false;
-    if (!handle_ || !score) return true;                      // host-only mode: the reference's answer
-    // which registered node is this?  The reference passes only the NodeInfo: use its Name,
-    // else the pointer AddNode saw; unknown nodes keep the reference's 0.0.
-    const NodeRecord *rec = nullptr;
-    if (!nodeInfo->Name.empty()) rec = node(nodeInfo->Name);
-    if (!rec) {
-        auto byPtr = infoToName_.find(nodeInfo);
-        if (byPtr != infoToName_.end()) rec = node(byPtr->second);
-    }
-    if (rec && rec->removed) rec = nullptr;
-    if (!rec) return true;
+    if (!handle_) return true;                                // host-only mode: the reference's answer
+    const NodeRecord *rec = recordOf(nodeInfo);
+    if (!rec) return true;                                    // a node AddNode never saw: the reference's answer, score 0.0
     uint32_t nk = UINT32_MAX;
-    const int64_t need = getOr0(podInfo->Requests, GPUMinMemoryMiB);
-    if (!scoreOne(*rec, (int)PodGPUCount(*podInfo), (int32_t)std::max<int64_t>(0, std::min<int64_t>(need, std::numeric_limits<int32_t>::max())), &nk).empty()) return true;
-    if (nk == UINT32_MAX) return false;                        // topology-feasible shape exists, but not on this node now
-    *score = 1.0 / (1.0 + (double)(nk >> 8));
+    const std::string derr = scoreOne(*rec, (int)PodGPUCount(*podInfo), minMemOf(*podInfo), &nk);
+    if (!derr.empty()) {
+        if (reasons) reasons->push_back({"kgpu: " + derr});
+        return false;
+    }
+    if (nk == UINT32_MAX) {                                   // a feasible shape exists in the cache, but not on this node now
+        if (reasons) reasons->push_back({"kgpu: not enough free GPUs on " + rec->name});
+        return false;
+    }
+    if (score) *score = 1.0 / (1.0 + (double)(nk >> 8));
+    if (fillAllocateFrom && !groupSchedulerMode_ && !podInfo->Name.empty()) {
+        Placement pl;                                         // remember the per-node placement for PodAllocate
+        pl.fits = true;
+        pl.cost = nk >> 8;
+        pl.gpuMask = nk & 0xFFu;
+        pl.nodeName = rec->name;
+        pl.key = ((uint64_t)pl.cost << 40) | ((uint64_t)rec->index << 8) | pl.gpuMask;
+        lastPlacement_[podInfo->Name] = pl;
+    }
     return true;
 }
 
-// gpu_scheduler.go:46-55 plus SURVEY.md 8(f) rank 1: when the pod was placed by ScoreBatch on
-// this node, expand (node, mask) into AllocateFrom: request name -> the node's own resource
-// name, which the node agent's Allocate regex (nvidia_gpu_manager.go:225-241) turns into
-// NVIDIA_VISIBLE_DEVICES.  Containers take GPUs in sorted-name order, lowest slot first.
+// gpu_scheduler.go:46-55 plus SURVEY.md 8(f) rank 1: expand (node, mask) into AllocateFrom: request name -> the
+// node's own resource name, which the node agent's Allocate regex (nvidia_gpu_manager.go:225-241) turns into
+// NVIDIA_VISIBLE_DEVICES.  The placement is the one ScoreBatch / ProposeBatch / PlaceBatch / PodFitsDevice
+// recorded for this pod ON THIS NODE; without one it is computed now for this node.  Containers take GPUs in
+// sorted-name order, lowest slot first.  groupSchedulerMode: the reference's behaviour only (DevRequests).
 std::string NvidiaGPUScheduler::PodAllocate(types::NodeInfo *nodeInfo, types::PodInfo *podInfo) {
     bool found = false;
     const std::string err = TranslatePodGPUResources(cache_, *nodeInfo, *podInfo, &found);
     if (!err.empty()) return err;
     if (!found) return "TranslatePodGPUResources fails as no translation is found";
-    auto it = lastPlacement_.find(podInfo->Name);
-    if (podInfo->Name.empty() || it == lastPlacement_.end() || !it->second.fits) return "";
-    const NodeRecord *rec = node(it->second.nodeName);
+    if (groupSchedulerMode_ || !handle_) return "";
+    const NodeRecord *here = recordOf(nodeInfo);
+    Placement pl;
+    auto it = podInfo->Name.empty() ? lastPlacement_.end() : lastPlacement_.find(podInfo->Name);
+    if (it != lastPlacement_.end() && it->second.fits && (!here || here->name == it->second.nodeName)) {
+        pl = it->second;
+    } else if (here) {                                        // no placement recorded for this node: ask the device now
+        uint32_t nk = UINT32_MAX;
+        const std::string derr = scoreOne(*here, (int)PodGPUCount(*podInfo), minMemOf(*podInfo), &nk);
+        if (!derr.empty()) return derr;
+        if (nk == UINT32_MAX) return "PodAllocate: not enough free GPUs on " + here->name;
+        pl.fits = true;
+        pl.cost = nk >> 8;
+        pl.gpuMask = nk & 0xFFu;
+        pl.nodeName = here->name;
+        pl.key = ((uint64_t)pl.cost << 40) | ((uint64_t)here->index << 8) | pl.gpuMask;
+        if (!podInfo->Name.empty()) lastPlacement_[podInfo->Name] = pl;
+    } else {
+        return "";
+    }
+    const NodeRecord *rec = node(pl.nodeName);
     if (!rec) return "";
     std::vector<int> slotsLeft;
     for (int i = 0; i < 8; i++)
-        if ((it->second.gpuMask >> i) & 1u) slotsLeft.push_back(i);
+        if ((pl.gpuMask >> i) & 1u) slotsLeft.push_back(i);
     size_t next = 0;
     auto fill = [&](types::ContainerInfo &cont, size_t *cursor) {
         cont.AllocateFrom.clear();
@@ -646,38 +722,43 @@ std::string NvidiaGPUScheduler::PodAllocate(types::NodeInfo *nodeInfo, types::Po
     return "";
 }
 
-// gpu_scheduler.go:57-63 are no-ops in the reference (the core tracks usage).  Here they keep
-// the device-side free masks current for pods placed by ScoreBatch.
+std::string NvidiaGPUScheduler::pushMask(NodeRecord &rec) {
+    if (!handle_ || dirty_) return "";                        // host-only, or a re-upload is pending anyway
+    for (const std::string &c : changed_)
+        if (c == rec.name) return "";                         // kgpu_update_node will carry the mask
+    if (kgpu_set_free_mask(handle_, rec.index, (int32_t)(rec.removed ? 0 : (rec.presentMask & ~rec.usedMask))) != KGPU_OK)
+        return lastError_ = kgpu_last_error(handle_);
+    return "";
+}
+
+// gpu_scheduler.go:57-63 are no-ops in the reference (the core tracks usage).  Here they keep the device-side free
+// masks current.  Take is idempotent: a placement PlaceBatch already committed on the
+// device, or one taken before, succeeds without touching anything (callers of the reference never see an error
+// from these methods); GPUs that are in use by ANOTHER pod are an error -- the caller must re-score that pod.
 std::string NvidiaGPUScheduler::TakePodResources(types::NodeInfo * /*nodeInfo*/, types::PodInfo *podInfo) {
     auto it = lastPlacement_.find(podInfo->Name);
     if (podInfo->Name.empty() || it == lastPlacement_.end() || !it->second.fits) return "";
+    if (it->second.committed) return "";
     auto n = nodes_.find(it->second.nodeName);
     if (n == nodes_.end()) return "";
-    if (n->second.usedMask & it->second.gpuMask) return lastError_ = "TakePodResources: GPUs already in use on " + n->first;
+    if (n->second.usedMask & it->second.gpuMask)
+        return lastError_ = "TakePodResources: GPUs of pod " + podInfo->Name + " already in use on " + n->first + " (score the pod again)";
     n->second.usedMask |= it->second.gpuMask;
-    if (handle_ && !dirty_) {
-        if (kgpu_set_free_mask(handle_, n->second.index, (int32_t)(n->second.presentMask & ~n->second.usedMask)) != KGPU_OK)
-            return lastError_ = kgpu_last_error(handle_);
-    } else {
-        dirty_ = true;
-    }
-    return "";
+    it->second.committed = true;
+    return pushMask(n->second);
 }
 
 std::string NvidiaGPUScheduler::ReturnPodResources(types::NodeInfo * /*nodeInfo*/, types::PodInfo *podInfo) {
     auto it = lastPlacement_.find(podInfo->Name);
     if (podInfo->Name.empty() || it == lastPlacement_.end() || !it->second.fits) return "";
     auto n = nodes_.find(it->second.nodeName);
-    if (n == nodes_.end()) return "";
-    n->second.usedMask &= ~it->second.gpuMask;
-    if (handle_ && !dirty_) {
-        if (kgpu_set_free_mask(handle_, n->second.index, (int32_t)(n->second.presentMask & ~n->second.usedMask)) != KGPU_OK)
-            return lastError_ = kgpu_last_error(handle_);
-    } else {
-        dirty_ = true;
+    if (n == nodes_.end() || !it->second.committed) {          // never taken: just forget the proposal
+        lastPlacement_.erase(it);
+        return "";
     }
+    n->second.usedMask &= ~it->second.gpuMask;
     lastPlacement_.erase(it);
-    return "";
+    return pushMask(n->second);
 }
 
 std::unique_ptr<NvidiaGPUScheduler> CreateDeviceSchedulerPlugin(std::string *err) {

@@ -131,6 +131,7 @@ struct Placement {
     std::string nodeName;
     uint32_t gpuMask = 0;       // bit i = GPU slot i of that node
     uint64_t key = UINT64_MAX;  // raw (cost<<40 | node_id<<8 | mask)
+    bool committed = false;     // the GPUs are already taken on the device (PlaceBatch) / by TakePodResources
 };
 
 // ---- gpu_scheduler.go: the DeviceScheduler boundary ------------------------------------
@@ -138,7 +139,13 @@ class NvidiaGPUScheduler {
 public:
     // devices empty => host logic only (tree cache / translation); every scoring call
     // then fails loudly -- there is no CPU scorer in the product.
-    explicit NvidiaGPUScheduler(const std::vector<int> &devices = {0});
+    // groupSchedulerMode = false (default): the plugin's own (node, GPU set) is authoritative -- PodAllocate fills
+    //   AllocateFrom itself and UsingGroupScheduler() returns false, so the core does not run its group allocator
+    //   over the rewritten DevRequests a second time ("return false iff it fills AllocateFrom").
+    // groupSchedulerMode = true: the reference's contract (gpu_scheduler.go:69-71 returns true): PodAllocate only
+    //   rewrites DevRequests (ConvertToBestGPURequests), AllocateFrom is left to the core's group allocator, and
+    //   the GPU's score is advisory.
+    explicit NvidiaGPUScheduler(const std::vector<int> &devices = {0}, bool groupSchedulerMode = false);
     ~NvidiaGPUScheduler();
     NvidiaGPUScheduler(const NvidiaGPUScheduler &) = delete;
     NvidiaGPUScheduler &operator=(const NvidiaGPUScheduler &) = delete;
@@ -152,7 +159,7 @@ public:
     std::string TakePodResources(types::NodeInfo *nodeInfo, types::PodInfo *podInfo);
     std::string ReturnPodResources(types::NodeInfo *nodeInfo, types::PodInfo *podInfo);
     std::string GetName() const { return "nvidiagpu"; }
-    bool UsingGroupScheduler() const { return true; }
+    bool UsingGroupScheduler() const { return groupSchedulerMode_; }
 
     // Extensions (no reference counterpart).
     // Real NVML link matrix for a node (int32[8][8] row-major, levels 0..15) instead of the
@@ -169,6 +176,10 @@ public:
     // scored (K3).  The placements are remembered like ScoreBatch's and the usage is recorded, so a
     // later PodAllocate / ReturnPodResources works on them.
     std::string PlaceBatch(const std::vector<const types::PodInfo *> &pods, std::vector<Placement> *out);
+    // Conflict-free PROPOSALS for a whole cycle: like PlaceBatch (each pod sees the GPUs the pods before it would
+    // take) but on a scratch copy of the device state -- nothing is taken until TakePodResources commits a pod.
+    // This is the conflict resolution ScoreBatch lacks: its snapshot scores hand every pod of equal k the same GPUs.
+    std::string ProposeBatch(const std::vector<const types::PodInfo *> &pods, std::vector<Placement> *out);
     std::string LastError() const { return lastError_; }
     const TreeCache &cache() const { return cache_; }
     bool hasDevice() const { return handle_ != nullptr; }
@@ -192,14 +203,19 @@ private:
     std::string syncNode(const NodeRecord &rec);
     std::string flushNodes();
     std::string scoreOne(const NodeRecord &rec, int k, int32_t minMemMiB, uint32_t *nodeKey);
-    std::string runBatch(const std::vector<const types::PodInfo *> &pods, std::vector<Placement> *out, bool sequential);
+    enum class BatchMode { Snapshot, Sequential, DryRun };
+    std::string runBatch(const std::vector<const types::PodInfo *> &pods, std::vector<Placement> *out, BatchMode mode);
+    const NodeRecord *recordOf(const types::NodeInfo *nodeInfo) const;
+    std::string pushMask(NodeRecord &rec);
     TreeCache cache_;
     std::map<std::string, NodeRecord> nodes_;
     std::vector<std::string> indexToName_;
     std::map<std::string, Placement> lastPlacement_;   // pod name -> ScoreBatch result
     std::map<const types::NodeInfo *, std::string> infoToName_;   // AddNode's NodeInfo* -> node name
     kgpu_ctx *handle_ = nullptr;
-    bool dirty_ = false;                                // host node array newer than device copy
+    bool dirty_ = false;                                // node COUNT changed: the device array must be re-uploaded
+    std::vector<std::string> changed_;                  // existing nodes whose matrix / presence changed (kgpu_update_node)
+    bool groupSchedulerMode_ = false;
     std::string lastError_;
 };
 

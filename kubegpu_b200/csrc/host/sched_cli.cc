@@ -63,10 +63,12 @@ void dumpPod(const types::PodInfo &pod) {
 }  // namespace
 
 int main(int argc, char **argv) {
-    bool noDevice = false;
-    for (int i = 1; i < argc; i++)
+    bool noDevice = false, groupMode = false;
+    for (int i = 1; i < argc; i++) {
         if (std::string(argv[i]) == "--no-device") noDevice = true;
-    NvidiaGPUScheduler sched(noDevice ? std::vector<int>{} : std::vector<int>{0});
+        if (std::string(argv[i]) == "--group-scheduler") groupMode = true;      // the reference's contract: see device_scheduler.h
+    }
+    NvidiaGPUScheduler sched(noDevice ? std::vector<int>{} : std::vector<int>{0}, groupMode);
     if (!noDevice && !sched.hasDevice()) {
         fprintf(stderr, "kgpu_sched_cli: %s\n", sched.LastError().c_str());
         return 2;
@@ -168,13 +170,17 @@ int main(int argc, char **argv) {
             const std::string err = cmd == "take" ? sched.TakePodResources(nullptr, &g_pods[podName])
                                                   : sched.ReturnPodResources(nullptr, &g_pods[podName]);
             printf("  err=%s\n", err.c_str());
-        } else if (cmd == "scorebatch" || cmd == "placebatch") {
+        } else if (cmd == "using") {
+            printf("  UsingGroupScheduler=%d name=%s\n", sched.UsingGroupScheduler() ? 1 : 0, sched.GetName().c_str());
+        } else if (cmd == "scorebatch" || cmd == "placebatch" || cmd == "proposebatch") {
             std::vector<const types::PodInfo *> pods;
             std::string podName;
             while (in >> podName)
                 if (g_pods.count(podName)) pods.push_back(&g_pods[podName]);
             std::vector<Placement> out;
-            const std::string err = cmd == "placebatch" ? sched.PlaceBatch(pods, &out) : sched.ScoreBatch(pods, &out);
+            const std::string err = cmd == "placebatch"     ? sched.PlaceBatch(pods, &out)
+                                    : cmd == "proposebatch" ? sched.ProposeBatch(pods, &out)
+                                                            : sched.ScoreBatch(pods, &out);
             printf("  err=%s\n", err.c_str());
             for (size_t i = 0; i < out.size(); i++)
                 printf("  %s fits=%d cost=%u node=%s mask=0x%02x\n", pods[i]->Name.c_str(), out[i].fits ? 1 : 0, out[i].cost,

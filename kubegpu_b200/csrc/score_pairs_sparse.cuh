@@ -26,6 +26,7 @@ namespace kgpu {
 constexpr int SP_THREADS = KGPU_SP_THREADS;
 constexpr int SP_WARPS = SP_THREADS / 32;
 constexpr int SP_CHUNK = 512;       // pods per shared-memory chunk; sIdx packs (position | k << 9) in 16 bits
+static_assert(SP_CHUNK == 512, "sparse_work.h: kSparseChunk must equal SP_CHUNK");
 constexpr int SP_ROW = 29;          // padded row of 28 pair costs per lane in shared memory
 #ifndef KGPU_SP_MINBLOCKS
 #define KGPU_SP_MINBLOCKS 8          // 64 registers, no spills, 32 warps/SM (profiles/r01_k1s_sweep.txt)
@@ -311,6 +312,7 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
     __shared__ SpEnt sTab[SP_WARPS][SP_TAB];           // per warp, bucket order: multipliers | results
     __shared__ uint32_t sHotLo[SP_THREADS], sHotHi[SP_THREADS];   // position g -> byte (1 << GPU index), g = 0..3 | 4..7
     __shared__ int32_t sNode[SP_THREADS];              // slot -> node index (-1 = padding)
+    __shared__ unsigned long long sAcc[SP_POS];        // multi-tile items: running minimum per pod position across the tiles
 
     const int tid = threadIdx.x;
     SpEnt *const tab = sTab[tid >> 5];
@@ -319,11 +321,19 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
     // ---- staging: the node's compacted pair costs (7 x 16 B), permutation and free count ----------
     // which tile, which pods: a work item {tile, pod_begin, pod_end} of the host's list (sparse_work.h), or the
     // plain grid (tile = blockIdx.x, equal pod ranges along blockIdx.y) when there is no list
-    int64_t tile_index = blockIdx.x, p_begin = (int64_t)blockIdx.y * pods_per_split, p_end = min(P, p_begin + pods_per_split);
+    int64_t tile_first = blockIdx.x, p_begin = (int64_t)blockIdx.y * pods_per_split, p_end = min(P, p_begin + pods_per_split);
+    int ntiles = 1;
     if (work != nullptr) {
         const int4 item = __ldg(work + blockIdx.x);
-        tile_index = item.x; p_begin = item.y; p_end = item.z;
+        tile_first = item.x; p_begin = item.y; p_end = item.z; ntiles = item.w;
     }
+    // ntiles > 1 (few pods: p_end - p_begin <= SP_CHUNK, the host guarantees it): the block walks a run of tiles;
+    // the pods are sorted once (first tile), the per-pod minimum is carried in sAcc and flushed once at the end.
+    const bool multi = ntiles > 1;
+#pragma unroll 1
+    for (int tt = 0; tt < ntiles; tt++) {
+    const int64_t tile_index = tile_first + tt;
+    if (tt > 0) __syncthreads();                       // the previous tile's flush has read sNode / sHot*
     const int64_t slot = tile_index * SP_THREADS + tid;
     // the slot's record: seven coalesced 16-byte loads, issued before anything waits on them
     int4 rw[7];
@@ -369,6 +379,7 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
 
     for (int64_t c0 = p_begin; c0 < p_end; c0 += SP_CHUNK) {
         const int cn = (int)min((int64_t)SP_CHUNK, p_end - c0);
+        if (!multi || tt == 0) {                   // the chunk's pod sort (once per item when it walks several tiles)
         __syncthreads();
         if (tid < NB) sCnt[tid] = 0;
         __syncthreads();
@@ -401,6 +412,7 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
             const int b = sK[i];
             const int at = atomicAdd(&sCnt[b], 1);
             sIdx[at] = (uint16_t)i;
+            if (multi) sAcc[at] = ~0ull;
             // the per-pod multiplier: the pod's own k less what its bucket adds back (= 1 at run time)
             const int4 req = __ldg(pods4 + c0 + i);
             const uint32_t one = MEM ? (uint32_t)req.w : (uint32_t)(req.x - (b < 9 ? b - 1 : 0));
@@ -421,6 +433,7 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
             }
         }
         __syncthreads();
+        }   // pod sort
 
         sp_run_k<0, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[0], sOff[1]);
         sp_run_k<1, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[1], sOff[2]);
@@ -465,9 +478,21 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
                 t |= t >> 16;
                 const uint32_t S = (t | (t >> 8)) & 0xFFu;
                 const unsigned long long nid = (unsigned long long)(node_id_base + (long long)sNode[best_slot]);
-                atomicMin(&keys[c0 + sIdx[i]], ((unsigned long long)cost << 40) | (nid << 8) | S);
+                const unsigned long long key = ((unsigned long long)cost << 40) | (nid << 8) | S;
+                if (multi) sAcc[i] = min(sAcc[i], key);      // position i belongs to this thread for the whole item
+                else atomicMin(&keys[c0 + sIdx[i]], key);
+            }
+            if (multi) {                                     // the next tile starts from "no result" again
+#pragma unroll
+                for (int w = 0; w < SP_WARPS; w++) sTab[w][i / SP_GROUP].best[i % SP_GROUP] = INF32;
             }
         }
+    }
+    }   // tiles of the item
+    if (multi) {
+        const int served = sOff[9];
+        for (int i = tid; i < served; i += SP_THREADS)
+            if (sIdx[i] != SP_DUMMY && sAcc[i] != ~0ull) atomicMin(&keys[p_begin + sIdx[i]], sAcc[i]);
     }
 }
 

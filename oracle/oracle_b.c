@@ -303,3 +303,139 @@ void kgpu_oracle_place_batch(const int32_t *topo, int32_t *free_mask, int64_t N,
     }
     free(nb);
 }
+
+/* ---- fair CPU twins for the bench ("a CPU twin with the same two-level minima") ------------- */
+
+/* The nine node keys of one node from its 256-entry subset-cost table. */
+static void node_keys_from_table(const uint32_t *cost, unsigned fm, uint32_t *nk9)
+{
+    for (int k = 0; k <= 8; k++) nk9[k] = NODE_NO_FIT;
+    for (unsigned S = 0; S < 256; S++) {
+        if (S & ~fm) continue;
+        int k = __builtin_popcount(S);
+        uint32_t key = (cost[S] << 8) | S;
+        if (key < nk9[k]) nk9[k] = key;
+    }
+}
+
+/* Sequential placement with the SAME data structure as the GPU kernel K3 (place_sequential.cuh): node keys
+ * nb[9][N], minima per 128-node tile, minima per supertile of 32 tiles; per pod: scan the supertile minima,
+ * take the winner, re-enumerate that one node, refresh its tile and its supertile.  One thread (the chain is
+ * serial).  Same results as kgpu_oracle_place_batch (tests assert it). */
+void kgpu_oracle_place_batch_tiled(const int32_t *topo, int32_t *free_mask, int64_t N,
+                                   int64_t node_id_base, const int32_t *pods, int64_t P,
+                                   const int32_t *W, uint64_t *out_keys)
+{
+    const int64_t TILE = 128, SUP = 32;
+    const int64_t T = (N + TILE - 1) / TILE, ST = (T + SUP - 1) / SUP;
+    uint32_t *nb = (uint32_t *)malloc(sizeof(uint32_t) * 9 * (size_t)(T * TILE > 0 ? T * TILE : 1));
+    uint64_t *tb = (uint64_t *)malloc(sizeof(uint64_t) * 9 * (size_t)(T > 0 ? T : 1));
+    uint64_t *sb = (uint64_t *)malloc(sizeof(uint64_t) * 9 * (size_t)(ST > 0 ? ST : 1));
+    uint32_t cost[256], nk9[9];
+    for (int64_t i = 0; i < 9 * T * TILE; i++) nb[i] = NODE_NO_FIT;
+    for (int64_t n = 0; n < N; n++) {
+        build_cost_table(topo + 64 * n, W, cost);
+        node_keys_from_table(cost, (unsigned)free_mask[n] & 0xFFu, nk9);
+        for (int k = 0; k <= 8; k++) nb[(int64_t)k * T * TILE + n] = nk9[k];
+    }
+    for (int k = 0; k <= 8; k++) {
+        for (int64_t t = 0; t < T; t++) {
+            uint64_t b = KGPU_NO_FIT;
+            for (int64_t n = t * TILE; n < (t + 1) * TILE; n++) {
+                uint32_t v = nb[(int64_t)k * T * TILE + n];
+                if (v != NODE_NO_FIT) { uint64_t key = pod_key(v, (uint64_t)(node_id_base + n)); if (key < b) b = key; }
+            }
+            tb[(int64_t)k * T + t] = b;
+        }
+        for (int64_t s = 0; s < ST; s++) {
+            uint64_t b = KGPU_NO_FIT;
+            for (int64_t t = s * SUP; t < (s + 1) * SUP && t < T; t++)
+                if (tb[(int64_t)k * T + t] < b) b = tb[(int64_t)k * T + t];
+            sb[(int64_t)k * ST + s] = b;
+        }
+    }
+    for (int64_t p = 0; p < P; p++) {
+        int k = pods[4 * p];
+        out_keys[p] = KGPU_NO_FIT;
+        if (k < 0 || k > 8) continue;
+        uint64_t win = KGPU_NO_FIT;
+        for (int64_t s = 0; s < ST; s++)
+            if (sb[(int64_t)k * ST + s] < win) win = sb[(int64_t)k * ST + s];
+        out_keys[p] = win;
+        if (win == KGPU_NO_FIT || k == 0) continue;
+        const int64_t n = (int64_t)((win >> 8) & 0xFFFFFFFFu) - node_id_base;
+        free_mask[n] = (int32_t)(((uint32_t)free_mask[n] & 0xFFu) & ~(uint32_t)(win & 0xFFu));
+        build_cost_table(topo + 64 * n, W, cost);
+        node_keys_from_table(cost, (unsigned)free_mask[n] & 0xFFu, nk9);
+        const int64_t t = n / TILE, s = t / SUP;
+        for (int kk = 0; kk <= 8; kk++) {
+            nb[(int64_t)kk * T * TILE + n] = nk9[kk];
+            uint64_t b = KGPU_NO_FIT;
+            for (int64_t m = t * TILE; m < (t + 1) * TILE; m++) {
+                uint32_t v = nb[(int64_t)kk * T * TILE + m];
+                if (v != NODE_NO_FIT) { uint64_t key = pod_key(v, (uint64_t)(node_id_base + m)); if (key < b) b = key; }
+            }
+            tb[(int64_t)kk * T + t] = b;
+            b = KGPU_NO_FIT;
+            for (int64_t u = s * SUP; u < (s + 1) * SUP && u < T; u++)
+                if (tb[(int64_t)kk * T + u] < b) b = tb[(int64_t)kk * T + u];
+            sb[(int64_t)kk * ST + s] = b;
+        }
+    }
+    free(nb); free(tb); free(sb);
+}
+
+/* Snapshot scoring memoised by k (what the GPU's memo_by_k variant does): with no per-pod constraint a pod's
+ * key depends on the pod only through k, so best[k] over all nodes is computed once (threads split the nodes)
+ * and every pod reads best[k_p].  Pods with min_mem > 0 are not memoisable and are left KGPU_NO_FIT here. */
+struct memo_job {
+    const int32_t *topo, *free_mask, *W;
+    int64_t n0, n1, node_id_base;
+    uint64_t best[9];
+};
+
+static void *memo_worker(void *arg)
+{
+    struct memo_job *j = (struct memo_job *)arg;
+    uint32_t cost[256], nk9[9];
+    for (int k = 0; k <= 8; k++) j->best[k] = KGPU_NO_FIT;
+    for (int64_t n = j->n0; n < j->n1; n++) {
+        build_cost_table(j->topo + 64 * n, j->W, cost);
+        node_keys_from_table(cost, (unsigned)j->free_mask[n] & 0xFFu, nk9);
+        for (int k = 0; k <= 8; k++)
+            if (nk9[k] != NODE_NO_FIT) {
+                uint64_t key = pod_key(nk9[k], (uint64_t)(j->node_id_base + n));
+                if (key < j->best[k]) j->best[k] = key;
+            }
+    }
+    return NULL;
+}
+
+void kgpu_oracle_score_batch_memo(const int32_t *topo, const int32_t *free_mask, int64_t N,
+                                  int64_t node_id_base, const int32_t *pods, int64_t P,
+                                  const int32_t *W, uint64_t *out_keys, int nthreads)
+{
+    if (nthreads < 1) nthreads = 1;
+    if ((int64_t)nthreads > N) nthreads = N > 0 ? (int)N : 1;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
+    struct memo_job *jobs = (struct memo_job *)malloc(sizeof(struct memo_job) * (size_t)nthreads);
+    for (int t = 0; t < nthreads; t++) {
+        jobs[t].topo = topo; jobs[t].free_mask = free_mask; jobs[t].W = W;
+        jobs[t].n0 = N * t / nthreads; jobs[t].n1 = N * (t + 1) / nthreads; jobs[t].node_id_base = node_id_base;
+        if (t > 0) pthread_create(&th[t], NULL, memo_worker, &jobs[t]);
+    }
+    memo_worker(&jobs[0]);
+    uint64_t best[9];
+    for (int k = 0; k <= 8; k++) best[k] = jobs[0].best[k];
+    for (int t = 1; t < nthreads; t++) {
+        pthread_join(th[t], NULL);
+        for (int k = 0; k <= 8; k++)
+            if (jobs[t].best[k] < best[k]) best[k] = jobs[t].best[k];
+    }
+    for (int64_t p = 0; p < P; p++) {
+        int k = pods[4 * p];
+        out_keys[p] = (k >= 0 && k <= 8 && pods[4 * p + 3] <= 0) ? best[k] : KGPU_NO_FIT;
+    }
+    free(th);
+    free(jobs);
+}

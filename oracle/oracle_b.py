@@ -59,7 +59,10 @@ def lib() -> ctypes.CDLL:
         L.kgpu_oracle_score_batch_fast_mem.restype = None
         L.kgpu_oracle_score_batch_fast_mem.argtypes = [i32p, i32p, i32p, ctypes.c_int64, ctypes.c_int64, i32p,
                                                        ctypes.c_int64, i32p, u64p, ctypes.c_int]
-        for fn in (L.kgpu_oracle_place_batch, L.kgpu_oracle_place_batch_plain):
+        L.kgpu_oracle_score_batch_memo.restype = None
+        L.kgpu_oracle_score_batch_memo.argtypes = [i32p, i32p, ctypes.c_int64, ctypes.c_int64, i32p,
+                                                   ctypes.c_int64, i32p, u64p, ctypes.c_int]
+        for fn in (L.kgpu_oracle_place_batch, L.kgpu_oracle_place_batch_plain, L.kgpu_oracle_place_batch_tiled):
             fn.restype = None
             fn.argtypes = [i32p, i32p, ctypes.c_int64, ctypes.c_int64, i32p, ctypes.c_int64, i32p, u64p]
         L.kgpu_oracle_place_batch_mem.restype = None
@@ -110,9 +113,21 @@ def score_batch(topo, free_mask, pods, W=DEFAULT_WEIGHTS, node_id_base: int = 0,
     return out
 
 
-def place_batch(topo, free_mask, pods, W=DEFAULT_WEIGHTS, node_id_base: int = 0, plain: bool = False, mem=None):
+def score_batch_memo(topo, free_mask, pods, W=DEFAULT_WEIGHTS, node_id_base: int = 0, nthreads: int = 1) -> np.ndarray:
+    """Snapshot scoring memoised by k (the CPU twin of the GPU's memo_by_k variant): best[k] over all nodes once,
+    every pod reads best[k_p].  Pods with min_mem > 0 are not memoisable (NO_FIT here)."""
+    topo, free_mask, pods, W = _i32(topo), _i32(free_mask), _i32(pods), _i32(W)
+    N, P = free_mask.shape[0], pods.shape[0]
+    out = np.empty(P, dtype=np.uint64)
+    lib().kgpu_oracle_score_batch_memo(_p(topo, ctypes.c_int32), _p(free_mask, ctypes.c_int32), N, int(node_id_base),
+                                       _p(pods, ctypes.c_int32), P, _p(W, ctypes.c_int32), _p(out, ctypes.c_uint64), int(nthreads))
+    return out
+
+
+def place_batch(topo, free_mask, pods, W=DEFAULT_WEIGHTS, node_id_base: int = 0, plain: bool = False, mem=None, tiled: bool = False):
     """K3 twin: sequential stateful placement.  Returns (keys[P], free_mask_after[N]).  With mem[N,8]
-    the pods' min_mem (pods[:,3]) is honoured (plain loop)."""
+    the pods' min_mem (pods[:,3]) is honoured (plain loop).  tiled: the same two-level minima as the GPU
+    kernel (the fair single-thread CPU baseline of the sequential path)."""
     topo, pods, W = _i32(topo), _i32(pods), _i32(W)
     free_after = np.array(free_mask, dtype=np.int32, copy=True)
     N, P = free_after.shape[0], pods.shape[0]
@@ -124,7 +139,7 @@ def place_batch(topo, free_mask, pods, W=DEFAULT_WEIGHTS, node_id_base: int = 0,
                                           int(node_id_base), _p(pods, ctypes.c_int32), P, _p(W, ctypes.c_int32),
                                           _p(out, ctypes.c_uint64))
         return out, free_after
-    fn = lib().kgpu_oracle_place_batch_plain if plain else lib().kgpu_oracle_place_batch
+    fn = lib().kgpu_oracle_place_batch_plain if plain else lib().kgpu_oracle_place_batch_tiled if tiled else lib().kgpu_oracle_place_batch
     fn(_p(topo, ctypes.c_int32), _p(free_after, ctypes.c_int32), N, int(node_id_base), _p(pods, ctypes.c_int32), P,
        _p(W, ctypes.c_int32), _p(out, ctypes.c_uint64))
     return out, free_after

@@ -193,11 +193,17 @@ void emu_push_and_sync(const unsigned long long *local, int64_t P, unsigned long
     emu::launch(dim3((unsigned)((P + 255) / 256)), dim3(256), [&] { kgpu::push_and_sync(local, P, tab, 0, 1, epoch, ticket); });
 }
 
-// The host-side work-list builder alone (sparse_work.h): items as int32[.][4], returns the count.
-int64_t emu_sparse_work(const uint8_t *tile_class, int64_t tiles, int64_t P, int64_t resident, int32_t *out, int64_t cap) {
+// The host-side work-list builder alone (sparse_work.h): items as int32[.][4] {tile, pod_begin, pod_end, ntiles} and
+// their model weights, returns the count.
+int64_t emu_sparse_work(const uint8_t *tile_class, int64_t tiles, int64_t P, int64_t resident, int32_t *out, int64_t cap,
+                        long long *weight_out) {
     std::vector<kgpu::SparseWorkItem> items;
-    kgpu::build_sparse_work(std::vector<uint8_t>(tile_class, tile_class + tiles), P, resident, items);
-    for (size_t i = 0; i < items.size() && (int64_t)i < cap; i++) std::memcpy(out + 4 * i, &items[i], 16);
+    std::vector<int64_t> weight;
+    kgpu::build_sparse_work(std::vector<uint8_t>(tile_class, tile_class + tiles), P, resident, items, kgpu::SparseWorkParams(), &weight);
+    for (size_t i = 0; i < items.size() && (int64_t)i < cap; i++) {
+        std::memcpy(out + 4 * i, &items[i], 16);
+        weight_out[i] = weight[i];
+    }
     return (int64_t)items.size();
 }
 

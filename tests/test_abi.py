@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(built_lib):
 
 def test_version_and_error_path_without_device(built_lib):
     L = _lib.load()
-    assert L.kgpu_version().decode() == "0.1.0"
+    assert L.kgpu_version().decode() == "0.2.0"
     # bad arguments are rejected before any CUDA call
     h = ctypes.c_void_p()
     assert L.kgpu_create(None, 0, ctypes.byref(h)) == _lib.ERR_INVALID

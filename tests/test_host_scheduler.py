@@ -296,7 +296,7 @@ def test_score_batch_allocate_take_return_on_gpu(cli, oracle_b):
     for node, pod, k in (("A", "p4", 4), ("B", "p4", 4), ("C", "p4", 4), ("C", "p2", 2)):
         line = got.split("> fits %s %s\n" % (node, pod))[1].splitlines()[0]
         s = score_of(names.index(node), k)
-        assert line == ("  fits=0 reasons=0 score=0" if s is None else "  fits=1 reasons=0 score=%.17g" % s)
+        assert line == ("  fits=0 reasons=1 score=0" if s is None else "  fits=1 reasons=0 score=%.17g" % s)
     # PodAllocate after ScoreBatch: p3 (k=3) was placed on B's 4-group, slots 0,1,2 -> real GPU ids
     alloc = got.split("> allocate B p3\n")[1].split("> take")[0]
     assert "err=\n" in alloc
@@ -381,3 +381,67 @@ def test_host_memory_constraint_and_place_batch(cli, golden_dir, tmp_path, oracl
     assert after[1] == "  small fits=0 cost=0 node= mask=0x00"          # the cluster is full now
     alloc = got.split("> allocate B q1\n")[1]
     assert alloc.count("from ") == 4 and "/gpu/" in alloc
+
+
+@pytest.mark.gpu
+def test_take_is_idempotent_and_propose_batch_resolves_conflicts(cli, oracle_b):
+    """ADVICE r1 (device_scheduler.cc): (1) PlaceBatch already took the GPUs on the device, the TakePodResources the
+    DeviceScheduler contract makes next must succeed; (2) ScoreBatch is snapshot scoring -- pods of equal k get the
+    same GPUs and only the first Take can succeed; ProposeBatch hands out conflict-free proposals instead (the
+    sequential placement run on a scratch copy of the device state), every Take succeeds and the state after the
+    Takes equals the sequential oracle's."""
+    from kubegpu_b200 import synth
+    ids = ["GPU-%02d" % i for i in range(8)]
+    script = "\n".join([
+        node_line("A", [[2, 2], [2, 2]], ids=ids), node_line("B", [[4], [2, 2]], ids=ids),
+        "pod a1 run a req=2", "pod a2 run a req=2", "pod a3 run a req=2", "pod a4 run a req=4", "pod a5 run a req=4",
+        "using",
+        "scorebatch a1 a2", "take a1", "take a2",                    # snapshot: the same GPUs twice -> second Take refused
+        "return a1", "return a2",
+        "proposebatch a1 a2 a3 a4 a5", "scorebatch a4",              # proposals take nothing: a4 still sees a free cluster
+        "take a1", "take a2", "take a3", "take a4", "take a5", "take a1",
+        "scorebatch a4", "allocate A a1",
+        "placebatch a3", "take a3",
+    ]) + "\n"
+    got = run_cli(cli, script, device=True)
+    assert got.split("> using\n")[1].splitlines()[0] == "  UsingGroupScheduler=0 name=nvidiagpu"
+    snap = got.split("> scorebatch a1 a2\n")[1].splitlines()
+    assert snap[1].split("fits=1")[1] == snap[2].split("fits=1")[1]            # identical (node, mask)
+    t = got.split("> take a1\n")[1].splitlines()
+    assert t[0] == "  err=" and "already in use" in got.split("> take a2\n")[1].splitlines()[0]
+    tA, tB = synth.shape_matrix([[2, 2], [2, 2]]), synth.shape_matrix([[4], [2, 2]])
+    topo, free = np.stack([tA, tB]), np.array([0xFF, 0xFF], np.int32)
+    pods = synth.make_pods(np.array([2, 2, 2, 4, 4], np.int32))
+    want, wf = oracle_b.place_batch(topo, free, pods)
+    names = ["A", "B"]
+    prop = got.split("> proposebatch a1 a2 a3 a4 a5\n")[1].splitlines()
+    assert prop[0] == "  err="
+    for line, pod, key in zip(prop[1:6], ["a1", "a2", "a3", "a4", "a5"], want):
+        u = oracle_b.unpack_key(key)
+        assert line == "  %s fits=1 cost=%d node=%s mask=0x%02x" % (pod, u[0], names[u[1]], u[2])
+    k4 = oracle_b.unpack_key(oracle_b.score_batch(topo, free, synth.make_pods(np.array([4], np.int32)))[0])
+    assert got.split("> scorebatch a4\n")[1].splitlines()[1] == "  a4 fits=1 cost=%d node=%s mask=0x%02x" % (k4[0], names[k4[1]], k4[2])
+    takes = got.split("> proposebatch")[1].split("> take ")[1:7]
+    assert all(blk.splitlines()[1] == "  err=" for blk in takes)              # a1..a5, and a1 again (idempotent)
+    after = oracle_b.score_batch(topo, wf, synth.make_pods(np.array([4], np.int32)))[0]
+    line = got.split("> scorebatch a4\n")[2].splitlines()[1]
+    u = oracle_b.unpack_key(after)
+    assert line == ("  a4 fits=0 cost=0 node= mask=0x00" if u is None else "  a4 fits=1 cost=%d node=%s mask=0x%02x" % (u[0], names[u[1]], u[2]))
+    alloc = got.split("> allocate A a1\n")[1].split("> placebatch")[0]
+    u1 = oracle_b.unpack_key(want[0])
+    froms = [ln.strip() for ln in alloc.splitlines() if ln.strip().startswith("from")]
+    assert len(froms) == 2 and {f.split("/gpu/")[-1].split("/")[0] for f in froms} == {"GPU-%02d" % i for i in range(8) if (u1[2] >> i) & 1}
+    tail = got.split("> placebatch a3\n")[1]
+    assert tail.splitlines()[0] == "  err=" and tail.split("> take a3\n")[1].splitlines()[0] == "  err="
+
+
+@pytest.mark.gpu
+def test_group_scheduler_mode_is_the_reference_contract(cli):
+    """--group-scheduler: UsingGroupScheduler() == true like gpu_scheduler.go:69-71, PodAllocate only rewrites
+    DevRequests and leaves AllocateFrom to the core's group allocator."""
+    script = "\n".join([node_line("A", [[2, 2], [2, 2]]), "pod p run a req=2", "using", "scorebatch p", "allocate A p"]) + "\n"
+    import subprocess
+    got = subprocess.run([cli, "--group-scheduler"], input=script, capture_output=True, text=True, check=True).stdout
+    assert got.split("> using\n")[1].splitlines()[0] == "  UsingGroupScheduler=1 name=nvidiagpu"
+    alloc = got.split("> allocate A p\n")[1]
+    assert "err=\n" in alloc and "from " not in alloc and "/gpugrp1/0/gpugrp0/0/gpu/" in alloc

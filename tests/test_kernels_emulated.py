@@ -187,23 +187,35 @@ def test_emulated_sparse_work_list(emu, oracle_b):
         assert (_run(emu.emu_score_sparse, topo, free, pods, W, mem=mem, base=4, splits=-resident) == want).all(), resident
 
 
-@pytest.mark.parametrize("P", [1, 31, 32, 1000, 10_000])
-@pytest.mark.parametrize("resident", [1, 1184])
-def test_sparse_work_list_partitions_every_tile(emu, P, resident):
+@pytest.mark.parametrize("P", [1, 31, 32, 512, 513, 1000, 10_000])
+@pytest.mark.parametrize("resident", [1, 16, 1184])
+def test_sparse_work_list_partitions_the_tile_pod_plane(emu, P, resident):
+    """Every (tile, pod) cell is covered exactly once; items come heaviest first; pod ranges start on multiples of
+    32; runs of several tiles only when the whole batch fits one chunk of the block's pod sort."""
     emu.emu_sparse_work.restype = ctypes.c_int64
     rng = np.random.default_rng(P + resident)
-    tile_class = rng.integers(0, 9, size=57).astype(np.uint8)
+    ntile = 57 if P > 512 else 700
+    tile_class = np.sort(rng.integers(0, 9, size=ntile).astype(np.uint8))[::-1].copy()      # the order puts class 8 first
     out = np.zeros((200_000, 4), dtype=np.int32)
-    n = emu.emu_sparse_work(_p(tile_class, ctypes.c_uint8), ctypes.c_int64(57), ctypes.c_int64(P), ctypes.c_int64(resident),
-                            _p(out), ctypes.c_int64(len(out)))
-    items = out[:n]
-    assert 57 <= n <= len(out)
-    assert (np.diff(items[:, 3]) <= 0).all()                     # heaviest first
-    for t in range(57):
-        mine = items[items[:, 0] == t]
-        mine = mine[np.argsort(mine[:, 1])]
-        assert mine[0, 1] == 0 and mine[-1, 2] == P and (mine[1:, 1] == mine[:-1, 2]).all()   # a partition of [0, P)
-        assert (mine[:, 1] % 32 == 0).all() and (mine[:, 2] > mine[:, 1]).all()
+    weight = np.zeros(200_000, dtype=np.int64)
+    n = emu.emu_sparse_work(_p(tile_class, ctypes.c_uint8), ctypes.c_int64(ntile), ctypes.c_int64(P), ctypes.c_int64(resident),
+                            _p(out), ctypes.c_int64(len(out)), _p(weight, ctypes.c_longlong))
+    items, weight = out[:n], weight[:n]
+    assert 1 <= n <= len(out)
+    assert (np.diff(weight) <= 0).all() and (weight > 0).all()                     # heaviest first
+    assert (items[:, 3] >= 1).all()
+    if P > 512:
+        assert (items[:, 3] == 1).all()
+    else:
+        assert ((items[:, 1] == 0) & (items[:, 2] == P)).all()                     # runs carry the whole (one-chunk) batch
+        assert items[:, 3].max() <= 64
+        if resident == 1:
+            assert items[:, 3].max() > 1                                           # few resident blocks: tiles are grouped
+    cover = np.zeros((ntile, P), dtype=np.int32)
+    for t, b, e, nt in items:
+        assert b % 32 == 0 and e > b and 0 <= t and t + nt <= ntile
+        cover[t:t + nt, b:e] += 1
+    assert (cover == 1).all()
 
 
 def test_emulated_sparse_single_class_tiles(emu, oracle_b):
@@ -340,3 +352,24 @@ def test_emulated_validate_topo(emu):
     topo[40, 9] = 16
     topo[77, 3] = -1
     assert emu.emu_validate_topo(_p(topo), ctypes.c_int64(100)) == 40 * 64 + 9
+
+
+@pytest.mark.parametrize("resident", [1, 3])
+def test_emulated_multi_tile_items_few_pods(emu, oracle_b, resident):
+    """Few pods (one chunk): a block walks a RUN of tiles, sorts the pods once, carries the per-pod minimum in
+    shared memory and flushes once.  Cost ties across tiles must still go to the lower node id, winners move
+    between tiles, invalid k and memory-constrained pods ride along."""
+    W = oracle_b.DEFAULT_WEIGHTS
+    topo, free, pods = synth.gen_c2(N=1500, P=40)            # few shapes: ties across tiles are the rule
+    pods[3, 0], pods[4, 0] = 0, 9
+    for trial in range(3):
+        want = oracle_b.score_batch(topo, free, pods, W, node_id_base=7)
+        assert (_run(emu.emu_score_sparse, topo, free, pods, W, base=7, splits=-resident) == want).all(), trial
+        for key in want:                                      # take the winners away: the next trial finds others
+            if key != np.uint64(0xFFFFFFFFFFFFFFFF):
+                free[(int(key >> np.uint64(8)) & 0xFFFFFFFF) - 7] = 0
+    topo, free, mem, pods = synth.gen_c6(N=900, P=33)
+    want = oracle_b.score_batch(topo, free, pods, mem=mem)
+    assert (_run(emu.emu_score_sparse, topo, free, pods, W, mem=mem, splits=-resident) == want).all()
+    p1 = synth.make_pods(np.array([3], dtype=np.int32))       # a single pod
+    assert (_run(emu.emu_score_sparse, topo, free, p1, W, splits=-resident) == oracle_b.score_batch(topo, free, p1, W)).all()

@@ -139,3 +139,17 @@ def test_freeing_gpus_never_hurts_and_monotone_in_k(oracle_b):
                 assert b != ob.NODE_NO_FIT and (b >> 8) <= (a >> 8)
         costs = [ob.node_key(M, more, k) >> 8 for k in range(1, bin(more).count("1") + 1)]
         assert costs == sorted(costs)                # with non-negative weights a bigger set never costs less
+
+
+def test_cpu_twins_for_the_bench_agree_with_the_plain_oracle(oracle_b):
+    """The fair CPU baselines bench.py times next to the GPU (two-level-minima sequential placement, k-memoised
+    snapshot scoring) give the plain oracle's bits."""
+    for gen, n, p in ((synth.gen_c2, 5000, 700), (synth.gen_c4, 4133, 500), (synth.gen_c2, 100, 300)):
+        topo, free, pods = gen(N=n, P=p)
+        pods[3, 0], pods[4, 0] = 0, 9
+        want, wf = oracle_b.place_batch(topo, free, pods, node_id_base=5)
+        got, gf = oracle_b.place_batch(topo, free, pods, node_id_base=5, tiled=True)
+        assert (got == want).all() and (gf == wf).all()
+        for nt in (1, 3):
+            assert (oracle_b.score_batch_memo(topo, free, pods, node_id_base=5, nthreads=nt)
+                    == oracle_b.score_batch(topo, free, pods, node_id_base=5, fast=True, nthreads=2)).all()
