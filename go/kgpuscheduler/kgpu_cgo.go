@@ -63,6 +63,28 @@ func (k *handle) setFreeMask(idx int64, free int32) error {
 	return nil
 }
 
+// setFreeMasks: a cycle's Take/Return in ONE call (one H2D copy + one kernel on the device).
+func (k *handle) setFreeMasks(idx []int64, free []int32) error {
+	if len(idx) == 0 {
+		return nil
+	}
+	if rc := C.kgpu_set_free_masks(k.h, (*C.int64_t)(unsafe.Pointer(&idx[0])), (*C.int32_t)(unsafe.Pointer(&free[0])),
+		C.int64_t(len(idx))); rc != C.KGPU_OK {
+		return k.err("kgpu_set_free_masks")
+	}
+	return nil
+}
+
+// fitLookup: (cost<<8 | mask) of one node for one GPU count from the handle's host-side (node, k)
+// table -- no launch, no copy: this is what PodFitsDevice calls once per (node, pod) pair.
+func (k *handle) fitLookup(node int64, gpus int32) (uint32, error) {
+	var out C.uint32_t
+	if rc := C.kgpu_fit_lookup(k.h, C.int64_t(node), C.int32_t(gpus), &out); rc != C.KGPU_OK {
+		return 0, k.err("kgpu_fit_lookup")
+	}
+	return uint32(out), nil
+}
+
 // scoreBatch: pods is P*4 int32 {k, pod_id, flags, reserved}; returns P keys
 // (cost<<40 | node<<8 | mask) or NoFit.
 func (k *handle) scoreBatch(pods []int32) ([]uint64, error) {
@@ -88,15 +110,20 @@ func (k *handle) scorePair(node int64, gpus int32) (uint32, error) {
 }
 
 // placeBatch: stateful sequential placement (pods in order, the device-side free masks are
-// updated).  Same buffers as scoreBatch.
-func (k *handle) placeBatch(pods []int32) ([]uint64, error) {
+// updated).  dryRun: conflict-free proposals on a scratch copy of the masks, nothing is taken.
+// Same buffers as scoreBatch.
+func (k *handle) placeBatch(pods []int32, dryRun bool) ([]uint64, error) {
 	keys := make([]uint64, len(pods)/4)
 	if len(keys) == 0 {
 		return keys, nil
 	}
-	if rc := C.kgpu_place_batch(k.h, (*C.int32_t)(unsafe.Pointer(&pods[0])), C.int64_t(len(keys)),
-		(*C.uint64_t)(unsafe.Pointer(&keys[0]))); rc != C.KGPU_OK {
-		return nil, k.err("kgpu_place_batch")
+	flags := C.int(0)
+	if dryRun {
+		flags = C.KGPU_PLACE_DRY_RUN
+	}
+	if rc := C.kgpu_place_batch_ex(k.h, (*C.int32_t)(unsafe.Pointer(&pods[0])), C.int64_t(len(keys)),
+		(*C.uint64_t)(unsafe.Pointer(&keys[0])), flags); rc != C.KGPU_OK {
+		return nil, k.err("kgpu_place_batch_ex")
 	}
 	return keys, nil
 }

@@ -18,6 +18,10 @@ import (
 
 var gpuKey = regexp.MustCompile(string(types.DeviceGroupPrefix) + `/(gpugrp1/(.*?)/gpugrp0/(.*?)/gpu/(.*?))/cards`)
 
+// a DevRequests key that names one GPU card (compiled ONCE: the reference compiles its regexps per call,
+// gpu.go:131, which is the per-call cost SURVEY.md 3 criticises)
+var gpuCardReq = regexp.MustCompile(`/gpu/.*/cards$`)
+
 type nodeRec struct {
 	index   int64
 	names   []string // slot -> "gpugrp1/a/gpugrp0/b/gpu/<id>"
@@ -28,9 +32,10 @@ type nodeRec struct {
 }
 
 type placement struct {
-	node string
-	mask uint32
-	cost uint32
+	node      string
+	mask      uint32
+	cost      uint32
+	committed bool // the GPUs are already taken on the device (PlaceBatch) or by TakePodResources
 }
 
 // NvidiaGPUScheduler implements devicescheduler.DeviceScheduler.
@@ -39,8 +44,13 @@ type NvidiaGPUScheduler struct {
 	h      *handle
 	nodes  map[string]*nodeRec
 	byIdx  []string
-	dirty  bool
-	placed map[string]placement // pod name -> last ScoreBatch result
+	dirty   bool            // node COUNT changed: re-upload
+	changed map[string]bool // existing nodes whose matrix / presence changed: kgpu_update_node each
+	placed  map[string]placement // pod name -> last placement
+	// GroupSchedulerMode false (default): the plugin's (node, GPU set) is authoritative: PodAllocate fills
+	// AllocateFrom and UsingGroupScheduler() returns false.  true: the reference's contract
+	// (gpu_scheduler.go:69-71): DevRequests only, the core's group allocator does the rest.
+	GroupSchedulerMode bool
 }
 
 // New creates the scheduler on the given CUDA devices (one handle shards over all of them).
@@ -49,7 +59,7 @@ func New(devs []int32) (*NvidiaGPUScheduler, error) {
 	if err != nil {
 		return nil, err
 	}
-	return &NvidiaGPUScheduler{h: h, nodes: map[string]*nodeRec{}, placed: map[string]placement{}}, nil
+	return &NvidiaGPUScheduler{h: h, nodes: map[string]*nodeRec{}, changed: map[string]bool{}, placed: map[string]placement{}}, nil
 }
 
 func level(a, b []string) int32 { // same gpugrp0 -> 5, same gpugrp1 -> 3, else 1
@@ -82,6 +92,9 @@ func (ns *NvidiaGPUScheduler) AddNode(nodeName string, nodeInfo *types.NodeInfo)
 		rec = &nodeRec{index: int64(len(ns.byIdx))}
 		ns.nodes[nodeName] = rec
 		ns.byIdx = append(ns.byIdx, nodeName)
+		ns.dirty = true
+	} else {
+		ns.changed[nodeName] = true
 	}
 	rec.removed, rec.names, rec.topo = false, nil, [64]int32{}
 	for i, a := range slots {
@@ -93,7 +106,6 @@ func (ns *NvidiaGPUScheduler) AddNode(nodeName string, nodeInfo *types.NodeInfo)
 		}
 	}
 	rec.present = uint32(1)<<uint(len(slots)) - 1
-	ns.dirty = true
 }
 
 func (ns *NvidiaGPUScheduler) RemoveNode(nodeName string) {
@@ -101,14 +113,31 @@ func (ns *NvidiaGPUScheduler) RemoveNode(nodeName string) {
 	ns.mu.Lock()
 	defer ns.mu.Unlock()
 	if rec, ok := ns.nodes[nodeName]; ok {
-		rec.removed, ns.dirty = true, true
+		rec.removed = true
+		ns.changed[nodeName] = true
 	}
+}
+
+func freeOf(rec *nodeRec) int32 {
+	if rec.removed {
+		return 0
+	}
+	return int32(rec.present &^ rec.used)
 }
 
 func (ns *NvidiaGPUScheduler) flush() error {
 	if !ns.dirty {
+		// only existing nodes changed: one 256-byte update each instead of re-uploading the cluster
+		for name := range ns.changed {
+			rec := ns.nodes[name]
+			if err := ns.h.updateNode(rec.index, &rec.topo, freeOf(rec)); err != nil {
+				return err
+			}
+		}
+		ns.changed = map[string]bool{}
 		return nil
 	}
+	ns.changed = map[string]bool{}
 	topo := make([]int32, 64*len(ns.byIdx))
 	free := make([]int32, len(ns.byIdx))
 	for i, name := range ns.byIdx {
@@ -141,8 +170,7 @@ func podGPUs(podInfo *types.PodInfo) int32 { // gpu.go:295-303
 	return int32(n)
 }
 
-// ScoreBatch is the batched side door: one kernel launch for a whole scheduling cycle.
-func (ns *NvidiaGPUScheduler) ScoreBatch(pods []*types.PodInfo) ([]uint64, error) {
+func (ns *NvidiaGPUScheduler) runBatch(pods []*types.PodInfo, mode int) ([]uint64, error) { // 0 snapshot, 1 sequential, 2 dry run
 	ns.mu.Lock()
 	defer ns.mu.Unlock()
 	if err := ns.flush(); err != nil {
@@ -152,16 +180,47 @@ func (ns *NvidiaGPUScheduler) ScoreBatch(pods []*types.PodInfo) ([]uint64, error
 	for i, p := range pods {
 		req[4*i], req[4*i+1] = podGPUs(p), int32(i)
 	}
-	keys, err := ns.h.scoreBatch(req)
+	var keys []uint64
+	var err error
+	if mode == 0 {
+		keys, err = ns.h.scoreBatch(req)
+	} else {
+		keys, err = ns.h.placeBatch(req, mode == 2)
+	}
 	if err != nil {
 		return nil, err
 	}
 	for i, p := range pods {
-		if keys[i] != NoFit {
-			ns.placed[p.Name] = placement{ns.byIdx[(keys[i]>>8)&0xFFFFFFFF], uint32(keys[i] & 0xFF), uint32(keys[i] >> 40)}
+		if keys[i] == NoFit {
+			delete(ns.placed, p.Name)
+			continue
 		}
+		pl := placement{ns.byIdx[(keys[i]>>8)&0xFFFFFFFF], uint32(keys[i] & 0xFF), uint32(keys[i] >> 40), mode == 1}
+		if mode == 1 { // the device already took them: TakePodResources is a no-op
+			ns.nodes[pl.node].used |= pl.mask
+		}
+		ns.placed[p.Name] = pl
 	}
 	return keys, nil
+}
+
+// ScoreBatch is the batched side door: one kernel launch for a whole scheduling cycle (snapshot scores:
+// pods of equal k get the same GPUs -- commit one, re-score the rest, or use ProposeBatch).
+func (ns *NvidiaGPUScheduler) ScoreBatch(pods []*types.PodInfo) ([]uint64, error) { return ns.runBatch(pods, 0) }
+
+// PlaceBatch places the cycle in order ON the device: each pod takes its GPUs before the next is scored.
+func (ns *NvidiaGPUScheduler) PlaceBatch(pods []*types.PodInfo) ([]uint64, error) { return ns.runBatch(pods, 1) }
+
+// ProposeBatch: conflict-free proposals (PlaceBatch on a scratch copy of the device state); TakePodResources
+// commits a pod.
+func (ns *NvidiaGPUScheduler) ProposeBatch(pods []*types.PodInfo) ([]uint64, error) { return ns.runBatch(pods, 2) }
+
+// nodeKey: (cost<<8 | mask) of this node for the pod, from the (node, k) fit table (no launch per call).
+func (ns *NvidiaGPUScheduler) nodeKey(rec *nodeRec, podInfo *types.PodInfo) (uint32, error) {
+	if err := ns.flush(); err != nil {
+		return 0, err
+	}
+	return ns.h.fitLookup(rec.index, podGPUs(podInfo))
 }
 
 func (ns *NvidiaGPUScheduler) PodFitsDevice(nodeInfo *types.NodeInfo, podInfo *types.PodInfo, fillAllocateFrom bool) (bool, []devicescheduler.PredicateFailureReason, float64) {
@@ -171,16 +230,16 @@ func (ns *NvidiaGPUScheduler) PodFitsDevice(nodeInfo *types.NodeInfo, podInfo *t
 	}
 	ns.mu.Lock()
 	defer ns.mu.Unlock()
-	rec, ok := ns.nodes[nodeInfo.Name]
-	if !ok || rec.removed || ns.flush() != nil {
-		return true, nil, 0.0
+	rec, ok := ns.nodes[nodeInfo.Name] // NodeInfo.Name: field of KubeDevice-API's NodeInfo (assumed; the reference never reads it)
+	if !ok || rec.removed {
+		return true, nil, 0.0 // a node AddNode never saw: the reference's answer
 	}
-	nk, err := ns.h.scorePair(rec.index, podGPUs(podInfo))
-	if err != nil {
-		return true, nil, 0.0
+	nk, err := ns.nodeKey(rec, podInfo)
+	if err != nil || nk == 0xFFFFFFFF {
+		return false, nil, 0.0 // device error or no free GPU set on this node now: does not fit (errors collapse to false, gpu_scheduler.go:35-42)
 	}
-	if nk == 0xFFFFFFFF {
-		return false, nil, 0.0
+	if fillAllocateFrom && !ns.GroupSchedulerMode {
+		ns.placed[podInfo.Name] = placement{nodeInfo.Name, nk & 0xFF, nk >> 8, false}
 	}
 	return true, nil, 1.0 / (1.0 + float64(nk>>8))
 }
@@ -189,9 +248,23 @@ func (ns *NvidiaGPUScheduler) PodAllocate(nodeInfo *types.NodeInfo, podInfo *typ
 	if err := (&ref.NvidiaGPUScheduler{}).PodAllocate(nodeInfo, podInfo); err != nil {
 		return err
 	}
+	if ns.GroupSchedulerMode {
+		return nil // the reference's contract: DevRequests rewritten, AllocateFrom left to the core
+	}
 	ns.mu.Lock()
 	defer ns.mu.Unlock()
 	pl, ok := ns.placed[podInfo.Name]
+	if here, known := ns.nodes[nodeInfo.Name]; known && (!ok || pl.node != nodeInfo.Name) {
+		nk, err := ns.nodeKey(here, podInfo) // no placement recorded for this node: ask the device now
+		if err != nil {
+			return err
+		}
+		if nk == 0xFFFFFFFF {
+			return fmt.Errorf("PodAllocate: not enough free GPUs on %s", nodeInfo.Name)
+		}
+		pl, ok = placement{nodeInfo.Name, nk & 0xFF, nk >> 8, false}, true
+		ns.placed[podInfo.Name] = pl
+	}
 	if !ok {
 		return nil
 	}
@@ -217,7 +290,7 @@ func (ns *NvidiaGPUScheduler) PodAllocate(nodeInfo *types.NodeInfo, podInfo *typ
 		}
 		sort.Strings(reqs)
 		for _, r := range reqs {
-			if next < len(slots) && regexp.MustCompile(`/gpu/.*/cards$`).MatchString(r) {
+			if next < len(slots) && gpuCardReq.MatchString(r) {
 				cont.AllocateFrom[types.ResourceName(r)] = types.ResourceName(fmt.Sprintf("%s/%s/cards", types.DeviceGroupPrefix, rec.names[slots[next]]))
 				next++
 			}
@@ -227,6 +300,9 @@ func (ns *NvidiaGPUScheduler) PodAllocate(nodeInfo *types.NodeInfo, podInfo *typ
 	return nil
 }
 
+// take / release: gpu_scheduler.go:57-63 are no-ops in the reference.  Take is idempotent (a placement PlaceBatch
+// committed on the device, or one taken before, succeeds without touching anything); GPUs in use by ANOTHER pod
+// are an error: score that pod again.
 func (ns *NvidiaGPUScheduler) take(podInfo *types.PodInfo, release bool) error {
 	ns.mu.Lock()
 	defer ns.mu.Unlock()
@@ -236,18 +312,26 @@ func (ns *NvidiaGPUScheduler) take(podInfo *types.PodInfo, release bool) error {
 	}
 	rec := ns.nodes[pl.node]
 	if release {
-		rec.used &^= pl.mask
 		delete(ns.placed, podInfo.Name)
+		if !pl.committed {
+			return nil
+		}
+		rec.used &^= pl.mask
 	} else {
+		if pl.committed {
+			return nil
+		}
 		if rec.used&pl.mask != 0 {
-			return fmt.Errorf("TakePodResources: GPUs already in use on %s", pl.node)
+			return fmt.Errorf("TakePodResources: GPUs of pod %s already in use on %s (score the pod again)", podInfo.Name, pl.node)
 		}
 		rec.used |= pl.mask
+		pl.committed = true
+		ns.placed[podInfo.Name] = pl
 	}
-	if ns.dirty {
-		return nil
+	if ns.dirty || ns.changed[pl.node] {
+		return nil // a re-upload / kgpu_update_node is pending and will carry the mask
 	}
-	return ns.h.setFreeMask(rec.index, int32(rec.present&^rec.used))
+	return ns.h.setFreeMask(rec.index, freeOf(rec))
 }
 
 func (ns *NvidiaGPUScheduler) TakePodResources(nodeInfo *types.NodeInfo, podInfo *types.PodInfo) error {
@@ -260,4 +344,6 @@ func (ns *NvidiaGPUScheduler) ReturnPodResources(nodeInfo *types.NodeInfo, podIn
 
 func (ns *NvidiaGPUScheduler) GetName() string { return "nvidiagpu" }
 
-func (ns *NvidiaGPUScheduler) UsingGroupScheduler() bool { return true }
+// UsingGroupScheduler: false when this plugin fills AllocateFrom itself (default), true in GroupSchedulerMode
+// (the reference, gpu_scheduler.go:69-71).
+func (ns *NvidiaGPUScheduler) UsingGroupScheduler() bool { return ns.GroupSchedulerMode }

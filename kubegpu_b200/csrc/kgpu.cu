@@ -879,7 +879,10 @@ int kgpu_place_batch_ex(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out
         kgpu::place_init<<<dim3((unsigned)T, (unsigned)views.n), kgpu::PLACE_TILE, 0, s.stream>>>(
             reinterpret_cast<const int4 *>(s.d_topo), d_free, s.d_mem, s.n, Npad, s.node_id_base, W, PC, views, s.d_nodebest,
             s.d_tilebest, T);
-        kgpu::place_sequential<<<1, kgpu::PLACE_THREADS, 0, s.stream>>>(s.d_topo, d_free, s.d_mem, s.n, Npad, s.node_id_base,
+        static const cudaError_t place_attr = cudaFuncSetAttribute(kgpu::place_sequential, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                                   (int)kgpu::PLACE_DYN_SMEM);
+        KGPU_CUDA(h, place_attr);
+        kgpu::place_sequential<<<1, kgpu::PLACE_THREADS, kgpu::PLACE_DYN_SMEM, s.stream>>>(s.d_topo, d_free, s.d_mem, s.n, Npad, s.node_id_base,
                                                                         reinterpret_cast<const int4 *>(s.d_pods), P, W, views,
                                                                         s.d_nodebest, s.d_tilebest, T, s.d_keys);
         h->launches += 2;

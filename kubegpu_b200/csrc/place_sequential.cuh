@@ -157,6 +157,31 @@ __device__ __forceinline__ uint32_t node_key_warp(int k, const int32_t *half, ui
     return __reduce_min_sync(0xFFFFFFFFu, key);
 }
 
+// Warp minimum of 64-bit keys with two REDUX.MIN (high word, then the low words of the lanes that hold it)
+// instead of five rounds of two 32-bit shuffles + compare-select.
+__device__ __forceinline__ unsigned long long warp_min_u64_redux(unsigned long long v) {
+    const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+    const uint32_t mhi = __reduce_min_sync(0xFFFFFFFFu, hi);
+    const uint32_t mlo = __reduce_min_sync(0xFFFFFFFFu, hi == mhi ? lo : 0xFFFFFFFFu);
+    return ((unsigned long long)mhi << 32) | mlo;
+}
+
+constexpr int PLACE_POD_CHUNK = 1024;       // pod requests staged in shared memory (16 KB)
+constexpr size_t PLACE_DYN_SMEM = 2 * (size_t)PLACE_SUPER_CAP * sizeof(unsigned long long);
+
+// One persistent block.  Per pod (the serial chain; v3):
+//   1. every warp finds the winner by itself: the supertile minima of (view, k) sit in shared memory (<= a few
+//      entries per lane), the minimum IS the winning (cost, node, subset); two REDUX.  No barrier: the minima are
+//      double buffered by UPDATE EPOCH (an epoch = one pod that placed something): winners are read from copy
+//      e & 1, refreshed values are written to copy (e + 1) & 1 at once and to copy e & 1 one epoch later (by the
+//      same lane, before its new writes), i.e. after the barrier that ends epoch e -- so no warp can see a
+//      refreshed minimum while another still looks for the winner.
+//   2. commit + refresh, warp per (view, k) task: all global loads of a task (the winner's topology row, the
+//      node keys of its tile, the tile minima of its supertile) are issued together, then the warp re-enumerates
+//      the winner (lane per subset, half tables), takes the tile minimum with one REDUX over a 32-bit composite
+//      (cost << 15 | node offset << 8 | S; cost < 2^17) and the supertile minimum with two.
+//   3. ONE barrier.
+// Pod requests are staged PLACE_POD_CHUNK at a time; indices are 32-bit shifts (supertiles are 32 << j tiles).
 __global__ void __launch_bounds__(PLACE_THREADS, 1)
 place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_mask, const int32_t *__restrict__ gpu_mem,
                  int64_t N, int64_t Npad, int64_t node_id_base, const int4 *__restrict__ pods4, int64_t P, Weights W,
@@ -166,94 +191,139 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
     __shared__ int32_t sViewMin[PLACE_MAX_VIEWS];                 // static indexing of the kernel parameter only
     __shared__ int32_t sCost[PLACE_WARPS][64];                    // per warp: the winner node's cost matrix
     __shared__ int32_t sHalf[PLACE_WARPS][PLACE_HALF];            // per warp: its half tables (node_key_warp)
-    __shared__ unsigned long long sRed[2][PLACE_WARPS];           // double buffered by pod parity
-    __shared__ unsigned long long sSuper[PLACE_SUPER_CAP];        // super[v][k][ST]
+#ifdef __CUDACC__
+    extern __shared__ unsigned long long sSuperDyn[];             // super[copy][v][k][ST]: 2 x 36 KB of DYNAMIC shared memory
+    unsigned long long (*sSuper)[PLACE_SUPER_CAP] = reinterpret_cast<unsigned long long (*)[PLACE_SUPER_CAP]>(sSuperDyn);
+#else
+    __shared__ unsigned long long sSuper[2][PLACE_SUPER_CAP];     // (CPU emulation build)
+#endif
+    __shared__ int32_t sPendIdx[PLACE_MAX_VIEWS * 9];             // per task: entry still to be written to the other copy
+    __shared__ unsigned long long sPendVal[PLACE_MAX_VIEWS * 9];
+    __shared__ int4 sPods[PLACE_POD_CHUNK];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int V = views.n;
-    const int64_t super_tiles = place_super_tiles(T, V);
-    const int64_t ST = (T + super_tiles - 1) / super_tiles;
+    const int super_tiles = (int)place_super_tiles(T, V);         // 32 << j
+    const int st_shift = 31 - __clz(super_tiles);
+    const int ST = (int)((T + super_tiles - 1) >> st_shift);
+    const int Ti = (int)T;
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < 16; i++) sW[i] = W.w[i];
 #pragma unroll
         for (int i = 0; i < PLACE_MAX_VIEWS; i++) sViewMin[i] = views.min_mem[i];
     }
-    // supertile minima from the tile minima place_init left in memory
-    for (int64_t idx = tid; idx < (int64_t)V * 9 * ST; idx += PLACE_THREADS) {
-        const int64_t vk = idx / ST, st = idx % ST;
-        const int64_t t1 = min(T, (st + 1) * super_tiles);
+    if (tid < PLACE_MAX_VIEWS * 9) sPendIdx[tid] = -1;
+    // supertile minima from the tile minima place_init left in memory (both copies)
+    for (int idx = tid; idx < V * 9 * ST; idx += PLACE_THREADS) {
+        const int vk = idx / ST, st = idx - vk * ST;
+        const int t1 = min(Ti, (st + 1) << st_shift);
         unsigned long long b = ~0ull;
-        for (int64_t t = st * super_tiles; t < t1; t++) b = min(b, tilebest[vk * T + t]);
-        sSuper[idx] = b;
+        for (int t = st << st_shift; t < t1; t++) b = min(b, tilebest[(int64_t)vk * T + t]);
+        sSuper[0][idx] = b;
+        sSuper[1][idx] = b;
     }
-    __syncthreads();
+    uint32_t epoch = 0;                                           // block-uniform: pods that placed something so far
+    const int ntask = V * 9;
 
-    for (int64_t p = 0; p < P; p++) {
-        const int4 req = __ldg(pods4 + p);                // block-uniform
-        const int k = req.x;
-        if (k < 0 || k > 8) {
-            if (tid == 0) keys[p] = ~0ull;
-            continue;
-        }
-        int v = 0;                                        // the pod's view: the one with its min_mem
-        for (int j = 1; j < V; j++)
-            if (req.w == sViewMin[j]) v = j;
-        // 1. best supertile of (v, k): its minimum is the winning (cost, node, subset) itself
-        const unsigned long long *sp = sSuper + ((int64_t)v * 9 + k) * ST;
-        unsigned long long best = ~0ull;
-        for (int64_t s = tid; s < ST; s += PLACE_THREADS) best = min(best, sp[s]);
-        best = warp_min_u64(best);
-        unsigned long long *red = sRed[p & 1];
-        if (lane == 0) red[warp] = best;
+    for (int64_t p0 = 0; p0 < P; p0 += PLACE_POD_CHUNK) {
+        const int pn = (int)min((int64_t)PLACE_POD_CHUNK, P - p0);
         __syncthreads();
-        const unsigned long long win = warp_min_u64(lane < PLACE_WARPS ? red[lane] : ~0ull);   // every warp for itself
-        if (tid == 0) keys[p] = win;
-        if (win == ~0ull || k == 0) continue;             // nothing fits / nothing to take (block-uniform)
+        for (int i = tid; i < pn; i += PLACE_THREADS) sPods[i] = __ldg(pods4 + p0 + i);
+        __syncthreads();
+#pragma unroll 1
+        for (int pi = 0; pi < pn; pi++) {
+            const int4 req = sPods[pi];                       // block-uniform
+            const int k = req.x;
+            if (k < 0 || k > 8) {
+                if (tid == 0) keys[p0 + pi] = ~0ull;
+                continue;
+            }
+            int v = 0;                                        // the pod's view: the one with its min_mem
+            for (int j = 1; j < V; j++)
+                if (req.w == sViewMin[j]) v = j;
+            // 1. the winner, by every warp for itself
+            const unsigned long long *sp = sSuper[epoch & 1] + (v * 9 + k) * ST;
+            unsigned long long best = ~0ull;
+            for (int s = lane; s < ST; s += 32) best = min(best, sp[s]);
+            const unsigned long long win = warp_min_u64_redux(best);
+            if (tid == 0) keys[p0 + pi] = win;
+            if (win == ~0ull || k == 0) continue;             // nothing fits / nothing to take (block-uniform)
 
-        // 2. commit and refresh, warp by warp.  The new free mask is old & ~S whether a warp reads the
-        // mask before or after warp 0 has written it back.
-        const int64_t node = (int64_t)((win >> 8) & 0xFFFFFFFFull) - node_id_base;
-        const uint32_t S = (uint32_t)(win & 0xFFull);
-        const int64_t tile = node / PLACE_TILE, st = tile / super_tiles;
-        if (warp < min(PLACE_WARPS, V * 9)) {
-            int32_t *cost = sCost[warp];
-            cost[lane] = sW[__ldg(topo + node * 64 + lane) & 15];
-            cost[lane + 32] = sW[__ldg(topo + node * 64 + lane + 32) & 15];
-            const uint32_t fm = ((uint32_t)free_mask[node] & 0xFFu) & ~S;
-            const int32_t my_mem = (gpu_mem != nullptr && lane < 8) ? __ldg(gpu_mem + node * 8 + lane) : 0x7FFFFFFF;
-            __syncwarp();
-            int32_t *half = sHalf[warp];
-            build_half_tables(cost, half, lane);
-            __syncwarp();
-            if (warp == 0 && lane == 0) free_mask[node] = (int32_t)fm;
-            for (int task = warp; task < V * 9; task += PLACE_WARPS) {
-                const int tv = task / 9, tk = task % 9;
-                const int64_t vk = task;
-                // independent global loads first: the tile's node keys, the supertile's tile minima
-                uint32_t nb[PLACE_TILE / 32];
+            // 2. commit and refresh, warp by warp
+            const uint32_t nid = (uint32_t)(win >> 8);
+            const int node = (int)((int64_t)nid - node_id_base);
+            const uint32_t S = (uint32_t)(win & 0xFFull);
+            const int tile = node >> 7, st = tile >> st_shift;
+            static_assert(PLACE_TILE == 128, "tile index is node >> 7");
+            if (warp < min(PLACE_WARPS, ntask)) {
+                // every global load this warp needs, issued before anything waits
+                const int32_t l0 = __ldg(topo + (int64_t)node * 64 + lane), l1 = __ldg(topo + (int64_t)node * 64 + lane + 32);
+                const uint32_t fm = ((uint32_t)free_mask[node] & 0xFFu) & ~S;   // old & ~S whether or not warp 0 has written it back
+                const int32_t my_mem = (gpu_mem != nullptr && lane < 8) ? __ldg(gpu_mem + (int64_t)node * 8 + lane) : 0x7FFFFFFF;
+                uint32_t nb0[PLACE_TILE / 32];
+                unsigned long long tb0 = ~0ull;
+                {
+                    const int64_t vk = warp;                  // the first task of this warp
 #pragma unroll
-                for (int j = 0; j < PLACE_TILE / 32; j++) nb[j] = nodebest[vk * Npad + tile * PLACE_TILE + lane + 32 * j];
-                unsigned long long sb = ~0ull;
-                for (int64_t t = st * super_tiles + lane; t < min(T, (st + 1) * super_tiles); t += 32)
-                    if (t != tile) sb = min(sb, tilebest[vk * T + t]);
-                const uint32_t ok = tv == 0 ? 0xFFu : (__ballot_sync(0xFFFFFFFFu, my_mem >= sViewMin[tv]) & 0xFFu);
-                const uint32_t nk = node_key_warp(tk, half, fm & ok, lane);
-                if (lane == 0) nodebest[vk * Npad + node] = nk;
-                unsigned long long tb = ~0ull;
-#pragma unroll
-                for (int j = 0; j < PLACE_TILE / 32; j++) {
-                    const int64_t n = tile * PLACE_TILE + lane + 32 * j;
-                    tb = min(tb, wide_key(n == node ? nk : nb[j], (unsigned long long)(node_id_base + n)));
+                    for (int j = 0; j < PLACE_TILE / 32; j++) nb0[j] = nodebest[vk * Npad + tile * PLACE_TILE + lane + 32 * j];
+                    for (int t = (st << st_shift) + lane; t < min(Ti, (st + 1) << st_shift); t += 32)
+                        if (t != tile) tb0 = min(tb0, tilebest[vk * T + t]);
                 }
-                tb = warp_min_u64(tb);
-                sb = warp_min_u64(min(sb, tb));
-                if (lane == 0) {
-                    tilebest[vk * T + tile] = tb;
-                    sSuper[vk * ST + st] = sb;
+                int32_t *cost = sCost[warp];
+                cost[lane] = sW[l0 & 15];
+                cost[lane + 32] = sW[l1 & 15];
+                __syncwarp();
+                int32_t *half = sHalf[warp];
+                build_half_tables(cost, half, lane);
+                __syncwarp();
+                if (warp == 0 && lane == 0) free_mask[node] = (int32_t)fm;
+                for (int task = warp; task < ntask; task += PLACE_WARPS) {
+                    const int tv = task / 9, tk = task - tv * 9;
+                    const int64_t vk = task;
+                    uint32_t nb[PLACE_TILE / 32];
+                    unsigned long long sb = ~0ull;
+                    if (task == warp) {
+#pragma unroll
+                        for (int j = 0; j < PLACE_TILE / 32; j++) nb[j] = nb0[j];
+                        sb = tb0;
+                    } else {                                  // more tasks than warps (several views): load now
+#pragma unroll
+                        for (int j = 0; j < PLACE_TILE / 32; j++) nb[j] = nodebest[vk * Npad + tile * PLACE_TILE + lane + 32 * j];
+                        for (int t = (st << st_shift) + lane; t < min(Ti, (st + 1) << st_shift); t += 32)
+                            if (t != tile) sb = min(sb, tilebest[vk * T + t]);
+                    }
+                    const uint32_t ok = tv == 0 ? 0xFFu : (__ballot_sync(0xFFFFFFFFu, my_mem >= sViewMin[tv]) & 0xFFu);
+                    const uint32_t nk = node_key_warp(tk, half, fm & ok, lane);
+                    // tile minimum: 32-bit composite cost << 15 | node offset << 8 | S (cost <= 28 * 4095 < 2^17)
+                    uint32_t m = INF32;
+#pragma unroll
+                    for (int j = 0; j < PLACE_TILE / 32; j++) {
+                        const int off = lane + 32 * j;
+                        const uint32_t key = (tile * PLACE_TILE + off == node) ? nk : nb[j];
+                        if (key != INF32) m = min(m, ((key >> 8) << 15) | ((uint32_t)off << 8) | (key & 0xFFu));
+                    }
+                    m = __reduce_min_sync(0xFFFFFFFFu, m);
+                    const unsigned long long tb =
+                        m == INF32 ? ~0ull
+                                   : (((unsigned long long)(m >> 15) << 40) |
+                                      ((unsigned long long)(node_id_base + (int64_t)tile * PLACE_TILE + ((m >> 8) & 127u)) << 8) | (m & 0xFFu));
+                    sb = warp_min_u64_redux(min(sb, tb));
+                    if (lane == 0) {
+                        nodebest[vk * Npad + node] = nk;
+                        tilebest[vk * T + tile] = tb;
+                        // last epoch's refreshed minimum reaches the copy the winners are read from NEXT epoch ...
+                        const int pe = sPendIdx[task];
+                        if (pe >= 0) sSuper[(epoch + 1) & 1][pe] = sPendVal[task];
+                        // ... and this epoch's goes to that copy now, to the other one an epoch later
+                        sSuper[(epoch + 1) & 1][vk * ST + st] = sb;
+                        sPendIdx[task] = (int)(vk * ST + st);
+                        sPendVal[task] = sb;
+                    }
                 }
             }
+            epoch++;
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 

@@ -179,6 +179,7 @@ inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 // ---- integer intrinsics ----------------------------------------------------------------------------------
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 inline unsigned __vimin3_u32(unsigned a, unsigned b, unsigned c) { unsigned m = a < b ? a : b; return m < c ? m : c; }
 inline unsigned __vimax3_u32(unsigned a, unsigned b, unsigned c) { unsigned m = a > b ? a : b; return m > c ? m : c; }
 inline unsigned __viaddmin_u32(unsigned a, unsigned b, unsigned c) { unsigned s = a + b; return s < c ? s : c; }
