@@ -301,6 +301,7 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"                      # no version banner on stdout: one JSON line only
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")            # host-side barriers: waiting ranks must not spin on their GPU
     W = max(3, args.warmup)
     K = max(1, args.steps)
     peak, peak_src = measured_peak_gbs()
@@ -757,9 +758,12 @@ def main():
                                       "The algorithmic figure counts 260 B per pair, i.e. the uncompacted matrix."}
 
     # ---- N > 1: the single-process multi-device handle (in-library NCCL all-gather), on rank 0 ---------------
-    if world > 1:
-        barrier()
-        if rank == 0 and extras:
+    if world > 1 and extras:
+        # The other ranks wait on the HOST (gloo): an NCCL barrier would keep a spinning kernel on their GPUs and
+        # rank 0's work on those devices would be time-sliced against it.
+        torch.cuda.synchronize()
+        dist.barrier(group=host_group)
+        if rank == 0:
             md = {}
             try:
                 ftopo, ffree, _ = synth.gen_c2(N_NODES, 0)
@@ -779,7 +783,7 @@ def main():
             except Exception as e:
                 md = {"error": repr(e)}
             line["multi_device_handle"] = md
-        barrier()
+        dist.barrier(group=host_group)
 
     if rank == 0:
         par = line.get("parity_in_run")

@@ -222,7 +222,11 @@ int build_order(kgpu_ctx *h, kgpu_shard &s) {
 // Bring the K1s node cache of shard s up to date (order, compacted records); everything runs on s.stream and
 // has completed when this returns, so a following launch on any stream sees it.
 int ensure_node_cache(kgpu_ctx *h, kgpu_shard &s) {
-    if (!s.order_dirty && s.stale_nodes * 8 > s.n) s.order_dirty = true;     // many free counts changed: re-sort
+    static const int64_t resort_div = [] { const char *e = getenv("KGPU_RESORT_DIV"); int v = e ? atoi(e) : 0; return (int64_t)(v > 0 ? v : 200); }();
+    // Nodes whose free count changed keep their slot, so their warp enumerates for the LARGEST count among its 32
+    // lanes: measured on C2, 1 % of the nodes changed -> the next step takes 1.03 ms instead of 0.48; a re-sort +
+    // recompaction costs 0.18 ms.  So re-sort as soon as more than n / 200 nodes have changed (KGPU_RESORT_DIV).
+    if (!s.order_dirty && s.stale_nodes * resort_div > s.n) s.order_dirty = true;
     if (!s.order_dirty && !s.compact_dirty) return KGPU_OK;
     if (s.order_dirty) {
         const int rc = build_order(h, s);
@@ -391,7 +395,11 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
             const int4 *d_work = nullptr;
             if (use_work) {
                 if (s.work_P != P) {
-                    kgpu::build_sparse_work(s.tile_class, P, resident, s.h_work);
+                    kgpu::SparseWorkParams prm;
+                    static const int max_run = [] { const char *e = getenv("KGPU_SP_MAXRUN"); return e ? atoi(e) : 0; }();
+                    if (max_run > 0) prm.max_run = max_run;
+                    const int64_t res_list = P <= kgpu::kSparseChunk ? (int64_t)s.sm_count * KGPU_SP_STREAM_MINBLOCKS : resident;
+                    kgpu::build_sparse_work(s.tile_class, P, res_list, s.h_work, prm);
                     if ((int64_t)s.h_work.size() > s.work_cap) {
                         if (s.d_work) cudaFree(s.d_work);
                         s.d_work = nullptr; s.work_cap = 0;
@@ -407,13 +415,17 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
             }
             bool byte_keys = true;       // every cost < 2^16 <=> 28 * max weight < 65536
             for (int i = 0; i < 16; i++) byte_keys = byte_keys && h->W[i] <= 2340;
-#define KGPU_LAUNCH_SPARSE(MEMF, BK)                                                                          \
-    kgpu::score_pairs_sparse<true, MEMF, BK><<<grid, kgpu::SP_THREADS, 0, st>>>(                              \
+#define KGPU_LAUNCH_SPARSE(MEMF, BK, ST)                                                                      \
+    kgpu::score_pairs_sparse<true, MEMF, BK, ST><<<grid, kgpu::SP_THREADS, 0, st>>>(                          \
         s.d_rec, s.d_meta, s.d_mem, s.d_order, s.d_flag, s.node_id_base, pods4, P, (int)per, d_work, PC, d_keys)
-            if (byte_keys) KGPU_LAUNCH_SPARSE(false, true); else KGPU_LAUNCH_SPARSE(false, false);
+            // few pods (the batch is one chunk): the work list holds runs of tiles -> the STREAM instantiation
+            // (next tile's record prefetched into registers while the current one is scored)
+            const bool stream_build = use_work && P <= kgpu::kSparseChunk;
+            if (stream_build) { if (byte_keys) KGPU_LAUNCH_SPARSE(false, true, true); else KGPU_LAUNCH_SPARSE(false, false, true); }
+            else              { if (byte_keys) KGPU_LAUNCH_SPARSE(false, true, false); else KGPU_LAUNCH_SPARSE(false, false, false); }
             h->launches++;
             if (has_mem != 0) {
-                if (byte_keys) KGPU_LAUNCH_SPARSE(true, true); else KGPU_LAUNCH_SPARSE(true, false);
+                if (byte_keys) KGPU_LAUNCH_SPARSE(true, true, false); else KGPU_LAUNCH_SPARSE(true, false, false);
                 h->launches++;
             }
 #undef KGPU_LAUNCH_SPARSE

@@ -298,8 +298,15 @@ compact_nodes(const int4 *__restrict__ topo4, int32_t *free_mask, int64_t n_item
 }
 
 // grid = (work items) or (slot tiles, pod splits); block = SP_THREADS.  order[slot] = node index or -1 (padding).
-template <bool PER_PAIR, bool MEM, bool BYTE_KEYS>
-__global__ void __launch_bounds__(SP_THREADS, MEM ? 4 : KGPU_SP_MINBLOCKS)
+// STREAM (few pods, runs of tiles: the HBM-bound regime): the NEXT tile's record is loaded into a second register
+// set before the current tile's bucket loops, so every block always has a tile in flight from DRAM while it
+// computes (96 registers, 5 blocks per SM: 75 KB in flight per SM against the ~45 KB that 6.6 TB/s x ~1 us of
+// DRAM latency need).  Without it a block slot alternates between waiting for its tile and computing on it.
+#ifndef KGPU_SP_STREAM_MINBLOCKS
+#define KGPU_SP_STREAM_MINBLOCKS 5
+#endif
+template <bool PER_PAIR, bool MEM, bool BYTE_KEYS, bool STREAM = false>
+__global__ void __launch_bounds__(SP_THREADS, STREAM ? KGPU_SP_STREAM_MINBLOCKS : MEM ? 4 : KGPU_SP_MINBLOCKS)
 score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ meta,
                    const int32_t *__restrict__ gpu_mem, const int32_t *__restrict__ order,
                    const int *__restrict__ mem_flag, int64_t node_id_base, const int4 *__restrict__ pods4, int64_t P,
@@ -330,20 +337,35 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
     // ntiles > 1 (few pods: p_end - p_begin <= SP_CHUNK, the host guarantees it): the block walks a run of tiles;
     // the pods are sorted once (first tile), the per-pod minimum is carried in sAcc and flushed once at the end.
     const bool multi = ntiles > 1;
+    // a slot's record: seven coalesced 16-byte loads + node index + permutation / free count
+    auto load_tile = [&](int64_t t, int4 (&r)[7], int32_t &nd, uint32_t &m) {
+        const int4 *src = rec + t * (7 * SP_THREADS) + tid;
+#pragma unroll
+        for (int q = 0; q < 7; q++) r[q] = __ldg(src + q * SP_THREADS);
+        nd = __ldg(order + t * SP_THREADS + tid);
+        m = __ldg(meta + t * SP_THREADS + tid);
+    };
+    int4 nx[7];
+    int32_t nx_node = -1;
+    uint32_t nx_pm = 0;
+    if (STREAM) load_tile(tile_first, nx, nx_node, nx_pm);
 #pragma unroll 1
     for (int tt = 0; tt < ntiles; tt++) {
     const int64_t tile_index = tile_first + tt;
     if (tt > 0) __syncthreads();                       // the previous tile's flush has read sNode / sHot*
     const int64_t slot = tile_index * SP_THREADS + tid;
-    // the slot's record: seven coalesced 16-byte loads, issued before anything waits on them
     int4 rw[7];
-    {
-        const int4 *src = rec + tile_index * (7 * SP_THREADS) + tid;
+    int32_t node;
+    uint32_t pm;                                       // eight 3-bit GPU indices | free count << 24
+    if (STREAM) {
 #pragma unroll
-        for (int t = 0; t < 7; t++) rw[t] = __ldg(src + t * SP_THREADS);
+        for (int q = 0; q < 7; q++) rw[q] = nx[q];
+        node = nx_node;
+        pm = nx_pm;
+        if (tt + 1 < ntiles) load_tile(tile_index + 1, nx, nx_node, nx_pm);     // in flight during this tile's loops
+    } else {
+        load_tile(tile_index, rw, node, pm);           // issued before anything waits on them
     }
-    const int32_t node = __ldg(order + slot);
-    const uint32_t pm = __ldg(meta + slot);             // eight 3-bit GPU indices | free count << 24
     const bool valid = node >= 0;
     sNode[tid] = node;
     const uint32_t nfree = pm >> 24;                     // 0 for padding slots
@@ -361,7 +383,13 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
     // order IS (cost, node) order and the flush can min the four warp keys directly.
     bool ordered = false;
     if (BYTE_KEYS) {
-        const int32_t prev = tid > 0 ? __ldg(order + slot - 1) : -1;
+        int32_t prev;
+        if (STREAM) {                                  // no dependent global load on the streaming path
+            __syncthreads();
+            prev = tid > 0 ? sNode[tid - 1] : -1;
+        } else {
+            prev = tid > 0 ? __ldg(order + slot - 1) : -1;
+        }
         ordered = __syncthreads_and(tid == 0 || node < 0 || (prev >= 0 && prev < node)) != 0;
     }
     PairCosts C;

@@ -97,12 +97,14 @@ void emu_launch_sparse(const EmuCache &c, const int32_t *free_mask, const int32_
     }
     bool byte_keys = true;                               // kgpu.cu: every cost < 2^16
     for (int i = 0; i < 16; i++) byte_keys = byte_keys && W[i] <= 2340;
-#define EMU_SPARSE(MEMF, BK)                                                                                   \
+#define EMU_SPARSE(MEMF, BK, ST)                                                                               \
     emu::launch(grid, dim3(kgpu::SP_THREADS), [&] {                                                            \
-        kgpu::score_pairs_sparse<true, MEMF, BK>(c.rec, c.meta, mem, c.order.data(), &flag, node_id_base, pods4, P, per, work, kPC, keys); \
+        kgpu::score_pairs_sparse<true, MEMF, BK, ST>(c.rec, c.meta, mem, c.order.data(), &flag, node_id_base, pods4, P, per, work, kPC, keys); \
     })
-    if (byte_keys) EMU_SPARSE(false, true); else EMU_SPARSE(false, false);
-    if (flag) { if (byte_keys) EMU_SPARSE(true, true); else EMU_SPARSE(true, false); }
+    const bool stream_build = splits < 0 && P <= kgpu::kSparseChunk;      // kgpu.cu: runs of tiles -> the STREAM instantiation
+    if (stream_build) { if (byte_keys) EMU_SPARSE(false, true, true); else EMU_SPARSE(false, false, true); }
+    else              { if (byte_keys) EMU_SPARSE(false, true, false); else EMU_SPARSE(false, false, false); }
+    if (flag) { if (byte_keys) EMU_SPARSE(true, true, false); else EMU_SPARSE(true, false, false); }
 #undef EMU_SPARSE
 }
 

@@ -208,7 +208,7 @@ def test_sparse_work_list_partitions_the_tile_pod_plane(emu, P, resident):
         assert (items[:, 3] == 1).all()
     else:
         assert ((items[:, 1] == 0) & (items[:, 2] == P)).all()                     # runs carry the whole (one-chunk) batch
-        assert items[:, 3].max() <= 64
+        assert items[:, 3].max() <= 16
         if resident == 1:
             assert items[:, 3].max() > 1                                           # few resident blocks: tiles are grouped
     cover = np.zeros((ntile, P), dtype=np.int32)
