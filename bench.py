@@ -647,7 +647,7 @@ def main():
         line["state_churn"] = {"step_after_1pct_mask_churn_ms": float(np.median(churn_ms)), "set_free_masks_ms": float(np.median(upd_ms)),
                                "nodes_changed_per_step": N_NODES // 100, "e2e_value": N_PODS / (float(np.median(churn_ms)) * 1e-3), "unit": UNIT,
                                "parity": {"ok": ok, "pods_checked": S},
-                               "what": "kgpu_set_free_masks (1 H2D + 1 kernel: scatter + refresh of those nodes' records; re-sort when > n/8 "
+                               "what": "kgpu_set_free_masks (1 H2D + 1 kernel: scatter + refresh of those nodes' records; re-sort when > n/200 "
                                        "nodes have changed) + kgpu_score_batch, host buffers, wall clock"}
         # PodFitsDevice served from the (node, k) fit table
         scorer.build_fit_table()

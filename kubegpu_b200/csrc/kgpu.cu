@@ -105,6 +105,7 @@ struct kgpu_ctx {
         void *peer_base[kgpu::PEER_MAX_WORLD] = {};
         unsigned long long *local = nullptr;
         uint32_t epoch = 0;
+        int64_t used_len[2] = {0, 0};       // entries of each result buffer that may hold keys (cleaned by the push kernel)
         bool connected = false;
     } xch;
 };
@@ -326,7 +327,7 @@ int apply_node_updates(kgpu_ctx *h, kgpu_shard &s, const int32_t *idx, const int
 // Enqueue K1 for P pods on shard s: d_keys[p] = best placement over this shard's nodes.
 // has_mem: 1 / 0 = the host knows whether some pod carries min_mem > 0; -1 = unknown (device buffers).
 int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, unsigned long long *d_keys,
-                 cudaStream_t st, int has_mem) {
+                 cudaStream_t st, int has_mem, bool keys_are_clean = false) {
     if (P <= 0) return KGPU_OK;
     if ((reinterpret_cast<uintptr_t>(d_pods) & 15u) != 0)
         return fail(h, KGPU_ERR_INVALID, "pods pointer must be 16-byte aligned");
@@ -337,7 +338,7 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
     const int4 *pods4 = reinterpret_cast<const int4 *>(d_pods);
 
     const int4 *mem4 = reinterpret_cast<const int4 *>(s.d_mem);
-    KGPU_CUDA(h, cudaMemsetAsync(d_keys, 0xFF, (size_t)P * 8, st));
+    if (!keys_are_clean) KGPU_CUDA(h, cudaMemsetAsync(d_keys, 0xFF, (size_t)P * 8, st));
     if (s.n == 0) return KGPU_OK;
 
     const bool wpp = h->variant == KGPU_VARIANT_WARP_PER_PAIR;
@@ -1051,6 +1052,7 @@ int kgpu_exchange_init(kgpu_t *h, int world, int rank, int64_t max_pods, unsigne
     KGPU_CUDA(h, cudaMalloc(&h->xch.base, xch_bytes(max_pods)));
     KGPU_CUDA(h, cudaMalloc(&h->xch.local, (size_t)max_pods * 8));
     KGPU_CUDA(h, cudaMemset(h->xch.base, 0xFF, (size_t)max_pods * 16));                                   // both result buffers: NO_FIT
+    KGPU_CUDA(h, cudaMemset(h->xch.local, 0xFF, (size_t)max_pods * 8));                                   // the push kernel keeps it that way
     KGPU_CUDA(h, cudaMemset(xch_flags(h->xch.base, max_pods), 0, kgpu::PEER_MAX_WORLD * 4 + 16));         // flags, ticket
     KGPU_CUDA(h, cudaDeviceSynchronize());
     cudaIpcMemHandle_t ipc;
@@ -1092,10 +1094,9 @@ int kgpu_score_batch_exchange(kgpu_t *h, const int32_t *d_pods, int64_t P, const
     const int64_t mp = h->xch.max_pods;
     *d_final_keys = reinterpret_cast<const uint64_t *>(xch_results(h->xch.base, mp, buf));
     if (P == 0) return KGPU_OK;
-    // the other buffer is what peers push into NEXT epoch: clean it before this rank can reach this epoch's barrier
-    // (all max_pods entries: the next batch may be longer than this one)
-    KGPU_CUDA(h, cudaMemsetAsync(xch_results(h->xch.base, mp, buf ^ 1), 0xFF, (size_t)mp * 8, st));
-    const int rc = launch_score(h, s, d_pods, P, h->xch.local, st, (batch_flags & KGPU_BATCH_NO_MIN_MEM) ? 0 : -1);
+    // K1 accumulates into xch.local (kept at NO_FIT between steps by the push kernel), then ONE kernel pushes, cleans
+    // the other result buffer and meets the peers: two launches per step
+    const int rc = launch_score(h, s, d_pods, P, h->xch.local, st, (batch_flags & KGPU_BATCH_NO_MIN_MEM) ? 0 : -1, true);
     if (rc != KGPU_OK) return rc;
     kgpu::PeerTable tab;
     memset(&tab, 0, sizeof tab);
@@ -1104,7 +1105,10 @@ int kgpu_score_batch_exchange(kgpu_t *h, const int32_t *d_pods, int64_t P, const
         tab.flags[r] = xch_flags(h->xch.peer_base[r], mp);
     }
     unsigned int *ticket = reinterpret_cast<unsigned int *>(xch_flags(h->xch.base, mp) + kgpu::PEER_MAX_WORLD);
-    kgpu::push_and_sync<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(h->xch.local, P, tab, h->xch.rank, h->xch.world, epoch, ticket);
+    kgpu::push_and_sync<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(h->xch.local, P, tab, h->xch.rank, h->xch.world, epoch, ticket,
+                                                                     xch_results(h->xch.base, mp, buf ^ 1), h->xch.used_len[buf ^ 1]);
+    h->xch.used_len[buf ^ 1] = 0;
+    h->xch.used_len[buf] = P;
     h->launches++;
     KGPU_CUDA(h, cudaGetLastError());
     return KGPU_OK;

@@ -7,10 +7,10 @@
 //   * sync: the last block to finish (atomic ticket) publishes "rank r has pushed epoch e" into every
 //     rank's flag array and spins until all G ranks have published e.  When the kernel ends, this rank's
 //     result array holds the global per-pod minimum, the same on every rank.
-// Result arrays are double buffered by epoch parity; the host resets the OTHER buffer before this kernel
-// (stream order), so it is clean before any peer can reach the next epoch (they pass this epoch's barrier
+// Result arrays are double buffered by epoch parity; the OTHER buffer is cleaned by this kernel before the rank's
+// arrival flag is set, so it is clean before any peer can reach the next epoch (they pass this epoch's barrier
 // only after this rank arrived at it).
-// EXPERIMENTAL: written without GPU access (round-2 prep); needs a 2-GPU run before it is trusted.
+// Measured (round 2, 2 x B200, C2): keys bit-identical to one GPU and to the NCCL path (tests/test_gpu_multi.py).
 #pragma once
 #include <cstdint>
 
@@ -23,19 +23,26 @@ struct PeerTable {
     uint32_t *flags[PEER_MAX_WORLD];               // every rank's flag array [world]
 };
 
+// The step is TWO launches per rank (K1 + this kernel): the kernel also does the housekeeping the host used to enqueue
+// as memsets -- it resets the rank's local key array behind itself (K1 of the next step accumulates into it with atomic
+// min) and cleans the OTHER result buffer (entries [0, clean_len): what the step before last left there) BEFORE the rank
+// announces its arrival, so the buffer is clean before any peer can pass this epoch's barrier and push the next epoch.
 __global__ void __launch_bounds__(256)
-push_and_sync(const unsigned long long *__restrict__ local_keys, int64_t P, PeerTable peers, int rank, int world,
-              uint32_t epoch, unsigned int *ticket) {
+push_and_sync(unsigned long long *__restrict__ local_keys, int64_t P, PeerTable peers, int rank, int world,
+              uint32_t epoch, unsigned int *ticket, unsigned long long *__restrict__ other_buffer, int64_t clean_len) {
     __shared__ bool last;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < clean_len; i += stride) other_buffer[i] = ~0ull;
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < P) {
         const unsigned long long k = local_keys[p];
+        local_keys[p] = ~0ull;                     // ready for the next step's K1
         if (k != ~0ull) {
 #pragma unroll 1
             for (int g = 0; g < world; g++) atomicMin_system(peers.results[g] + p, k);
         }
     }
-    __threadfence_system();                        // this thread's pushes before the ticket
+    __threadfence_system();                        // this thread's pushes (and its cleaning) before the ticket
     __syncthreads();
     if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     __syncthreads();

@@ -32,7 +32,7 @@ namespace kgpu {
 
 constexpr int PLACE_TILE = 128;
 #ifndef KGPU_PLACE_THREADS
-#define KGPU_PLACE_THREADS 512      // 16 warps: cheap barriers, 9 of them busy per view in the refresh
+#define KGPU_PLACE_THREADS 320      // 10 warps: one per k (9 busy with one view), cheap block barrier
 #endif
 constexpr int PLACE_THREADS = KGPU_PLACE_THREADS;
 constexpr int PLACE_WARPS = PLACE_THREADS / 32;
@@ -140,12 +140,13 @@ __device__ __forceinline__ void build_half_tables(const int32_t *sCost, int32_t 
 }
 
 // (cost<<8 | S) of one node for k GPUs, computed by a whole warp: lane per candidate subset.
-__device__ __forceinline__ uint32_t node_key_warp(int k, const int32_t *half, uint32_t fm, int lane) {
+// `subsets` = the k-subsets of 8 in increasing order in SHARED memory (the constant-memory table indexed by lane would
+// serialise: one address per cycle).
+__device__ __forceinline__ uint32_t node_key_warp(int k, const int32_t *half, uint32_t fm, int lane, const uint8_t *subsets, int nsub) {
     if (k == 0) return 0u;
-    const int nsub = c_nsub[k];
     uint32_t key = INF32;
     for (int s = lane; s < nsub; s += 32) {
-        const uint32_t S = c_subsets[k][s];
+        const uint32_t S = subsets[s];
         if (S & ~fm) continue;
         const uint32_t lo = S & 15u, hi = S >> 4;
         uint32_t cost = (uint32_t)half[lo] + (uint32_t)half[16 + hi];
@@ -169,17 +170,20 @@ __device__ __forceinline__ unsigned long long warp_min_u64_redux(unsigned long l
 constexpr int PLACE_POD_CHUNK = 1024;       // pod requests staged in shared memory (16 KB)
 constexpr size_t PLACE_DYN_SMEM = 2 * (size_t)PLACE_SUPER_CAP * sizeof(unsigned long long);
 
-// One persistent block.  Per pod (the serial chain; v3):
+// One persistent block.  Per pod (the serial chain; v4):
 //   1. every warp finds the winner by itself: the supertile minima of (view, k) sit in shared memory (<= a few
 //      entries per lane), the minimum IS the winning (cost, node, subset); two REDUX.  No barrier: the minima are
 //      double buffered by UPDATE EPOCH (an epoch = one pod that placed something): winners are read from copy
 //      e & 1, refreshed values are written to copy (e + 1) & 1 at once and to copy e & 1 one epoch later (by the
 //      same lane, before its new writes), i.e. after the barrier that ends epoch e -- so no warp can see a
 //      refreshed minimum while another still looks for the winner.
-//   2. commit + refresh, warp per (view, k) task: all global loads of a task (the winner's topology row, the
-//      node keys of its tile, the tile minima of its supertile) are issued together, then the warp re-enumerates
-//      the winner (lane per subset, half tables), takes the tile minimum with one REDUX over a 32-bit composite
-//      (cost << 15 | node offset << 8 | S; cost < 2^17) and the supertile minimum with two.
+//   2. commit + refresh, warp per (view, k) task.  Sequential placement keeps hitting the same few nodes (the
+//      cheapest node takes pods until it is full), so every warp CACHES, in registers / its shared-memory rows,
+//      what it loaded for the previous winner: the node's half tables and free mask (same node), the node keys of
+//      its tile (same tile), the tile minima of its supertile (same supertile).  A pod whose winner stays in the
+//      cached supertile touches no global memory on the chain (stores are fire and forget); otherwise all loads
+//      of the task are issued together.  Re-enumeration: lane per subset from the half tables; tile minimum: one
+//      REDUX over a 32-bit composite (cost << 15 | node offset << 8 | S; cost < 2^17); supertile minimum: two.
 //   3. ONE barrier.
 // Pod requests are staged PLACE_POD_CHUNK at a time; indices are 32-bit shifts (supertiles are 32 << j tiles).
 __global__ void __launch_bounds__(PLACE_THREADS, 1)
@@ -189,8 +193,10 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
                  unsigned long long *__restrict__ keys) {
     __shared__ int32_t sW[16];
     __shared__ int32_t sViewMin[PLACE_MAX_VIEWS];                 // static indexing of the kernel parameter only
-    __shared__ int32_t sCost[PLACE_WARPS][64];                    // per warp: the winner node's cost matrix
+    __shared__ int32_t sCost[PLACE_WARPS][64];                    // per warp: the cached node's cost matrix
     __shared__ int32_t sHalf[PLACE_WARPS][PLACE_HALF];            // per warp: its half tables (node_key_warp)
+    __shared__ uint8_t sSub[9][72];                               // the k-subsets of 8 GPUs, increasing
+    __shared__ int32_t sNsub[9];
 #ifdef __CUDACC__
     extern __shared__ unsigned long long sSuperDyn[];             // super[copy][v][k][ST]: 2 x 36 KB of DYNAMIC shared memory
     unsigned long long (*sSuper)[PLACE_SUPER_CAP] = reinterpret_cast<unsigned long long (*)[PLACE_SUPER_CAP]>(sSuperDyn);
@@ -212,6 +218,11 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
 #pragma unroll
         for (int i = 0; i < PLACE_MAX_VIEWS; i++) sViewMin[i] = views.min_mem[i];
     }
+    if (tid < 9) {
+        const int n = c_nsub[tid];
+        sNsub[tid] = n;
+        for (int i = 0; i < n; i++) sSub[tid][i] = c_subsets[tid][i];
+    }
     if (tid < PLACE_MAX_VIEWS * 9) sPendIdx[tid] = -1;
     // supertile minima from the tile minima place_init left in memory (both copies)
     for (int idx = tid; idx < V * 9 * ST; idx += PLACE_THREADS) {
@@ -224,6 +235,14 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
     }
     uint32_t epoch = 0;                                           // block-uniform: pods that placed something so far
     const int ntask = V * 9;
+    // what this warp has cached for its FIRST task (task == warp)
+    int c_node = -1, c_tile = -1, c_st = -1;                      // warp-uniform
+    uint32_t c_fm = 0;
+    int32_t c_mem = 0x7FFFFFFF;                                   // lanes 0..7: memory of the cached node's GPUs
+    uint32_t nbr[PLACE_TILE / 32];                                // per lane: node keys of the cached tile
+    unsigned long long tsr = ~0ull;                               // per lane: minimum of tile c_st * 32 + lane (super_tiles == 32 only)
+#pragma unroll
+    for (int j = 0; j < PLACE_TILE / 32; j++) nbr[j] = INF32;
 
     for (int64_t p0 = 0; p0 < P; p0 += PLACE_POD_CHUNK) {
         const int pn = (int)min((int64_t)PLACE_POD_CHUNK, P - p0);
@@ -256,50 +275,74 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
             const int tile = node >> 7, st = tile >> st_shift;
             static_assert(PLACE_TILE == 128, "tile index is node >> 7");
             if (warp < min(PLACE_WARPS, ntask)) {
-                // every global load this warp needs, issued before anything waits
-                const int32_t l0 = __ldg(topo + (int64_t)node * 64 + lane), l1 = __ldg(topo + (int64_t)node * 64 + lane + 32);
-                const uint32_t fm = ((uint32_t)free_mask[node] & 0xFFu) & ~S;   // old & ~S whether or not warp 0 has written it back
-                const int32_t my_mem = (gpu_mem != nullptr && lane < 8) ? __ldg(gpu_mem + (int64_t)node * 8 + lane) : 0x7FFFFFFF;
-                uint32_t nb0[PLACE_TILE / 32];
-                unsigned long long tb0 = ~0ull;
-                {
-                    const int64_t vk = warp;                  // the first task of this warp
-#pragma unroll
-                    for (int j = 0; j < PLACE_TILE / 32; j++) nb0[j] = nodebest[vk * Npad + tile * PLACE_TILE + lane + 32 * j];
-                    for (int t = (st << st_shift) + lane; t < min(Ti, (st + 1) << st_shift); t += 32)
-                        if (t != tile) tb0 = min(tb0, tilebest[vk * T + t]);
+                const int64_t vk0 = warp;                     // this warp's first (cached) task
+                const bool new_node = node != c_node, new_tile = tile != c_tile;
+                const bool cache_super = super_tiles == 32;
+                const bool new_st = !cache_super || st != c_st;
+                // every global load this pod needs from this warp, issued before anything waits
+                int32_t l0 = 0, l1 = 0;
+                uint32_t fm_mem = 0;
+                if (new_node) {
+                    l0 = __ldg(topo + (int64_t)node * 64 + lane);
+                    l1 = __ldg(topo + (int64_t)node * 64 + lane + 32);
+                    fm_mem = (uint32_t)free_mask[node] & 0xFFu;       // before or after warp 0's write-back: & ~S below either way
+                    c_mem = (gpu_mem != nullptr && lane < 8) ? __ldg(gpu_mem + (int64_t)node * 8 + lane) : 0x7FFFFFFF;
                 }
-                int32_t *cost = sCost[warp];
-                cost[lane] = sW[l0 & 15];
-                cost[lane + 32] = sW[l1 & 15];
-                __syncwarp();
+                if (new_tile) {
+#pragma unroll
+                    for (int j = 0; j < PLACE_TILE / 32; j++) nbr[j] = nodebest[vk0 * Npad + tile * PLACE_TILE + lane + 32 * j];
+                }
+                unsigned long long sb0 = ~0ull;               // !cache_super: minimum over the supertile's OTHER tiles
+                if (cache_super) {
+                    if (new_st) {
+                        const int t = (st << 5) + lane;
+                        tsr = t < Ti ? tilebest[vk0 * T + t] : ~0ull;
+                    }
+                } else {
+                    for (int t = (st << st_shift) + lane; t < min(Ti, (st + 1) << st_shift); t += 32)
+                        if (t != tile) sb0 = min(sb0, tilebest[vk0 * T + t]);
+                }
                 int32_t *half = sHalf[warp];
-                build_half_tables(cost, half, lane);
-                __syncwarp();
+                if (new_node) {
+                    int32_t *cost = sCost[warp];
+                    cost[lane] = sW[l0 & 15];
+                    cost[lane + 32] = sW[l1 & 15];
+                    __syncwarp();
+                    build_half_tables(cost, half, lane);
+                    __syncwarp();
+                    c_fm = fm_mem;
+                    c_node = node;
+                }
+                c_tile = tile;
+                c_st = st;
+                const uint32_t fm = c_fm & ~S;
+                c_fm = fm;
                 if (warp == 0 && lane == 0) free_mask[node] = (int32_t)fm;
                 for (int task = warp; task < ntask; task += PLACE_WARPS) {
                     const int tv = task / 9, tk = task - tv * 9;
                     const int64_t vk = task;
+                    const bool cached = task == warp;
                     uint32_t nb[PLACE_TILE / 32];
-                    unsigned long long sb = ~0ull;
-                    if (task == warp) {
-#pragma unroll
-                        for (int j = 0; j < PLACE_TILE / 32; j++) nb[j] = nb0[j];
-                        sb = tb0;
-                    } else {                                  // more tasks than warps (several views): load now
+                    unsigned long long sb = sb0;
+                    if (!cached) {                            // more tasks than warps (several views): load now
 #pragma unroll
                         for (int j = 0; j < PLACE_TILE / 32; j++) nb[j] = nodebest[vk * Npad + tile * PLACE_TILE + lane + 32 * j];
+                        sb = ~0ull;
                         for (int t = (st << st_shift) + lane; t < min(Ti, (st + 1) << st_shift); t += 32)
                             if (t != tile) sb = min(sb, tilebest[vk * T + t]);
                     }
-                    const uint32_t ok = tv == 0 ? 0xFFu : (__ballot_sync(0xFFFFFFFFu, my_mem >= sViewMin[tv]) & 0xFFu);
-                    const uint32_t nk = node_key_warp(tk, half, fm & ok, lane);
+                    const uint32_t ok = tv == 0 ? 0xFFu : (__ballot_sync(0xFFFFFFFFu, c_mem >= sViewMin[tv]) & 0xFFu);
+                    const uint32_t nk = node_key_warp(tk, half, fm & ok, lane, sSub[tk], sNsub[tk]);
                     // tile minimum: 32-bit composite cost << 15 | node offset << 8 | S (cost <= 28 * 4095 < 2^17)
                     uint32_t m = INF32;
 #pragma unroll
                     for (int j = 0; j < PLACE_TILE / 32; j++) {
                         const int off = lane + 32 * j;
-                        const uint32_t key = (tile * PLACE_TILE + off == node) ? nk : nb[j];
+                        uint32_t key = cached ? nbr[j] : nb[j];
+                        if (tile * PLACE_TILE + off == node) {
+                            key = nk;
+                            if (cached) nbr[j] = nk;
+                        }
                         if (key != INF32) m = min(m, ((key >> 8) << 15) | ((uint32_t)off << 8) | (key & 0xFFu));
                     }
                     m = __reduce_min_sync(0xFFFFFFFFu, m);
@@ -307,7 +350,12 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
                         m == INF32 ? ~0ull
                                    : (((unsigned long long)(m >> 15) << 40) |
                                       ((unsigned long long)(node_id_base + (int64_t)tile * PLACE_TILE + ((m >> 8) & 127u)) << 8) | (m & 0xFFu));
-                    sb = warp_min_u64_redux(min(sb, tb));
+                    if (cached && cache_super) {
+                        if (lane == (tile & 31)) tsr = tb;
+                        sb = warp_min_u64_redux(tsr);
+                    } else {
+                        sb = warp_min_u64_redux(min(sb, tb));
+                    }
                     if (lane == 0) {
                         nodebest[vk * Npad + node] = nk;
                         tilebest[vk * T + tile] = tb;

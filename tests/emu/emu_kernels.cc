@@ -186,13 +186,14 @@ long long emu_validate_topo(const int32_t *topo, int64_t n) {
 
 // The peer-exchange kernel with world = 1 (the rank pushes into its own result array and passes its own
 // barrier): exercises the push, the last-block ticket and the flag protocol, not the cross-GPU part.
-void emu_push_and_sync(const unsigned long long *local, int64_t P, unsigned long long *result, uint32_t *flags,
-                       uint32_t epoch, unsigned int *ticket) {
+void emu_push_and_sync(unsigned long long *local, int64_t P, unsigned long long *result, uint32_t *flags,
+                       uint32_t epoch, unsigned int *ticket, unsigned long long *other, int64_t clean_len) {
     kgpu::PeerTable tab;
     std::memset(&tab, 0, sizeof tab);
     tab.results[0] = result;
     tab.flags[0] = flags;
-    emu::launch(dim3((unsigned)((P + 255) / 256)), dim3(256), [&] { kgpu::push_and_sync(local, P, tab, 0, 1, epoch, ticket); });
+    emu::launch(dim3((unsigned)((P + 255) / 256)), dim3(256),
+                [&] { kgpu::push_and_sync(local, P, tab, 0, 1, epoch, ticket, other, clean_len); });
 }
 
 // The host-side work-list builder alone (sparse_work.h): items as int32[.][4] {tile, pod_begin, pod_end, ntiles} and

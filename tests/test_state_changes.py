@@ -25,7 +25,7 @@ def test_batched_mask_updates_track_the_oracle(scorer, oracle_b):
     assert scorer.last_upload_ms > 0.0
     assert (scorer.score_batch(pods) == oracle_b.score_batch(topo, f, pods, fast=True, nthreads=8)).all()
     rng = np.random.default_rng(7)
-    for rnd in range(8):                       # 8 x 1500 changed nodes: crosses the re-sort threshold (n / 8) on the way
+    for rnd in range(8):                       # 8 x 1500 changed nodes: crosses the re-sort threshold (n / 200) every round
         idx = rng.integers(0, len(f), size=1500).astype(np.int64)         # duplicates happen: the last one wins
         masks = rng.integers(0, 256, size=1500).astype(np.int32)
         scorer.set_free_masks(idx, masks)
