@@ -44,7 +44,11 @@
  *                             all nodes and all k-subsets of free GPUs, so ties go
  *                             to the lower node_id, then the lower mask.
  *
- * Threading: every call on one handle is serialised by an internal mutex.
+ * Threading: every call on one handle is serialised by an internal mutex.  State-changing calls (upload, update,
+ * set_free_mask(s), place_batch) and the lazy rebuilds they trigger run on the handle's own stream and have COMPLETED
+ * when the call returns, so a following launch on any stream sees them.  The *_device entry points only enqueue: all
+ * such calls on one handle must go to ONE stream at a time (the handle's per-batch scratch -- the "batch has
+ * memory-constrained pods" flag, the work list -- is not duplicated per stream); use one handle per stream otherwise.
  * Errors: functions return KGPU_OK (0) or a negative KGPU_ERR_*; the message is
  * kept per handle (kgpu_last_error(h)) and per thread (kgpu_last_error(NULL)).
  * "No node fits" is a result (KGPU_NO_FIT), never an error.  Nothing here falls
