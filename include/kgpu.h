@@ -76,11 +76,14 @@ extern "C" {
 #define KGPU_MAX_WEIGHT 4095
 
 /* Kernel variants of K1 `score_pairs` (all bit-identical in result). */
-#define KGPU_VARIANT_AUTO 0          /* = SPARSE                                             */
+#define KGPU_VARIANT_AUTO 0          /* default: the cheapest path with identical keys for the batch at hand: pods without a
+                                      * memory requirement are memoised by k (best[k] over all nodes once, then a gather),
+                                      * pods with one are scored per pair by the memory-aware kernel (K1m)          */
 #define KGPU_VARIANT_WARP_PER_PAIR 1 /* north_star mapping: warp per (pod,node), lane per subset */
 #define KGPU_VARIANT_LANE_PER_NODE 2 /* lane per node, pair costs in registers, all C(8,k) subsets per pair */
-#define KGPU_VARIANT_MEMO_BY_K 3     /* global best[k] computed once, pods look it up (NOT the headline) */
-#define KGPU_VARIANT_SPARSE 5        /* lane per node, nodes ordered by free-GPU count, enumeration over free positions only */
+#define KGPU_VARIANT_MEMO_BY_K 3     /* global best[k] computed once, pods look it up (what AUTO does; dense K1m for min_mem pods) */
+#define KGPU_VARIANT_SPARSE 5        /* PER-PAIR work (north_star): lane per node, nodes ordered by free-GPU count, every pod
+                                      * enumerates the k-subsets of the node's free positions; bench.py's headline      */
 #define KGPU_VARIANT_TILE_MEMO 4     /* lane per node, per-k minima hoisted out of the pod loop (NOT the headline) */
 
 #define KGPU_KEY_COST(key) ((uint32_t)((key) >> 40))

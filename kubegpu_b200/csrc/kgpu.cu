@@ -89,7 +89,7 @@ struct kgpu_ctx {
     std::string err;
     std::vector<kgpu_shard> shards;
     int32_t W[16];
-    int variant = KGPU_VARIANT_SPARSE;
+    int variant = KGPU_VARIANT_AUTO;
     int64_t n_total = 0;
     int64_t launches = 0;
     double last_kernel_ms = 0.0;
@@ -341,8 +341,15 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
     if (!keys_are_clean) KGPU_CUDA(h, cudaMemsetAsync(d_keys, 0xFF, (size_t)P * 8, st));
     if (s.n == 0) return KGPU_OK;
 
+    // AUTO (the default): whatever is cheapest for THIS batch with identical keys -- pods without a memory requirement
+    // are memoisable by k under snapshot scoring (best[k] over all nodes once, then a gather: memo_best_by_k /
+    // memo_gather), pods with one go to K1m (the sparse MEM instantiation).  The per-pair kernels are the explicitly
+    // named variants (KGPU_VARIANT_SPARSE = what bench.py's headline times, per north_star).
+    const bool automode = h->variant == KGPU_VARIANT_AUTO;
+    const bool memo = automode || h->variant == KGPU_VARIANT_MEMO_BY_K;
     const bool wpp = h->variant == KGPU_VARIANT_WARP_PER_PAIR;
-    const bool sparse = h->variant == KGPU_VARIANT_SPARSE;
+    const bool sparse_main = h->variant == KGPU_VARIANT_SPARSE;
+    const bool sparse = sparse_main || (automode && has_mem != 0);
     if (sparse) {                      // order + compacted records current?  (no-op unless nodes / masks / weights changed)
         const int rc = ensure_node_cache(h, s);
         if (rc != KGPU_OK) return rc;
@@ -352,7 +359,7 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
         kgpu::any_mem_pod<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(pods4, P, s.d_flag);
         h->launches++;
     }
-    if (h->variant == KGPU_VARIANT_MEMO_BY_K) {
+    if (memo) {
         KGPU_CUDA(h, cudaMemsetAsync(s.d_bestk, 0xFF, 9 * 8, st));
         int blocks = (int)std::min<int64_t>((s.n + kgpu::LPN_THREADS - 1) / kgpu::LPN_THREADS, (int64_t)s.sm_count * 4);
         kgpu::memo_best_by_k<<<blocks, kgpu::LPN_THREADS, 0, st>>>(topo4, s.d_free, s.n, s.node_id_base, W, PC, s.d_bestk);
@@ -399,6 +406,12 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
                     kgpu::SparseWorkParams prm;
                     static const int max_run = [] { const char *e = getenv("KGPU_SP_MAXRUN"); return e ? atoi(e) : 0; }();
                     if (max_run > 0) prm.max_run = max_run;
+                    static const int env_tail = [] { const char *e = getenv("KGPU_SP_TAIL"); return e ? atoi(e) : -1; }();
+                    static const int env_waves = [] { const char *e = getenv("KGPU_SP_WAVES"); return e ? atoi(e) : -1; }();
+                    static const int env_floor = [] { const char *e = getenv("KGPU_SP_FLOOR"); return e ? atoi(e) : -1; }();
+                    if (env_tail >= 0) prm.tail_percent = env_tail;
+                    if (env_waves > 0) prm.waves = env_waves;
+                    if (env_floor > 0) prm.floor = env_floor;
                     const int64_t res_list = P <= kgpu::kSparseChunk ? (int64_t)s.sm_count * KGPU_SP_STREAM_MINBLOCKS : resident;
                     kgpu::build_sparse_work(s.tile_class, P, res_list, s.h_work, prm);
                     if ((int64_t)s.h_work.size() > s.work_cap) {
@@ -422,9 +435,11 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
             // few pods (the batch is one chunk): the work list holds runs of tiles -> the STREAM instantiation
             // (next tile's record prefetched into registers while the current one is scored)
             const bool stream_build = use_work && P <= kgpu::kSparseChunk;
-            if (stream_build) { if (byte_keys) KGPU_LAUNCH_SPARSE(false, true, true); else KGPU_LAUNCH_SPARSE(false, false, true); }
-            else              { if (byte_keys) KGPU_LAUNCH_SPARSE(false, true, false); else KGPU_LAUNCH_SPARSE(false, false, false); }
-            h->launches++;
+            if (sparse_main) {
+                if (stream_build) { if (byte_keys) KGPU_LAUNCH_SPARSE(false, true, true); else KGPU_LAUNCH_SPARSE(false, false, true); }
+                else              { if (byte_keys) KGPU_LAUNCH_SPARSE(false, true, false); else KGPU_LAUNCH_SPARSE(false, false, false); }
+                h->launches++;
+            }
             if (has_mem != 0) {
                 if (byte_keys) KGPU_LAUNCH_SPARSE(true, true, false); else KGPU_LAUNCH_SPARSE(true, false, false);
                 h->launches++;
@@ -598,8 +613,7 @@ int kgpu_get_weights(kgpu_t *h, int32_t w[KGPU_NUM_LEVELS]) {
 int kgpu_set_variant(kgpu_t *h, int variant) {
     if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_set_variant: NULL handle");
     std::lock_guard<std::mutex> g(h->mu);
-    if (variant == KGPU_VARIANT_AUTO) variant = KGPU_VARIANT_SPARSE;
-    if (variant < KGPU_VARIANT_WARP_PER_PAIR || variant > KGPU_VARIANT_SPARSE)
+    if (variant < KGPU_VARIANT_AUTO || variant > KGPU_VARIANT_SPARSE)
         return fail(h, KGPU_ERR_INVALID, "kgpu_set_variant: unknown variant %d", variant);
     h->variant = variant;
     return KGPU_OK;

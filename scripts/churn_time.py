@@ -8,7 +8,7 @@ import torch
 from kubegpu_b200 import _lib, synth
 from kubegpu_b200.scorer import Scorer
 topo, free, pods = synth.gen_c2()
-s = Scorer((0,)); s.upload_nodes(topo, free)
+s = Scorer((0,)); s.set_variant(_lib.VARIANT_SPARSE); s.upload_nodes(topo, free)
 hp = torch.from_numpy(pods).pin_memory(); hk = torch.empty(len(pods), dtype=torch.int64).pin_memory()
 for _ in range(3): s.score_batch_ptr(hp.data_ptr(), len(pods), hk.data_ptr())
 t0 = time.perf_counter()

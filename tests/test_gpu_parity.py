@@ -10,7 +10,7 @@ from kubegpu_b200 import _lib, synth
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [_lib.VARIANT_LANE_PER_NODE, _lib.VARIANT_WARP_PER_PAIR, _lib.VARIANT_MEMO_BY_K, _lib.VARIANT_TILE_MEMO,
+VARIANTS = [_lib.VARIANT_AUTO, _lib.VARIANT_LANE_PER_NODE, _lib.VARIANT_WARP_PER_PAIR, _lib.VARIANT_MEMO_BY_K, _lib.VARIANT_TILE_MEMO,
             _lib.VARIANT_SPARSE]
 
 

@@ -48,7 +48,7 @@ def test_synth_c6_shapes():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", [_lib.VARIANT_LANE_PER_NODE, _lib.VARIANT_WARP_PER_PAIR, _lib.VARIANT_MEMO_BY_K,
+@pytest.mark.parametrize("variant", [_lib.VARIANT_AUTO, _lib.VARIANT_LANE_PER_NODE, _lib.VARIANT_WARP_PER_PAIR, _lib.VARIANT_MEMO_BY_K,
                                      _lib.VARIANT_TILE_MEMO, _lib.VARIANT_SPARSE])
 def test_gpu_memory_aware_parity(oracle_b, variant):
     from kubegpu_b200.scorer import KgpuError, Scorer
