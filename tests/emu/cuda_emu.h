@@ -159,6 +159,8 @@ inline T __shfl_up_sync(unsigned, T v, int delta, int = 32) {      // lanes belo
 template <class T>
 inline T __ldg(const T *p) { return *p; }
 template <class T>
+inline T __ldcg(const T *p) { return *p; }
+template <class T>
 inline unsigned long long __cvta_generic_to_shared(T *p) { return (unsigned long long)(uintptr_t)p; }
 inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned atomicMin(unsigned *p, unsigned v) {
@@ -179,6 +181,7 @@ inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 // ---- integer intrinsics ----------------------------------------------------------------------------------
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __ffs(unsigned x) { return x == 0 ? 0 : __builtin_ctz(x) + 1; }
 inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 inline unsigned __vimin3_u32(unsigned a, unsigned b, unsigned c) { unsigned m = a < b ? a : b; return m < c ? m : c; }
 inline unsigned __vimax3_u32(unsigned a, unsigned b, unsigned c) { unsigned m = a > b ? a : b; return m > c ? m : c; }
