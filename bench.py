@@ -403,8 +403,11 @@ def main():
         token = torch.zeros(1, device=dev)
         for a, b in ev:
             flush.zero_()
-            if world > 1 and rendezvous:
-                dist.all_reduce(token)                 # device-side rendezvous so no rank times another's flush
+            if world > 1 and rendezvous:               # device-side rendezvous so no rank times another's flush
+                if push:
+                    scorer.exchange_barrier(stream.cuda_stream)   # the exchange kernel's own flag barrier: ranks leave within ~1 us
+                else:
+                    dist.all_reduce(token)             # (a ring all-reduce releases its ranks several us apart)
             a.record(stream)
             fn()
             b.record(stream)
@@ -478,7 +481,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "nodes": N_NODES, "pods": N_PODS,
-                       "parallelism": ("node list sharded over %d GPU(s), " % world + {"push": "peer-memory push + flag barrier (1 kernel, NVLink atomics)",
+                       "parallelism": ("node list sharded over %d GPU(s), " % world + {"push": "peer-memory exchange: stores into every rank's slots + flag barrier + local min (1 kernel over NVLink)",
                                                                                        "allreduce": "1 NCCL all-reduce(min)",
                                                                                        "nccl": "1 NCCL all-gather + K2"}[exchange]) if world > 1 else "1 GPU, no collective",
                        "kernel": "score_pairs_sparse (per pair: every k-subset of the node's free-GPU positions; not memoised by k: see `memoised`)",

@@ -189,21 +189,24 @@ int kgpu_get_free_masks(kgpu_t *h, int32_t *out_free_mask, int64_t n);
 int kgpu_reduce_shards_device(kgpu_t *h, const uint64_t *d_gathered, int G, int64_t P,
                               uint64_t *d_out, void *stream);
 
-/* Peer-memory key exchange for the one-process-per-GPU launch (EXPERIMENTAL; replaces the all-gather +
- * kgpu_reduce_shards_device pair; no reference counterpart).  Every rank:
- *   kgpu_exchange_init(h, world, rank, max_pods, handle)   allocate the rank's result/flag memory, export it
+/* Peer-memory key exchange for the one-process-per-GPU launch (replaces the all-gather + kgpu_reduce_shards_device pair;
+ * no reference counterpart).  Every rank:
+ *   kgpu_exchange_init(h, world, rank, max_pods, handle)   allocate the rank's slot/flag memory, export it
  *   <all-gather the KGPU_IPC_HANDLE_BYTES-byte handles through the launcher, e.g. torch.distributed>
  *   kgpu_exchange_connect(h, handles)                      map every peer's memory (handles = [world][64])
- *   kgpu_score_batch_exchange(h, d_pods, P, &d_final, stream)   per step: K1 on the local shard, then one
- *       kernel pushes the P bests into every rank's result array (64-bit atomic min over NVLink) and meets
- *       the other ranks at a flag barrier in peer memory.  *d_final (device memory owned by the handle,
- *       valid until the next-but-one call) then holds the global per-pod keys on every rank.
- * All ranks must make the same sequence of kgpu_score_batch_exchange calls.  Single-device handles only. */
+ *   kgpu_score_batch_exchange(h, d_pods, P, &d_final, stream, flags)   per step, TWO launches: K1 on the local shard, then
+ *       one kernel that stores the P bests into every rank's slot array over NVLink (plain coalesced stores), meets the
+ *       other ranks at a flag barrier in peer memory and takes the per-pod minimum over the G slots.  *d_final (device
+ *       memory owned by the handle, valid until the next-but-one call) then holds the global keys on every rank.
+ *   kgpu_exchange_barrier(h, stream)                       the same kernel with P = 0: a device-side barrier of the ranks
+ * All ranks must make the same sequence of exchange calls.  A rank that waits more than ~2 s for its peers raises an
+ * error (reported as KGPU_ERR_COMM by a later call) instead of hanging the GPU.  Single-device handles only. */
 #define KGPU_IPC_HANDLE_BYTES 64
 int kgpu_exchange_init(kgpu_t *h, int world, int rank, int64_t max_pods, unsigned char *out_handle);
 int kgpu_exchange_connect(kgpu_t *h, const unsigned char *handles);
 int kgpu_score_batch_exchange(kgpu_t *h, const int32_t *d_pods, int64_t P, const uint64_t **d_final_keys,
                               void *stream, int batch_flags);
+int kgpu_exchange_barrier(kgpu_t *h, void *stream);
 
 /* Number of CUDA kernels this handle has launched so far (bench bookkeeping). */
 int64_t kgpu_kernel_launches(kgpu_t *h);

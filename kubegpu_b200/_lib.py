@@ -13,7 +13,7 @@ SYMBOLS = [
     "kgpu_version", "kgpu_create", "kgpu_destroy", "kgpu_last_error", "kgpu_set_weights",
     "kgpu_get_weights", "kgpu_set_variant", "kgpu_upload_nodes", "kgpu_update_node",
     "kgpu_set_free_mask", "kgpu_set_free_masks", "kgpu_remove_node", "kgpu_build_fit_table", "kgpu_fit_lookup", "kgpu_last_upload_ms", "kgpu_upload_gpu_memory", "kgpu_update_gpu_memory", "kgpu_num_nodes", "kgpu_score_batch",
-    "kgpu_score_batch_device", "kgpu_score_batch_device_ex", "kgpu_score_pairs", "kgpu_place_batch", "kgpu_place_batch_ex", "kgpu_get_free_masks", "kgpu_reduce_shards_device", "kgpu_exchange_init", "kgpu_exchange_connect", "kgpu_score_batch_exchange", "kgpu_kernel_launches",
+    "kgpu_score_batch_device", "kgpu_score_batch_device_ex", "kgpu_score_pairs", "kgpu_place_batch", "kgpu_place_batch_ex", "kgpu_get_free_masks", "kgpu_reduce_shards_device", "kgpu_exchange_init", "kgpu_exchange_connect", "kgpu_score_batch_exchange", "kgpu_exchange_barrier", "kgpu_kernel_launches",
     "kgpu_last_kernel_ms",
 ]
 
@@ -98,6 +98,8 @@ def load() -> ctypes.CDLL:
     L.kgpu_exchange_connect.argtypes = [vp, vp]
     L.kgpu_score_batch_exchange.restype = ci
     L.kgpu_score_batch_exchange.argtypes = [vp, vp, i64, ctypes.POINTER(vp), vp, ci]
+    L.kgpu_exchange_barrier.restype = ci
+    L.kgpu_exchange_barrier.argtypes = [vp, vp]
     L.kgpu_kernel_launches.restype = i64
     L.kgpu_kernel_launches.argtypes = [vp]
     L.kgpu_last_kernel_ms.restype = ctypes.c_double

@@ -97,15 +97,15 @@ struct kgpu_ctx {
     double last_upload_ms = 0.0;
     kgpu::MultiDevice *multi = nullptr;   // NCCL communicator set, ndev > 1 only
     // peer-memory key exchange (kgpu_exchange_*): one allocation per rank, mapped by every peer:
-    //   results[2][max_pods] uint64 | flags[PEER_MAX_WORLD] uint32 | ticket uint32 ;  local[] is private
+    //   slots[2][world][max_pods] uint64 | flags[PEER_MAX_WORLD] uint32 | ticket | error ;  local[] and final_keys[] are private
     struct {
         int world = 0, rank = 0;
         int64_t max_pods = 0;
         void *base = nullptr;
         void *peer_base[kgpu::PEER_MAX_WORLD] = {};
         unsigned long long *local = nullptr;
+        unsigned long long *final_keys = nullptr;   // [2][max_pods]: the global keys of the last two epochs
         uint32_t epoch = 0;
-        int64_t used_len[2] = {0, 0};       // entries of each result buffer that may hold keys (cleaned by the push kernel)
         bool connected = false;
     } xch;
 };
@@ -586,6 +586,7 @@ int kgpu_destroy(kgpu_t *h) {
             if (h->xch.connected && r != h->xch.rank && h->xch.peer_base[r]) cudaIpcCloseMemHandle(h->xch.peer_base[r]);
         cudaFree(h->xch.base);
         cudaFree(h->xch.local);
+        cudaFree(h->xch.final_keys);
     }
     for (auto &s : h->shards) free_shard(s);
     delete h;
@@ -1048,9 +1049,15 @@ int kgpu_score_batch_device_ex(kgpu_t *h, const int32_t *d_pods, int64_t P, uint
 }
 
 namespace {
-size_t xch_bytes(int64_t max_pods) { return (size_t)max_pods * 16 + kgpu::PEER_MAX_WORLD * 4 + 16; }
-unsigned long long *xch_results(void *base, int64_t max_pods, int buf) { return reinterpret_cast<unsigned long long *>(base) + (int64_t)buf * max_pods; }
-uint32_t *xch_flags(void *base, int64_t max_pods) { return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(base) + (size_t)max_pods * 16); }
+// one allocation per rank, mapped by every peer: slots[2][world][max_pods] uint64 | flags[PEER_MAX_WORLD] uint32 | ticket | error
+size_t xch_slot_bytes(int world, int64_t max_pods) { return (size_t)2 * world * max_pods * 8; }
+size_t xch_bytes(int world, int64_t max_pods) { return xch_slot_bytes(world, max_pods) + kgpu::PEER_MAX_WORLD * 4 + 16; }
+unsigned long long *xch_slots(void *base, int world, int64_t max_pods, int buf) {
+    return reinterpret_cast<unsigned long long *>(base) + (int64_t)buf * world * max_pods;
+}
+uint32_t *xch_flags(void *base, int world, int64_t max_pods) {
+    return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(base) + xch_slot_bytes(world, max_pods));
+}
 }  // namespace
 
 int kgpu_exchange_init(kgpu_t *h, int world, int rank, int64_t max_pods, unsigned char *out_handle) {
@@ -1063,11 +1070,12 @@ int kgpu_exchange_init(kgpu_t *h, int world, int rank, int64_t max_pods, unsigne
     if (h->xch.base) return fail(h, KGPU_ERR_STATE, "kgpu_exchange_init: already initialised");
     kgpu_shard &s = h->shards[0];
     KGPU_CUDA(h, cudaSetDevice(s.dev));
-    KGPU_CUDA(h, cudaMalloc(&h->xch.base, xch_bytes(max_pods)));
+    KGPU_CUDA(h, cudaMalloc(&h->xch.base, xch_bytes(world, max_pods)));
     KGPU_CUDA(h, cudaMalloc(&h->xch.local, (size_t)max_pods * 8));
-    KGPU_CUDA(h, cudaMemset(h->xch.base, 0xFF, (size_t)max_pods * 16));                                   // both result buffers: NO_FIT
-    KGPU_CUDA(h, cudaMemset(h->xch.local, 0xFF, (size_t)max_pods * 8));                                   // the push kernel keeps it that way
-    KGPU_CUDA(h, cudaMemset(xch_flags(h->xch.base, max_pods), 0, kgpu::PEER_MAX_WORLD * 4 + 16));         // flags, ticket
+    KGPU_CUDA(h, cudaMalloc(&h->xch.final_keys, (size_t)max_pods * 8 * 2));
+    KGPU_CUDA(h, cudaMemset(h->xch.base, 0xFF, xch_slot_bytes(world, max_pods)));
+    KGPU_CUDA(h, cudaMemset(h->xch.local, 0xFF, (size_t)max_pods * 8));                                   // the exchange kernel keeps it that way
+    KGPU_CUDA(h, cudaMemset(xch_flags(h->xch.base, world, max_pods), 0, kgpu::PEER_MAX_WORLD * 4 + 16));  // flags, ticket, error
     KGPU_CUDA(h, cudaDeviceSynchronize());
     cudaIpcMemHandle_t ipc;
     KGPU_CUDA(h, cudaIpcGetMemHandle(&ipc, h->xch.base));
@@ -1093,6 +1101,44 @@ int kgpu_exchange_connect(kgpu_t *h, const unsigned char *handles) {
     return KGPU_OK;
 }
 
+namespace {
+// K1 (P > 0) + the exchange kernel on `st`; *d_final (may be NULL) receives where the global keys will be
+int exchange_step(kgpu_ctx *h, const int32_t *d_pods, int64_t P, const uint64_t **d_final_keys, cudaStream_t st, int batch_flags) {
+    kgpu_shard &s = h->shards[0];
+    KGPU_CUDA(h, cudaSetDevice(s.dev));
+    const int world = h->xch.world;
+    const int64_t mp = h->xch.max_pods;
+    int *d_err = reinterpret_cast<int *>(xch_flags(h->xch.base, world, mp) + kgpu::PEER_MAX_WORLD + 1);
+    if (h->xch.epoch > 0 && (h->xch.epoch & 1023u) == 0) {     // now and then: did a wait time out?  (costs a sync, so rarely)
+        int err = 0;
+        KGPU_CUDA(h, cudaMemcpyAsync(&err, d_err, sizeof err, cudaMemcpyDeviceToHost, st));
+        KGPU_CUDA(h, cudaStreamSynchronize(st));
+        if (err) return fail(h, KGPU_ERR_COMM, "key exchange: a rank waited more than ~2 s for its peers (ranks out of step or a peer died)");
+    }
+    const uint32_t epoch = ++h->xch.epoch;
+    const int buf = (int)(epoch & 1u);
+    unsigned long long *fin = h->xch.final_keys + (int64_t)buf * mp;
+    if (d_final_keys) *d_final_keys = reinterpret_cast<const uint64_t *>(fin);
+    if (P > 0) {
+        // K1 accumulates into xch.local (kept at NO_FIT between steps by the exchange kernel)
+        const int rc = launch_score(h, s, d_pods, P, h->xch.local, st, (batch_flags & KGPU_BATCH_NO_MIN_MEM) ? 0 : -1, true);
+        if (rc != KGPU_OK) return rc;
+    }
+    kgpu::PeerTable tab;
+    memset(&tab, 0, sizeof tab);
+    for (int r = 0; r < world; r++) {
+        tab.slots[r] = xch_slots(h->xch.peer_base[r], world, mp, buf);
+        tab.flags[r] = xch_flags(h->xch.peer_base[r], world, mp);
+    }
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(xch_flags(h->xch.base, world, mp) + kgpu::PEER_MAX_WORLD);
+    kgpu::gather_and_min<<<(unsigned)std::max<int64_t>(1, (P + 255) / 256), 256, 0, st>>>(h->xch.local, P, mp, tab, h->xch.rank, world, epoch, ticket,
+                                                                                        fin, d_err);
+    h->launches++;
+    KGPU_CUDA(h, cudaGetLastError());
+    return KGPU_OK;
+}
+}  // namespace
+
 int kgpu_score_batch_exchange(kgpu_t *h, const int32_t *d_pods, int64_t P, const uint64_t **d_final_keys, void *stream,
                               int batch_flags) {
     if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_score_batch_exchange: NULL handle");
@@ -1100,32 +1146,14 @@ int kgpu_score_batch_exchange(kgpu_t *h, const int32_t *d_pods, int64_t P, const
     if (!h->xch.connected) return fail(h, KGPU_ERR_STATE, "kgpu_score_batch_exchange: exchange not connected");
     if (P < 0 || P > h->xch.max_pods || (P > 0 && !d_pods) || !d_final_keys)
         return fail(h, KGPU_ERR_INVALID, "kgpu_score_batch_exchange: bad arguments (P <= max_pods of kgpu_exchange_init)");
-    kgpu_shard &s = h->shards[0];
-    cudaStream_t st = (cudaStream_t)stream;
-    KGPU_CUDA(h, cudaSetDevice(s.dev));
-    const uint32_t epoch = ++h->xch.epoch;
-    const int buf = (int)(epoch & 1u);
-    const int64_t mp = h->xch.max_pods;
-    *d_final_keys = reinterpret_cast<const uint64_t *>(xch_results(h->xch.base, mp, buf));
-    if (P == 0) return KGPU_OK;
-    // K1 accumulates into xch.local (kept at NO_FIT between steps by the push kernel), then ONE kernel pushes, cleans
-    // the other result buffer and meets the peers: two launches per step
-    const int rc = launch_score(h, s, d_pods, P, h->xch.local, st, (batch_flags & KGPU_BATCH_NO_MIN_MEM) ? 0 : -1, true);
-    if (rc != KGPU_OK) return rc;
-    kgpu::PeerTable tab;
-    memset(&tab, 0, sizeof tab);
-    for (int r = 0; r < h->xch.world; r++) {
-        tab.results[r] = xch_results(h->xch.peer_base[r], mp, buf);
-        tab.flags[r] = xch_flags(h->xch.peer_base[r], mp);
-    }
-    unsigned int *ticket = reinterpret_cast<unsigned int *>(xch_flags(h->xch.base, mp) + kgpu::PEER_MAX_WORLD);
-    kgpu::push_and_sync<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(h->xch.local, P, tab, h->xch.rank, h->xch.world, epoch, ticket,
-                                                                     xch_results(h->xch.base, mp, buf ^ 1), h->xch.used_len[buf ^ 1]);
-    h->xch.used_len[buf ^ 1] = 0;
-    h->xch.used_len[buf] = P;
-    h->launches++;
-    KGPU_CUDA(h, cudaGetLastError());
-    return KGPU_OK;
+    return exchange_step(h, d_pods, P, d_final_keys, (cudaStream_t)stream, batch_flags);
+}
+
+int kgpu_exchange_barrier(kgpu_t *h, void *stream) {
+    if (!h) return fail(h, KGPU_ERR_INVALID, "kgpu_exchange_barrier: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->xch.connected) return fail(h, KGPU_ERR_STATE, "kgpu_exchange_barrier: exchange not connected");
+    return exchange_step(h, nullptr, 0, nullptr, (cudaStream_t)stream, 0);
 }
 
 int kgpu_reduce_shards_device(kgpu_t *h, const uint64_t *d_gathered, int G, int64_t P, uint64_t *d_out, void *stream) {

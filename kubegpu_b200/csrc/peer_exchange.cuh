@@ -1,16 +1,20 @@
 // peer_exchange.cuh -- the multi-GPU key exchange over peer memory (NVLink / NVSwitch), for the
-// one-process-per-GPU launch.  Replaces "all-gather every rank's keys, then K2" (two launches through NCCL
-// and a reduction kernel) by ONE kernel per rank:
-//   * every rank owns a result array in memory its peers have mapped (CUDA IPC);
-//   * push: thread p sends this rank's best key of pod p into EVERY rank's result array with a 64-bit
-//     system-scope atomic min (P * G atomics of 8 bytes: 640 KB at P = 10k, G = 8; NO_FIT is not sent);
-//   * sync: the last block to finish (atomic ticket) publishes "rank r has pushed epoch e" into every
-//     rank's flag array and spins until all G ranks have published e.  When the kernel ends, this rank's
-//     result array holds the global per-pod minimum, the same on every rank.
-// Result arrays are double buffered by epoch parity; the OTHER buffer is cleaned by this kernel before the rank's
-// arrival flag is set, so it is clean before any peer can reach the next epoch (they pass this epoch's barrier
-// only after this rank arrived at it).
-// Measured (round 2, 2 x B200, C2): keys bit-identical to one GPU and to the NCCL path (tests/test_gpu_multi.py).
+// one-process-per-GPU launch.  Replaces "NCCL all-gather of every rank's keys, then K2" by ONE kernel per rank:
+//   * every rank owns slot arrays slots[2][G][max_pods] in memory its peers have mapped (CUDA IPC);
+//   * store: thread p writes this rank's best key of pod p into slot [rank] of EVERY rank's array with a plain
+//     8-byte store (coalesced, posted writes over NVLink: P * G * 8 bytes, 640 KB at P = 10k, G = 8) and resets the
+//     rank's local key array behind itself (K1 of the next step accumulates into it with atomic min);
+//   * sync: per block one system-scope fence (thread 0, after the block barrier: cumulative) and a ticket; the last
+//     block publishes "rank r has stored epoch e" into every rank's flag array; EVERY block then waits until all G
+//     flags of its own rank carry e;
+//   * min: thread p takes the minimum over the G slots of pod p (local reads) -> final[p].
+// Slot arrays are double buffered by epoch parity: a peer can run at most one epoch ahead (it passes this epoch's
+// barrier only after this rank arrived at it, i.e. after this rank finished READING the previous epoch), and then it
+// writes the other buffer.  No atomics on the data path, no cleaning: every slot is overwritten every epoch.
+// Round-2 history: the first version pushed with 64-bit system-scope atomic min into one result array per rank and
+// fenced per thread (correct, tests/test_gpu_multi.py; measured 18 us at 2 GPUs, 33 us at 8 -- no better than NCCL).
+// P == 0 is a pure barrier (bench.py aligns the ranks with it before each timed step).
+// A wait that exceeds ~2 s (a peer died, ranks out of step) raises *error instead of hanging the GPU.
 #pragma once
 #include <cstdint>
 
@@ -19,45 +23,51 @@ namespace kgpu {
 constexpr int PEER_MAX_WORLD = 16;
 
 struct PeerTable {
-    unsigned long long *results[PEER_MAX_WORLD];   // every rank's result array of THIS epoch's parity (own entry included)
+    unsigned long long *slots[PEER_MAX_WORLD];     // every rank's slot array of THIS epoch's parity: [G][max_pods]
     uint32_t *flags[PEER_MAX_WORLD];               // every rank's flag array [world]
 };
 
-// The step is TWO launches per rank (K1 + this kernel): the kernel also does the housekeeping the host used to enqueue
-// as memsets -- it resets the rank's local key array behind itself (K1 of the next step accumulates into it with atomic
-// min) and cleans the OTHER result buffer (entries [0, clean_len): what the step before last left there) BEFORE the rank
-// announces its arrival, so the buffer is clean before any peer can pass this epoch's barrier and push the next epoch.
 __global__ void __launch_bounds__(256)
-push_and_sync(unsigned long long *__restrict__ local_keys, int64_t P, PeerTable peers, int rank, int world,
-              uint32_t epoch, unsigned int *ticket, unsigned long long *__restrict__ other_buffer, int64_t clean_len) {
+gather_and_min(unsigned long long *__restrict__ local_keys, int64_t P, int64_t max_pods, PeerTable peers, int rank, int world,
+               uint32_t epoch, unsigned int *ticket, unsigned long long *__restrict__ final_keys, int *error) {
     __shared__ bool last;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < clean_len; i += stride) other_buffer[i] = ~0ull;
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < P) {
         const unsigned long long k = local_keys[p];
         local_keys[p] = ~0ull;                     // ready for the next step's K1
-        if (k != ~0ull) {
 #pragma unroll 1
-            for (int g = 0; g < world; g++) atomicMin_system(peers.results[g] + p, k);
+        for (int g = 0; g < world; g++) peers.slots[g][(int64_t)rank * max_pods + p] = k;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();                    // the block's stores (cumulative through the barrier) before the ticket
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last) {                                    // every store of this rank is ordered before what follows
+        if (threadIdx.x == 0) *ticket = 0;         // for the next launch (stream order)
+        if ((int)threadIdx.x < world) {
+            __threadfence_system();
+            volatile uint32_t *theirs = peers.flags[threadIdx.x];
+            theirs[rank] = epoch;                  // "rank has stored epoch" into peer threadIdx.x
         }
     }
-    __threadfence_system();                        // this thread's pushes (and its cleaning) before the ticket
-    __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!last) return;
-    // last block of this rank: every push of the rank is ordered before what follows
-    if (threadIdx.x == 0) *ticket = 0;             // for the next launch (stream order)
-    if ((int)threadIdx.x < world) {
-        __threadfence_system();
-        volatile uint32_t *theirs = peers.flags[threadIdx.x];
-        theirs[rank] = epoch;                      // "rank has pushed epoch" into peer threadIdx.x
+    if ((int)threadIdx.x < world) {                // all blocks: wait for every peer's flag in OUR flag array
         volatile uint32_t *mine = peers.flags[rank];
-        while ((int32_t)(mine[threadIdx.x] - epoch) < 0) {}   // wait for peer threadIdx.x (wrap-safe compare)
+        const long long t0 = clock64();
+        while ((int32_t)(mine[threadIdx.x] - epoch) < 0) {      // wrap-safe compare
+            if (clock64() - t0 > 4000000000LL) { *error = 1; break; }
+        }
     }
     __syncthreads();
-    __threadfence_system();
+    __threadfence_system();                        // acquire side: the flags were read before the slots are
+    if (p < P) {
+        const volatile unsigned long long *mine = peers.slots[rank];
+        unsigned long long best = ~0ull;
+#pragma unroll 1
+        for (int g = 0; g < world; g++) best = min(best, mine[(int64_t)g * max_pods + p]);
+        final_keys[p] = best;
+    }
 }
 
 }  // namespace kgpu

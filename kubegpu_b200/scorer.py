@@ -212,6 +212,10 @@ class Scorer:
         self._check(self._L.kgpu_score_batch_exchange(self._h, d_pods_addr, int(P), ctypes.byref(out), stream or None, int(batch_flags)))
         return int(out.value or 0)
 
+    def exchange_barrier(self, stream: int = 0) -> None:
+        """Device-side barrier of the ranks (the exchange kernel with no pods), enqueued on `stream`."""
+        self._check(self._L.kgpu_exchange_barrier(self._h, stream or None))
+
     @property
     def kernel_launches(self) -> int:
         return int(self._L.kgpu_kernel_launches(self._h))

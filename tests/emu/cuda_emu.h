@@ -180,6 +180,7 @@ inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 // ---- integer intrinsics ----------------------------------------------------------------------------------
+inline long long clock64() { return 0; }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __ffs(unsigned x) { return x == 0 ? 0 : __builtin_ctz(x) + 1; }
 inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }

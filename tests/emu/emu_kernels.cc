@@ -184,16 +184,16 @@ long long emu_validate_topo(const int32_t *topo, int64_t n) {
     return bad == ~0ull ? -1 : (long long)bad;
 }
 
-// The peer-exchange kernel with world = 1 (the rank pushes into its own result array and passes its own
-// barrier): exercises the push, the last-block ticket and the flag protocol, not the cross-GPU part.
-void emu_push_and_sync(unsigned long long *local, int64_t P, unsigned long long *result, uint32_t *flags,
-                       uint32_t epoch, unsigned int *ticket, unsigned long long *other, int64_t clean_len) {
+// The peer-exchange kernel with world = 1 (the rank stores into its own slot array and passes its own barrier):
+// exercises the stores, the ticket, the flag protocol and the final minimum, not the cross-GPU part.
+void emu_gather_and_min(unsigned long long *local, int64_t P, int64_t max_pods, unsigned long long *slots, uint32_t *flags,
+                        uint32_t epoch, unsigned int *ticket, unsigned long long *final_keys, int *error) {
     kgpu::PeerTable tab;
     std::memset(&tab, 0, sizeof tab);
-    tab.results[0] = result;
+    tab.slots[0] = slots;
     tab.flags[0] = flags;
-    emu::launch(dim3((unsigned)((P + 255) / 256)), dim3(256),
-                [&] { kgpu::push_and_sync(local, P, tab, 0, 1, epoch, ticket, other, clean_len); });
+    emu::launch(dim3((unsigned)std::max<int64_t>(1, (P + 255) / 256)), dim3(256),
+                [&] { kgpu::gather_and_min(local, P, max_pods, tab, 0, 1, epoch, ticket, final_keys, error); });
 }
 
 // The host-side work-list builder alone (sparse_work.h): items as int32[.][4] {tile, pod_begin, pod_end, ntiles} and

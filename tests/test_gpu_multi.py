@@ -65,8 +65,8 @@ def test_torchrun_bench_keys_equal_single_gpu(tmp_path):
 
 
 def test_torchrun_push_exchange_keys_equal_single_gpu():
-    """The peer-memory exchange (kgpu_score_batch_exchange: push with 64-bit atomic min over NVLink + flag
-    barrier, one kernel) must give the very same keys as one GPU and as the NCCL all-gather + K2 path."""
+    """The peer-memory exchange (kgpu_score_batch_exchange: stores into every rank's slots over NVLink + flag barrier +
+    local minimum, one kernel) must give the very same keys as one GPU and as the NCCL all-gather + K2 path."""
     import json
     import os
     import subprocess
@@ -86,4 +86,4 @@ def test_torchrun_push_exchange_keys_equal_single_gpu():
     two = line([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                 "--master-port", "29534", "bench.py", "--gpus", "2", "--steps", "5", "--warmup", "3", "--exchange", "push"])
     assert one["keys_sha256_12"] == one_push["keys_sha256_12"] == two["keys_sha256_12"]
-    assert "push" in two["config"]["parallelism"]
+    assert "peer-memory" in two["config"]["parallelism"]

@@ -250,34 +250,30 @@ def test_emulated_ragged_sizes(emu, oracle_b, kernel):
     assert (got == oracle_b.score_batch(topo[:5], none_free, pods[:16], W)).all()
 
 
-def test_emulated_push_and_sync_single_rank(emu):
-    """peer_exchange.cuh with world = 1: pushes land (NO_FIT is not sent), the local key array is left at NO_FIT for the
-    next step's K1, the OTHER result buffer is cleaned up to clean_len, the last block resets the ticket and publishes
-    the epoch; a second epoch into the same array keeps the minimum."""
-    emu.emu_push_and_sync.restype = None
-    P = 700
+def test_emulated_gather_and_min_single_rank(emu):
+    """peer_exchange.cuh with world = 1: the keys land in the rank's slot and come back as the final keys (NO_FIT included),
+    the local key array is left at NO_FIT for the next step's K1, the last block resets the ticket and publishes the epoch;
+    P = 0 is a pure barrier.  (One block only: the emulation runs blocks one after the other, and every block of
+    this kernel waits for the flag its rank's LAST block publishes -- on the GPU all blocks are resident.)"""
+    emu.emu_gather_and_min.restype = None
+    P, MP = 250, 1000
     rng = np.random.default_rng(3)
     local = rng.integers(1, 2**60, size=P, dtype=np.uint64)
     local[::7] = np.uint64(0xFFFFFFFFFFFFFFFF)
     sent = local.copy()
-    result = np.full(P, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)
-    other = rng.integers(1, 2**60, size=1000, dtype=np.uint64)
-    other_before = other.copy()
+    slots = rng.integers(1, 2**60, size=MP, dtype=np.uint64)           # stale content of an earlier epoch: must be overwritten
+    final = np.zeros(MP, dtype=np.uint64)
     flags = np.zeros(16, dtype=np.uint32)
     ticket = np.zeros(1, dtype=np.uint32)
+    err = np.zeros(1, dtype=np.int32)
     u64, u32 = ctypes.c_uint64, ctypes.c_uint32
-    emu.emu_push_and_sync(_p(local, u64), ctypes.c_int64(P), _p(result, u64), _p(flags, u32), 1, _p(ticket, u32),
-                          _p(other, u64), ctypes.c_int64(900))
-    assert (result == sent).all() and flags[0] == 1 and ticket[0] == 0
+    emu.emu_gather_and_min(_p(local, u64), ctypes.c_int64(P), ctypes.c_int64(MP), _p(slots, u64), _p(flags, u32), 1, _p(ticket, u32),
+                           _p(final, u64), _p(err))
+    assert (final[:P] == sent).all() and (slots[:P] == sent).all() and flags[0] == 1 and ticket[0] == 0 and err[0] == 0
     assert (local == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
-    assert (other[:900] == np.uint64(0xFFFFFFFFFFFFFFFF)).all() and (other[900:] == other_before[900:]).all()
-    lower = sent.copy()
-    lower[5:50] = np.uint64(7)
-    lower[::7] = np.uint64(0xFFFFFFFFFFFFFFFF)
-    want = np.minimum(sent, lower)
-    emu.emu_push_and_sync(_p(lower, u64), ctypes.c_int64(P), _p(result, u64), _p(flags, u32), 2, _p(ticket, u32),
-                          _p(other, u64), ctypes.c_int64(0))
-    assert (result == want).all() and flags[0] == 2 and ticket[0] == 0
+    emu.emu_gather_and_min(_p(local, u64), ctypes.c_int64(0), ctypes.c_int64(MP), _p(slots, u64), _p(flags, u32), 2, _p(ticket, u32),
+                           _p(final, u64), _p(err))
+    assert flags[0] == 2 and ticket[0] == 0 and (final[:P] == sent).all()
 
 
 # ---- node_state.cuh: device-side order, incremental record refresh, fit table, value-domain check ---------
