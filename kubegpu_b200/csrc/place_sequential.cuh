@@ -168,29 +168,22 @@ __device__ __forceinline__ unsigned long long warp_min_u64_redux(unsigned long l
 }
 
 constexpr int PLACE_POD_CHUNK = 1024;       // pod requests staged in shared memory (16 KB)
-constexpr int PLACE_NODE_CACHE = 16;        // block-wide: half tables + free mask of recent winner nodes
-constexpr int PLACE_TILE_CACHE = 8;         // per warp: node-key rows (its k) of recent winner tiles
-constexpr int PLACE_SUPER_CACHE = 4;        // per warp: tile minima (its k) of recent winner supertiles
-constexpr size_t PLACE_DYN_SUPER = 2 * (size_t)PLACE_SUPER_CAP * sizeof(unsigned long long);
-constexpr size_t PLACE_DYN_TILEC = (size_t)PLACE_WARPS * PLACE_TILE_CACHE * PLACE_TILE * sizeof(uint32_t);
-constexpr size_t PLACE_DYN_SUPERC = (size_t)PLACE_WARPS * PLACE_SUPER_CACHE * 32 * sizeof(unsigned long long);
-constexpr size_t PLACE_DYN_SMEM = PLACE_DYN_SUPER + PLACE_DYN_TILEC + PLACE_DYN_SUPERC;
+constexpr size_t PLACE_DYN_SMEM = 2 * (size_t)PLACE_SUPER_CAP * sizeof(unsigned long long);
 
-// One persistent block.  Per pod (the serial chain; v5):
+// One persistent block.  Per pod (the serial chain; v4):
 //   1. every warp finds the winner by itself: the supertile minima of (view, k) sit in shared memory (<= a few
 //      entries per lane), the minimum IS the winning (cost, node, subset); two REDUX.  No barrier: the minima are
 //      double buffered by UPDATE EPOCH (an epoch = one pod that placed something): winners are read from copy
 //      e & 1, refreshed values are written to copy (e + 1) & 1 at once and to copy e & 1 one epoch later (by the
 //      same lane, before its new writes), i.e. after the barrier that ends epoch e -- so no warp can see a
 //      refreshed minimum while another still looks for the winner.
-//   2. commit + refresh, warp per (view, k) task.  Sequential placement keeps returning to a handful of nodes (the
-//      cheapest node for each k takes pods until it is full), so what a pod needs from global memory is CACHED in
-//      shared memory: a block-wide cache of the half tables + free mask of the last 16 winner nodes, and per warp
-//      (i.e. per k) the node-key rows of the last 8 winner tiles and the tile minima of the last 4 winner
-//      supertiles.  A pod that hits all three touches no global memory on its chain (stores are write-through, fire
-//      and forget); a node-cache miss costs two extra barriers and one L2 round trip.  Re-enumeration: lane per
-//      subset from the half tables; tile minimum: one REDUX over a 32-bit composite (cost << 15 | node offset << 8
-//      | S; cost < 2^17); supertile minimum: two.
+//   2. commit + refresh, warp per (view, k) task.  Sequential placement keeps hitting the same few nodes (the
+//      cheapest node takes pods until it is full), so every warp CACHES, in registers / its shared-memory rows,
+//      what it loaded for the previous winner: the node's half tables and free mask (same node), the node keys of
+//      its tile (same tile), the tile minima of its supertile (same supertile).  A pod whose winner stays in the
+//      cached supertile touches no global memory on the chain (stores are fire and forget); otherwise all loads
+//      of the task are issued together.  Re-enumeration: lane per subset from the half tables; tile minimum: one
+//      REDUX over a 32-bit composite (cost << 15 | node offset << 8 | S; cost < 2^17); supertile minimum: two.
 //   3. ONE barrier.
 // Pod requests are staged PLACE_POD_CHUNK at a time; indices are 32-bit shifts (supertiles are 32 << j tiles).
 __global__ void __launch_bounds__(PLACE_THREADS, 1)
@@ -200,23 +193,15 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
                  unsigned long long *__restrict__ keys) {
     __shared__ int32_t sW[16];
     __shared__ int32_t sViewMin[PLACE_MAX_VIEWS];                 // static indexing of the kernel parameter only
-    __shared__ int32_t sCost[64];                                 // warp 0's scratch while it fills a node-cache entry
-    __shared__ int32_t sHalfN[PLACE_NODE_CACHE][PLACE_HALF];      // node cache: half tables (node_key_warp)
-    __shared__ int32_t sTagN[PLACE_NODE_CACHE];                   //   node index (-1 = empty)
-    __shared__ uint32_t sFmN[PLACE_NODE_CACHE];                   //   current free mask
-    __shared__ int32_t sMemN[PLACE_NODE_CACHE][8];                //   per-GPU memory (views)
-    __shared__ int32_t sRR;                                       //   next victim
+    __shared__ int32_t sCost[PLACE_WARPS][64];                    // per warp: the cached node's cost matrix
+    __shared__ int32_t sHalf[PLACE_WARPS][PLACE_HALF];            // per warp: its half tables (node_key_warp)
     __shared__ uint8_t sSub[9][72];                               // the k-subsets of 8 GPUs, increasing
     __shared__ int32_t sNsub[9];
 #ifdef __CUDACC__
-    extern __shared__ unsigned long long sDyn[];                  // DYNAMIC shared memory: super[2][CAP] | tile cache | supertile cache
-    unsigned long long (*sSuper)[PLACE_SUPER_CAP] = reinterpret_cast<unsigned long long (*)[PLACE_SUPER_CAP]>(sDyn);
-    uint32_t *sTileC = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(sDyn) + PLACE_DYN_SUPER);
-    unsigned long long *sSuperC = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(sDyn) + PLACE_DYN_SUPER + PLACE_DYN_TILEC);
+    extern __shared__ unsigned long long sSuperDyn[];             // super[copy][v][k][ST]: 2 x 36 KB of DYNAMIC shared memory
+    unsigned long long (*sSuper)[PLACE_SUPER_CAP] = reinterpret_cast<unsigned long long (*)[PLACE_SUPER_CAP]>(sSuperDyn);
 #else
     __shared__ unsigned long long sSuper[2][PLACE_SUPER_CAP];     // (CPU emulation build)
-    __shared__ uint32_t sTileC[PLACE_WARPS * PLACE_TILE_CACHE * PLACE_TILE];
-    __shared__ unsigned long long sSuperC[PLACE_WARPS * PLACE_SUPER_CACHE * 32];
 #endif
     __shared__ int32_t sPendIdx[PLACE_MAX_VIEWS * 9];             // per task: entry still to be written to the other copy
     __shared__ unsigned long long sPendVal[PLACE_MAX_VIEWS * 9];
@@ -232,9 +217,7 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
         for (int i = 0; i < 16; i++) sW[i] = W.w[i];
 #pragma unroll
         for (int i = 0; i < PLACE_MAX_VIEWS; i++) sViewMin[i] = views.min_mem[i];
-        sRR = 0;
     }
-    if (tid < PLACE_NODE_CACHE) sTagN[tid] = -1;
     if (tid < 9) {
         const int n = c_nsub[tid];
         sNsub[tid] = n;
@@ -252,12 +235,14 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
     }
     uint32_t epoch = 0;                                           // block-uniform: pods that placed something so far
     const int ntask = V * 9;
-    // per-warp caches of its FIRST task (task == warp): tags live in registers (lane e holds entry e's tag)
-    uint32_t *const myTileC = sTileC + (size_t)warp * PLACE_TILE_CACHE * PLACE_TILE;
-    unsigned long long *const mySuperC = sSuperC + (size_t)warp * PLACE_SUPER_CACHE * 32;
-    int tagT = -1, tagS = -1;                                     // lane < PLACE_TILE_CACHE / PLACE_SUPER_CACHE: that entry's tile / supertile
-    int rrT = 0, rrS = 0;                                         // warp-uniform victims
-    const bool cache_super = super_tiles == 32;
+    // what this warp has cached for its FIRST task (task == warp)
+    int c_node = -1, c_tile = -1, c_st = -1;                      // warp-uniform
+    uint32_t c_fm = 0;
+    int32_t c_mem = 0x7FFFFFFF;                                   // lanes 0..7: memory of the cached node's GPUs
+    uint32_t nbr[PLACE_TILE / 32];                                // per lane: node keys of the cached tile
+    unsigned long long tsr = ~0ull;                               // per lane: minimum of tile c_st * 32 + lane (super_tiles == 32 only)
+#pragma unroll
+    for (int j = 0; j < PLACE_TILE / 32; j++) nbr[j] = INF32;
 
     for (int64_t p0 = 0; p0 < P; p0 += PLACE_POD_CHUNK) {
         const int pn = (int)min((int64_t)PLACE_POD_CHUNK, P - p0);
@@ -283,107 +268,80 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
             if (tid == 0) keys[p0 + pi] = win;
             if (win == ~0ull || k == 0) continue;             // nothing fits / nothing to take (block-uniform)
 
-            // 2. commit and refresh
+            // 2. commit and refresh, warp by warp
             const uint32_t nid = (uint32_t)(win >> 8);
             const int node = (int)((int64_t)nid - node_id_base);
             const uint32_t S = (uint32_t)(win & 0xFFull);
             const int tile = node >> 7, st = tile >> st_shift;
             static_assert(PLACE_TILE == 128, "tile index is node >> 7");
-            // 2a. the node cache (block-wide; tags change only between the two barriers of a miss, so every warp
-            //     takes the same branch)
-            int e;
-            {
-                const int tag = lane < PLACE_NODE_CACHE ? sTagN[lane] : -2;
-                const uint32_t hit = __ballot_sync(0xFFFFFFFFu, tag == node);
-                if (hit == 0) {
-                    __syncthreads();                          // everybody has looked
-                    e = sRR;
-                    if (warp == 0) {
-                        const int32_t l0 = __ldg(topo + (int64_t)node * 64 + lane), l1 = __ldg(topo + (int64_t)node * 64 + lane + 32);
-                        const uint32_t fm_mem = (uint32_t)__ldcg(free_mask + node) & 0xFFu;    // L2: thread 0 writes masks through
-                        const int32_t mm = (gpu_mem != nullptr && lane < 8) ? __ldg(gpu_mem + (int64_t)node * 8 + lane) : 0x7FFFFFFF;
-                        sCost[lane] = sW[l0 & 15];
-                        sCost[lane + 32] = sW[l1 & 15];
-                        __syncwarp();
-                        build_half_tables(sCost, sHalfN[e], lane);
-                        if (lane < 8) sMemN[e][lane] = mm;
-                        if (lane == 0) {
-                            sTagN[e] = node;
-                            sFmN[e] = fm_mem;
-                        }
-                    }
-                    __syncthreads();                          // the entry is complete
-                    if (tid == 0) sRR = (e + 1) % PLACE_NODE_CACHE;   // read again only after this pod's final barrier
-                } else {
-                    e = __ffs(hit) - 1;
-                }
-            }
-            const uint32_t fm = sFmN[e] & ~S;                 // old & ~S whether or not thread 0 has stored the new mask yet
-            if (tid == 0) {
-                sFmN[e] = fm;
-                free_mask[node] = (int32_t)fm;
-            }
             if (warp < min(PLACE_WARPS, ntask)) {
-                const int32_t *half = sHalfN[e];
-                const int32_t my_mem = lane < 8 ? sMemN[e][lane] : 0x7FFFFFFF;
+                const int64_t vk0 = warp;                     // this warp's first (cached) task
+                const bool new_node = node != c_node, new_tile = tile != c_tile;
+                const bool cache_super = super_tiles == 32;
+                const bool new_st = !cache_super || st != c_st;
+                // every global load this pod needs from this warp, issued before anything waits
+                int32_t l0 = 0, l1 = 0;
+                uint32_t fm_mem = 0;
+                if (new_node) {
+                    l0 = __ldg(topo + (int64_t)node * 64 + lane);
+                    l1 = __ldg(topo + (int64_t)node * 64 + lane + 32);
+                    fm_mem = (uint32_t)free_mask[node] & 0xFFu;       // before or after warp 0's write-back: & ~S below either way
+                    c_mem = (gpu_mem != nullptr && lane < 8) ? __ldg(gpu_mem + (int64_t)node * 8 + lane) : 0x7FFFFFFF;
+                }
+                if (new_tile) {
+#pragma unroll
+                    for (int j = 0; j < PLACE_TILE / 32; j++) nbr[j] = nodebest[vk0 * Npad + tile * PLACE_TILE + lane + 32 * j];
+                }
+                unsigned long long sb0 = ~0ull;               // !cache_super: minimum over the supertile's OTHER tiles
+                if (cache_super) {
+                    if (new_st) {
+                        const int t = (st << 5) + lane;
+                        tsr = t < Ti ? tilebest[vk0 * T + t] : ~0ull;
+                    }
+                } else {
+                    for (int t = (st << st_shift) + lane; t < min(Ti, (st + 1) << st_shift); t += 32)
+                        if (t != tile) sb0 = min(sb0, tilebest[vk0 * T + t]);
+                }
+                int32_t *half = sHalf[warp];
+                if (new_node) {
+                    int32_t *cost = sCost[warp];
+                    cost[lane] = sW[l0 & 15];
+                    cost[lane + 32] = sW[l1 & 15];
+                    __syncwarp();
+                    build_half_tables(cost, half, lane);
+                    __syncwarp();
+                    c_fm = fm_mem;
+                    c_node = node;
+                }
+                c_tile = tile;
+                c_st = st;
+                const uint32_t fm = c_fm & ~S;
+                c_fm = fm;
+                if (warp == 0 && lane == 0) free_mask[node] = (int32_t)fm;
                 for (int task = warp; task < ntask; task += PLACE_WARPS) {
                     const int tv = task / 9, tk = task - tv * 9;
                     const int64_t vk = task;
                     const bool cached = task == warp;
-                    // node keys of the winner's tile for this task
                     uint32_t nb[PLACE_TILE / 32];
-                    int et = -1;
-                    if (cached) {
-                        const uint32_t hitT = __ballot_sync(0xFFFFFFFFu, lane < PLACE_TILE_CACHE && tagT == tile);
-                        if (hitT) {
-                            et = __ffs(hitT) - 1;
+                    unsigned long long sb = sb0;
+                    if (!cached) {                            // more tasks than warps (several views): load now
 #pragma unroll
-                            for (int j = 0; j < PLACE_TILE / 32; j++) nb[j] = myTileC[et * PLACE_TILE + lane + 32 * j];
-                        } else {
-                            et = rrT;
-                            rrT = (rrT + 1) % PLACE_TILE_CACHE;
-                            if (lane == et) tagT = tile;
-#pragma unroll
-                            for (int j = 0; j < PLACE_TILE / 32; j++) {
-                                nb[j] = __ldcg(nodebest + vk * Npad + tile * PLACE_TILE + lane + 32 * j);
-                                myTileC[et * PLACE_TILE + lane + 32 * j] = nb[j];      // every lane reads back only what it wrote
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < PLACE_TILE / 32; j++) nb[j] = __ldcg(nodebest + vk * Npad + tile * PLACE_TILE + lane + 32 * j);
-                    }
-                    // tile minima of the winner's supertile for this task
-                    unsigned long long ts = ~0ull, sb = ~0ull;
-                    int es = -1;
-                    if (cached && cache_super) {
-                        const uint32_t hitS = __ballot_sync(0xFFFFFFFFu, lane < PLACE_SUPER_CACHE && tagS == st);
-                        if (hitS) {
-                            es = __ffs(hitS) - 1;
-                            ts = mySuperC[es * 32 + lane];
-                        } else {
-                            es = rrS;
-                            rrS = (rrS + 1) % PLACE_SUPER_CACHE;
-                            if (lane == es) tagS = st;
-                            const int t = (st << 5) + lane;
-                            ts = t < Ti ? __ldcg(tilebest + vk * T + t) : ~0ull;
-                            mySuperC[es * 32 + lane] = ts;
-                        }
-                    } else {
+                        for (int j = 0; j < PLACE_TILE / 32; j++) nb[j] = nodebest[vk * Npad + tile * PLACE_TILE + lane + 32 * j];
+                        sb = ~0ull;
                         for (int t = (st << st_shift) + lane; t < min(Ti, (st + 1) << st_shift); t += 32)
-                            if (t != tile) sb = min(sb, __ldcg(tilebest + vk * T + t));
+                            if (t != tile) sb = min(sb, tilebest[vk * T + t]);
                     }
-                    const uint32_t ok = tv == 0 ? 0xFFu : (__ballot_sync(0xFFFFFFFFu, my_mem >= sViewMin[tv]) & 0xFFu);
+                    const uint32_t ok = tv == 0 ? 0xFFu : (__ballot_sync(0xFFFFFFFFu, c_mem >= sViewMin[tv]) & 0xFFu);
                     const uint32_t nk = node_key_warp(tk, half, fm & ok, lane, sSub[tk], sNsub[tk]);
                     // tile minimum: 32-bit composite cost << 15 | node offset << 8 | S (cost <= 28 * 4095 < 2^17)
                     uint32_t m = INF32;
 #pragma unroll
                     for (int j = 0; j < PLACE_TILE / 32; j++) {
                         const int off = lane + 32 * j;
-                        uint32_t key = nb[j];
+                        uint32_t key = cached ? nbr[j] : nb[j];
                         if (tile * PLACE_TILE + off == node) {
                             key = nk;
-                            if (cached) myTileC[et * PLACE_TILE + off] = nk;
+                            if (cached) nbr[j] = nk;
                         }
                         if (key != INF32) m = min(m, ((key >> 8) << 15) | ((uint32_t)off << 8) | (key & 0xFFu));
                     }
@@ -393,11 +351,8 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
                                    : (((unsigned long long)(m >> 15) << 40) |
                                       ((unsigned long long)(node_id_base + (int64_t)tile * PLACE_TILE + ((m >> 8) & 127u)) << 8) | (m & 0xFFu));
                     if (cached && cache_super) {
-                        if (lane == (tile & 31)) {
-                            ts = tb;
-                            mySuperC[es * 32 + lane] = tb;
-                        }
-                        sb = warp_min_u64_redux(ts);
+                        if (lane == (tile & 31)) tsr = tb;
+                        sb = warp_min_u64_redux(tsr);
                     } else {
                         sb = warp_min_u64_redux(min(sb, tb));
                     }
