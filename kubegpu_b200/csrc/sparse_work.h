@@ -74,7 +74,7 @@ inline void build_sparse_work(const std::vector<uint8_t> &tile_class, int64_t P,
         // measured (C2): short tail ranges help when every resident block gets several items anyway (100k nodes:
         // 0.4393 ms with 15 %, 0.4413 with 25 %, 0.4475 without), and only add fixed cost on small shards
         // (12.5k nodes: 0.0768 ms without, 0.0788 with 15 %, 0.0809 with 25 %)
-        const int64_t tail_percent = prm.tail_percent >= 0 ? prm.tail_percent : ((int64_t)tile_class.size() * 2 >= resident_blocks ? 15 : 0);
+        const int64_t tail_percent = prm.tail_percent >= 0 ? prm.tail_percent : ((int64_t)tile_class.size() * 4 >= resident_blocks ? 15 : 0);
         for (size_t t = 0; t < tile_class.size(); t++) {
             const int64_t c = kSparsePodCost[std::min<int>(tile_class[t], 8)];
             const int64_t per = std::max<int64_t>(32, (target - kSparseFixedCost) / c / 32 * 32);
