@@ -732,7 +732,7 @@ def main():
 
     # ---- the regime where HBM is the roof: millions of nodes, 1 / 32 pods (N = 1) ---------------------------
     if extras and world == 1:
-        n_big = 8_388_608
+        n_big = 10_485_760
         tb, fb, _ = synth.gen_c2(n_big, 0, seed=synth.SEED_C5)
         with Scorer((local_rank,)) as sb:
             sb.set_variant(_lib.VARIANT_SPARSE)
@@ -756,7 +756,7 @@ def main():
         del tb, fb
         line["hbm_regime"] = {"nodes": n_big, "points": pts, "peak_gbs": peak, "peak_source": peak_src, "upload_ms": up_big,
                               "bytes_per_node_streamed": RECORD_BYTES,
-                              "note": "1.0 GB of node records (> 126 MB L2), L2 flushed before every launch: every record comes from DRAM once; "
+                              "note": "1.26 GB of node records (> 126 MB L2), L2 flushed before every launch: every record comes from DRAM once; "
                                       "dram_gbs_min = 120 B x nodes / time is a lower bound of the DRAM rate (ncu: profiles/r02_k1s_stream_*). "
                                       "The algorithmic figure counts 260 B per pair, i.e. the uncompacted matrix."}
 

@@ -79,6 +79,7 @@ struct kgpu_shard {
     int4 *d_work = nullptr;
     int64_t work_cap = 0, work_P = -1;
     uint32_t *d_nodebest = nullptr;          // [views][9][Npad]  K3 tables
+    int32_t *d_half = nullptr;               // [Npad][96]  K3: half tables of every node (place_half_tables)
     unsigned long long *d_tilebest = nullptr;   // [views][9][T]
     int64_t place_cap = 0;
     int64_t pcap = 0;
@@ -500,6 +501,7 @@ void free_shard(kgpu_shard &s) {
     if (s.d_bestk) cudaFree(s.d_bestk);
     if (s.d_nodebest) cudaFree(s.d_nodebest);
     if (s.d_tilebest) cudaFree(s.d_tilebest);
+    if (s.d_half) cudaFree(s.d_half);
     if (s.d_work) cudaFree(s.d_work);
     if (s.ev0) cudaEventDestroy(s.ev0);
     if (s.ev1) cudaEventDestroy(s.ev1);
@@ -898,6 +900,9 @@ int kgpu_place_batch_ex(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out
             if (s.d_tilebest) cudaFree(s.d_tilebest);
             s.d_nodebest = nullptr; s.d_tilebest = nullptr; s.place_cap = 0;
             KGPU_CUDA(h, cudaMalloc(&s.d_nodebest, (size_t)Npad * views.n * 9 * 4));
+            if (s.d_half) cudaFree(s.d_half);
+            s.d_half = nullptr;
+            KGPU_CUDA(h, cudaMalloc(&s.d_half, (size_t)Npad * kgpu::PLACE_HALF * 4));
             KGPU_CUDA(h, cudaMalloc(&s.d_tilebest, (size_t)T * views.n * 9 * 8));
             s.place_cap = Npad * views.n;
         }
@@ -907,12 +912,15 @@ int kgpu_place_batch_ex(kgpu_t *h, const int32_t *pods, int64_t P, uint64_t *out
         kgpu::place_init<<<dim3((unsigned)T, (unsigned)views.n), kgpu::PLACE_TILE, 0, s.stream>>>(
             reinterpret_cast<const int4 *>(s.d_topo), d_free, s.d_mem, s.n, Npad, s.node_id_base, W, PC, views, s.d_nodebest,
             s.d_tilebest, T);
+        kgpu::place_half_tables<<<(unsigned)std::min<int64_t>((s.n + 3) / 4, (int64_t)s.sm_count * 16), 128, 0, s.stream>>>(
+            s.d_topo, s.n, W, s.d_half);
+        h->launches++;
         static const cudaError_t place_attr = cudaFuncSetAttribute(kgpu::place_sequential, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                                    (int)kgpu::PLACE_DYN_SMEM);
         KGPU_CUDA(h, place_attr);
         kgpu::place_sequential<<<1, kgpu::PLACE_THREADS, kgpu::PLACE_DYN_SMEM, s.stream>>>(s.d_topo, d_free, s.d_mem, s.n, Npad, s.node_id_base,
                                                                         reinterpret_cast<const int4 *>(s.d_pods), P, W, views,
-                                                                        s.d_nodebest, s.d_tilebest, T, s.d_keys);
+                                                                        s.d_nodebest, s.d_tilebest, T, s.d_half, s.d_keys);
         h->launches += 2;
         if (!dry) {
             s.order_dirty = true;        // the free masks have changed on the device: re-sort + recompact lazily

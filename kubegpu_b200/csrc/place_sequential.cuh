@@ -139,6 +139,36 @@ __device__ __forceinline__ void build_half_tables(const int32_t *sCost, int32_t 
     }
 }
 
+// The half tables of EVERY node, once per batch (they depend on topology and weights only): half_all[node][96].
+// place_sequential then fetches a winner's tables with three coalesced loads instead of rebuilding them on its
+// per-pod chain.  Warp per node.
+__global__ void __launch_bounds__(128)
+place_half_tables(const int32_t *__restrict__ topo, int64_t N, Weights W, int32_t *__restrict__ half_all) {
+    __shared__ int32_t sW[16];
+    __shared__ int32_t sCost[4][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) sW[i] = W.w[i];
+    }
+    __syncthreads();
+    for (int64_t node = (int64_t)blockIdx.x * 4 + warp; node < N; node += (int64_t)gridDim.x * 4) {
+        __syncwarp();
+        sCost[warp][lane] = sW[__ldg(topo + node * 64 + lane) & 15];
+        sCost[warp][lane + 32] = sW[__ldg(topo + node * 64 + lane + 32) & 15];
+        __syncwarp();
+        build_half_tables(sCost[warp], half_all + node * PLACE_HALF, lane);
+    }
+}
+
+__device__ __forceinline__ void prefetch_l1(const void *p) {
+#ifdef __CUDACC__
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // (cost<<8 | S) of one node for k GPUs, computed by a whole warp: lane per candidate subset.
 // `subsets` = the k-subsets of 8 in increasing order in SHARED memory (the constant-memory table indexed by lane would
 // serialise: one address per cycle).
@@ -190,11 +220,9 @@ __global__ void __launch_bounds__(PLACE_THREADS, 1)
 place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_mask, const int32_t *__restrict__ gpu_mem,
                  int64_t N, int64_t Npad, int64_t node_id_base, const int4 *__restrict__ pods4, int64_t P, Weights W,
                  PlaceViews views, uint32_t *__restrict__ nodebest, unsigned long long *__restrict__ tilebest, int64_t T,
-                 unsigned long long *__restrict__ keys) {
-    __shared__ int32_t sW[16];
+                 const int32_t *__restrict__ half_all /*[N][96], place_half_tables*/, unsigned long long *__restrict__ keys) {
     __shared__ int32_t sViewMin[PLACE_MAX_VIEWS];                 // static indexing of the kernel parameter only
-    __shared__ int32_t sCost[PLACE_WARPS][64];                    // per warp: the cached node's cost matrix
-    __shared__ int32_t sHalf[PLACE_WARPS][PLACE_HALF];            // per warp: its half tables (node_key_warp)
+    __shared__ int32_t sHalf[PLACE_WARPS][PLACE_HALF];            // per warp: the cached node's half tables (node_key_warp)
     __shared__ uint8_t sSub[9][72];                               // the k-subsets of 8 GPUs, increasing
     __shared__ int32_t sNsub[9];
 #ifdef __CUDACC__
@@ -212,9 +240,8 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
     const int st_shift = 31 - __clz(super_tiles);
     const int ST = (int)((T + super_tiles - 1) >> st_shift);
     const int Ti = (int)T;
+    (void)W;
     if (tid == 0) {
-#pragma unroll
-        for (int i = 0; i < 16; i++) sW[i] = W.w[i];
 #pragma unroll
         for (int i = 0; i < PLACE_MAX_VIEWS; i++) sViewMin[i] = views.min_mem[i];
     }
@@ -280,11 +307,13 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
                 const bool cache_super = super_tiles == 32;
                 const bool new_st = !cache_super || st != c_st;
                 // every global load this pod needs from this warp, issued before anything waits
-                int32_t l0 = 0, l1 = 0;
+                int32_t h0 = 0, h1 = 0, h2 = 0;
                 uint32_t fm_mem = 0;
-                if (new_node) {
-                    l0 = __ldg(topo + (int64_t)node * 64 + lane);
-                    l1 = __ldg(topo + (int64_t)node * 64 + lane + 32);
+                if (new_node) {                               // the winner's half tables: three coalesced loads (L1 if prefetched)
+                    const int32_t *src = half_all + (int64_t)node * PLACE_HALF;
+                    h0 = __ldg(src + lane);
+                    h1 = __ldg(src + lane + 32);
+                    h2 = __ldg(src + lane + 64);
                     fm_mem = (uint32_t)free_mask[node] & 0xFFu;       // before or after warp 0's write-back: & ~S below either way
                     c_mem = (gpu_mem != nullptr && lane < 8) ? __ldg(gpu_mem + (int64_t)node * 8 + lane) : 0x7FFFFFFF;
                 }
@@ -304,11 +333,10 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
                 }
                 int32_t *half = sHalf[warp];
                 if (new_node) {
-                    int32_t *cost = sCost[warp];
-                    cost[lane] = sW[l0 & 15];
-                    cost[lane + 32] = sW[l1 & 15];
                     __syncwarp();
-                    build_half_tables(cost, half, lane);
+                    half[lane] = h0;
+                    half[lane + 32] = h1;
+                    half[lane + 64] = h2;
                     __syncwarp();
                     c_fm = fm_mem;
                     c_node = node;
@@ -366,6 +394,28 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
                         sSuper[(epoch + 1) & 1][vk * ST + st] = sb;
                         sPendIdx[task] = (int)(vk * ST + st);
                         sPendVal[task] = sb;
+                    }
+                    if (cached) {
+                        // The next winner for THIS warp's (view, k), unless another pod changes that first: the minimum of
+                        // the row this warp has just brought up to date (copy (epoch + 1) & 1 is written by this warp
+                        // only).  Every second pod opens a node nobody has touched yet (a node holds at most 8 GPUs'
+                        // worth of pods), so its half tables and mask are brought into this SM's L1 now, off the chain.
+                        __syncwarp();
+                        const unsigned long long *row = sSuper[(epoch + 1) & 1] + vk * ST;
+                        unsigned long long cb = ~0ull;
+                        for (int s2 = lane; s2 < ST; s2 += 32) cb = min(cb, row[s2]);
+                        cb = warp_min_u64_redux(cb);
+                        if (cb != ~0ull) {
+                            const int64_t cand = (int64_t)((cb >> 8) & 0xFFFFFFFFull) - node_id_base;
+                            if (cand != c_node) {
+                                if (lane < 3) prefetch_l1(half_all + cand * PLACE_HALF + 32 * lane);
+                                if (lane == 3) prefetch_l1(free_mask + cand);
+                                if (lane == 4) prefetch_l1(nodebest + vk * Npad + (cand & ~(int64_t)127) + 0);
+                                if (lane == 5) prefetch_l1(nodebest + vk * Npad + (cand & ~(int64_t)127) + 32);
+                                if (lane == 6) prefetch_l1(nodebest + vk * Npad + (cand & ~(int64_t)127) + 64);
+                                if (lane == 7) prefetch_l1(nodebest + vk * Npad + (cand & ~(int64_t)127) + 96);
+                            }
+                        }
                     }
                 }
             }

@@ -345,11 +345,14 @@ int emu_place_batch(const int32_t *topo, int32_t *free_mask, const int32_t *gpu_
     const kgpu::Weights Ws = weights_of(W);
     emu::launch(dim3((unsigned)T, (unsigned)views.n), dim3(kgpu::PLACE_TILE),
                 [&] { kgpu::place_init(topo4, free_mask, mem, n, Npad, node_id_base, Ws, kPC, views, nodebest, tilebest, T); });
+    int32_t *half_all = aligned_array<int32_t>((size_t)Npad * kgpu::PLACE_HALF);
+    emu::launch(dim3((unsigned)std::min<int64_t>((n + 3) / 4, 8)), dim3(128),
+                [&] { kgpu::place_half_tables(reinterpret_cast<const int32_t *>(topo4), n, Ws, half_all); });
     emu::launch(dim3(1), dim3(kgpu::PLACE_THREADS), [&] {
         kgpu::place_sequential(reinterpret_cast<const int32_t *>(topo4), free_mask, mem, n, Npad, node_id_base, pods4, P, Ws, views,
-                               nodebest, tilebest, T, keys);
+                               nodebest, tilebest, T, half_all, keys);
     });
-    free(topo4); free(pods4); free(mem); free(nodebest); free(tilebest);
+    free(topo4); free(pods4); free(mem); free(nodebest); free(tilebest); free(half_all);
     return 0;
 }
 
