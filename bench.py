@@ -336,7 +336,7 @@ def main():
     h_pods = torch.from_numpy(pods).pin_memory()
     h_keys = torch.empty(N_PODS, dtype=torch.int64).pin_memory()
 
-    # ---- exchange: peer-memory push (one kernel: 64-bit atomic min into every rank's result array over NVLink
+    # ---- exchange: peer-memory exchange (one kernel: stores into every rank's slot array over NVLink
     # + flag barrier) when every rank can map every peer; else NCCL all-gather + K2 -------------------------
     exchange = args.exchange
     if exchange == "auto":
