@@ -18,6 +18,10 @@
  *          -> TranslatePodGPUResources                gpuschedulerplugin/gpu.go:94-127
  *          -> findBestTreeInCache + assignGPUs        gpuschedulerplugin/gpu.go:232-271
  *          batched over every (pod, node) pair instead of one cgo call per pair
+ *   kgpu_fit_lookup / kgpu_build_fit_table / kgpu_score_pairs
+ *       <- the same PodFitsDevice, called once per (node, pod) by the core: served from a host-side (node, k) table
+ *   kgpu_set_free_mask[s] / kgpu_place_batch[_ex] / kgpu_get_free_masks
+ *       <- TakePodResources / ReturnPodResources       gpuschedulerplugin/gpu_scheduler.go:57-63 (no-ops there)
  *   kgpu_reduce_shards_device
  *       <- (no reference counterpart; the reference is single-process) the final
  *          per-pod pick over the all-gathered shard results, SURVEY.md 8(e)
