@@ -395,7 +395,10 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
                         sPendIdx[task] = (int)(vk * ST + st);
                         sPendVal[task] = sb;
                     }
-                    if (cached) {
+#ifndef KGPU_PLACE_PREFETCH
+#define KGPU_PLACE_PREFETCH 0      // 0: off (default), 1: half tables + mask, 2: + the node-key row of the candidate's tile.  Measured on one box (C2): v4 12.37 ms, precomputed half tables 11.42, + prefetch 1: 13.19, 2: 13.95 -- the candidate search and the prefetch instructions cost more than the L1 hits save
+#endif
+                    if (cached && KGPU_PLACE_PREFETCH) {
                         // The next winner for THIS warp's (view, k), unless another pod changes that first: the minimum of
                         // the row this warp has just brought up to date (copy (epoch + 1) & 1 is written by this warp
                         // only).  Every second pod opens a node nobody has touched yet (a node holds at most 8 GPUs'
@@ -408,12 +411,9 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
                         if (cb != ~0ull) {
                             const int64_t cand = (int64_t)((cb >> 8) & 0xFFFFFFFFull) - node_id_base;
                             if (cand != c_node) {
-                                if (lane < 3) prefetch_l1(half_all + cand * PLACE_HALF + 32 * lane);
-                                if (lane == 3) prefetch_l1(free_mask + cand);
-                                if (lane == 4) prefetch_l1(nodebest + vk * Npad + (cand & ~(int64_t)127) + 0);
-                                if (lane == 5) prefetch_l1(nodebest + vk * Npad + (cand & ~(int64_t)127) + 32);
-                                if (lane == 6) prefetch_l1(nodebest + vk * Npad + (cand & ~(int64_t)127) + 64);
-                                if (lane == 7) prefetch_l1(nodebest + vk * Npad + (cand & ~(int64_t)127) + 96);
+                                if (lane < 4) prefetch_l1(lane < 3 ? (const void *)(half_all + cand * PLACE_HALF + 32 * lane) : (const void *)(free_mask + cand));
+                                if (KGPU_PLACE_PREFETCH >= 2 && lane >= 4 && lane < 8)
+                                    prefetch_l1(nodebest + vk * Npad + (cand & ~(int64_t)127) + 32 * (lane - 4));
                             }
                         }
                     }

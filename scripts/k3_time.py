@@ -3,8 +3,10 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from kubegpu_b200 import synth
+from kubegpu_b200 import _lib, synth
 from kubegpu_b200.scorer import Scorer
+if len(sys.argv) > 1:
+    _lib.LIB_PATH = os.path.abspath(sys.argv[1])        # time this build instead (A/B on one box)
 from oracle import oracle_b
 topo, free, pods = synth.gen_c2()
 want, wf = oracle_b.place_batch(topo, free, pods)
