@@ -56,6 +56,7 @@ struct kgpu_shard {
     int64_t ord_nb_cap = 0;
     unsigned long long *d_bad = nullptr;   // validate_topo_dev: first out-of-domain element
     int32_t *d_upd = nullptr;        // state-change scratch: [cap] node indices | [cap] masks
+    uint32_t *d_fit_patch = nullptr; // [9][cap] fit-table rows of the nodes a state change touched
     int64_t upd_cap = 0;
     uint32_t *d_fit = nullptr;       // (node, k) fit table on the device [9][n] and, patches, [9][upd]
     uint32_t *h_fit = nullptr;       // pinned host copy [9][n]: kgpu_fit_lookup / kgpu_score_pairs read it
@@ -166,11 +167,16 @@ int ensure_pod_capacity(kgpu_ctx *h, kgpu_shard &s, int64_t P) {
     return KGPU_OK;
 }
 
+// Classes of the K1s order are padded to whole warps (32).  Padding them to whole tiles (KGPU_ORDER_PAD=128: no block ever
+// mixes classes) was measured on C2 shards of 12.5k .. 100k nodes and bought nothing (0.0778 vs 0.0758 ms at 12.5k, equal
+// above), so the smaller order stays.
+const int kOrderPad = [] { const char *e = getenv("KGPU_ORDER_PAD"); const int v = e ? atoi(e) : 0; return v == 128 ? (int)kgpu::SP_THREADS : 32; }();
+
 // (Re)build the K1s order of shard s on the device: stable counting sort of the node indices by free-GPU
 // count (node_state.cuh).  One 80-byte read-back tells the host the class sizes (grid size, work list).
 int build_order(kgpu_ctx *h, kgpu_shard &s) {
     KGPU_CUDA(h, cudaSetDevice(s.dev));
-    const int64_t need_slots = s.n + 9 * 32 + kgpu::SP_THREADS;
+    const int64_t need_slots = s.n + 10 * kgpu::SP_THREADS;
     if (need_slots > s.slot_cap) {
         if (s.d_order) cudaFree(s.d_order);
         if (s.d_rec) cudaFree(s.d_rec);
@@ -195,7 +201,7 @@ int build_order(kgpu_ctx *h, kgpu_shard &s) {
     if (s.n > 0) {
         KGPU_CUDA(h, cudaMemsetAsync(s.d_order, 0xFF, (size_t)s.slot_cap * 4, s.stream));
         kgpu::order_count<<<nb, kgpu::ORD_BLOCK, 0, s.stream>>>(s.d_free, s.n, s.d_ord_cnt, nb);
-        kgpu::order_scan<<<1, kgpu::ORD_BLOCK, 0, s.stream>>>(s.d_ord_cnt, nb, s.d_ord_off, s.d_ord_meta, kgpu::SP_THREADS);
+        kgpu::order_scan<<<1, kgpu::ORD_BLOCK, 0, s.stream>>>(s.d_ord_cnt, nb, s.d_ord_off, s.d_ord_meta, kgpu::SP_THREADS, kOrderPad);
         kgpu::order_scatter<<<nb, kgpu::ORD_BLOCK, 0, s.stream>>>(s.d_free, s.n, s.d_ord_off, nb, s.d_order, s.d_slot_of);
         h->launches += 3;
         KGPU_CUDA(h, cudaGetLastError());
@@ -212,7 +218,7 @@ int build_order(kgpu_ctx *h, kgpu_shard &s) {
         if (cnt > 0)
             for (int64_t t = start / kgpu::SP_THREADS; t <= (start + cnt - 1) / kgpu::SP_THREADS; t++)
                 s.tile_class[(size_t)t] = std::max<uint8_t>(s.tile_class[(size_t)t], (uint8_t)c);
-        start += (cnt + 31) / 32 * 32;
+        start += (cnt + kOrderPad - 1) / kOrderPad * kOrderPad;
     }
     s.work_P = -1;
     s.order_dirty = false;
@@ -251,9 +257,11 @@ int ensure_node_cache(kgpu_ctx *h, kgpu_shard &s) {
 int ensure_upd_capacity(kgpu_ctx *h, kgpu_shard &s, int64_t m) {
     if (m <= s.upd_cap) return KGPU_OK;
     if (s.d_upd) cudaFree(s.d_upd);
-    s.d_upd = nullptr; s.upd_cap = 0;
+    if (s.d_fit_patch) cudaFree(s.d_fit_patch);
+    s.d_upd = nullptr; s.d_fit_patch = nullptr; s.upd_cap = 0;
     const int64_t cap = std::max<int64_t>(256, m + m / 2);
     KGPU_CUDA(h, cudaMalloc(&s.d_upd, (size_t)cap * 8));
+    KGPU_CUDA(h, cudaMalloc(&s.d_fit_patch, (size_t)cap * 36));
     s.upd_cap = cap;
     return KGPU_OK;
 }
@@ -308,14 +316,12 @@ int apply_node_updates(kgpu_ctx *h, kgpu_shard &s, const int32_t *idx, const int
     }
     KGPU_CUDA(h, cudaGetLastError());
     if (s.fit_valid) {
-        // rows of the changed nodes: fit_nodes over the list into d_fit's spare rows?  No: a private patch buffer
-        uint32_t *d_patch = nullptr;
-        KGPU_CUDA(h, cudaMallocAsync(&d_patch, (size_t)m * 36, s.stream));
-        kgpu::fit_nodes<<<(unsigned)((m + 127) / 128), 128, 0, s.stream>>>(topo4, s.d_free, s.d_upd, m, W, PC, d_patch);
+        // rows of the changed nodes -> the persistent patch buffer (grown with the index scratch) -> the host table
+        kgpu::fit_nodes<<<(unsigned)((m + 127) / 128), 128, 0, s.stream>>>(topo4, s.d_free, s.d_upd, m, W, PC, s.d_fit_patch);
         h->launches++;
+        KGPU_CUDA(h, cudaGetLastError());
         std::vector<uint32_t> rows((size_t)m * 9);
-        KGPU_CUDA(h, cudaMemcpyAsync(rows.data(), d_patch, (size_t)m * 36, cudaMemcpyDeviceToHost, s.stream));
-        KGPU_CUDA(h, cudaFreeAsync(d_patch, s.stream));
+        KGPU_CUDA(h, cudaMemcpyAsync(rows.data(), s.d_fit_patch, (size_t)m * 36, cudaMemcpyDeviceToHost, s.stream));
         KGPU_CUDA(h, cudaStreamSynchronize(s.stream));
         for (int k = 0; k < 9; k++)
             for (int64_t i = 0; i < m; i++) s.h_fit[(int64_t)k * s.n + idx[i]] = rows[(size_t)((int64_t)k * m + i)];
@@ -490,6 +496,7 @@ void free_shard(kgpu_shard &s) {
     if (s.d_ord_meta) cudaFree(s.d_ord_meta);
     if (s.d_bad) cudaFree(s.d_bad);
     if (s.d_upd) cudaFree(s.d_upd);
+    if (s.d_fit_patch) cudaFree(s.d_fit_patch);
     if (s.d_fit) cudaFree(s.d_fit);
     if (s.h_fit) cudaFreeHost(s.h_fit);
     if (s.d_free_scratch) cudaFree(s.d_free_scratch);

@@ -6,7 +6,7 @@
 //   validate_topo_dev   every topo value in 0..15?  first offending element through an atomic min
 //   order_count / order_scan / order_scatter
 //                       the K1s order = stable counting sort of the node indices by popcount(free_mask),
-//                       classes 8 .. 0, every class padded to whole warps with -1, the total to whole tiles.
+//                       classes 8 .. 0, every class padded to whole warps with -1 (`pad`), the total to whole tiles.
 //                       Stable = increasing node index inside a class, which the in-warp tie-break of K1s
 //                       relies on (score_pairs_sparse.cuh).
 //   fit_nodes           (cost<<8 | S) of every listed node for k = 0..8 -> fit[k][i]   (AddNode / Take / Return
@@ -52,7 +52,8 @@ order_count(const int32_t *__restrict__ free_mask, int64_t N, int32_t *__restric
 
 // pass 2 (one block): off[c * nb + b] = first slot of block b's class-c nodes; meta = class counts, n_slots
 __global__ void __launch_bounds__(ORD_BLOCK)
-order_scan(const int32_t *__restrict__ cnt, int nb, int32_t *__restrict__ off, long long *__restrict__ meta, int tile) {
+order_scan(const int32_t *__restrict__ cnt, int nb, int32_t *__restrict__ off, long long *__restrict__ meta, int tile,
+           int pad /*every class is padded to a multiple of this many slots: 32 (warps) or `tile` (class-pure tiles)*/) {
     __shared__ int32_t sWarp[32];
     __shared__ int32_t sTotal;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -87,7 +88,7 @@ order_scan(const int32_t *__restrict__ cnt, int nb, int32_t *__restrict__ off, l
             __syncthreads();
         }
         if (tid == 0) meta[c] = carry;
-        running += (carry + 31) / 32 * 32;
+        running += (carry + pad - 1) / pad * pad;
     }
     if (tid == 0) meta[9] = ((long long)running + tile - 1) / tile * tile;
 }

@@ -54,13 +54,13 @@ struct EmuCache {
 
 void emu_build_order(const int32_t *free_mask, int64_t n, EmuCache &c) {
     const int nb = (int)((n + kgpu::ORD_BLOCK - 1) / kgpu::ORD_BLOCK);
-    const int64_t cap = (n + 9 * 32 + 2 * kgpu::SP_THREADS) / kgpu::SP_THREADS * kgpu::SP_THREADS;
+    const int64_t cap = (n + 11 * kgpu::SP_THREADS) / kgpu::SP_THREADS * kgpu::SP_THREADS;
     c.order.assign((size_t)cap, -1);
     c.slot_of.assign((size_t)std::max<int64_t>(1, n), -1);
     std::vector<int32_t> cnt((size_t)nb * 9), off((size_t)nb * 9);
     long long meta[kgpu::ORD_META] = {0};
     emu::launch(dim3((unsigned)nb), dim3(kgpu::ORD_BLOCK), [&] { kgpu::order_count(free_mask, n, cnt.data(), nb); });
-    emu::launch(dim3(1), dim3(kgpu::ORD_BLOCK), [&] { kgpu::order_scan(cnt.data(), nb, off.data(), meta, kgpu::SP_THREADS); });
+    emu::launch(dim3(1), dim3(kgpu::ORD_BLOCK), [&] { kgpu::order_scan(cnt.data(), nb, off.data(), meta, kgpu::SP_THREADS, 32); });
     emu::launch(dim3((unsigned)nb), dim3(kgpu::ORD_BLOCK),
                 [&] { kgpu::order_scatter(free_mask, n, off.data(), nb, c.order.data(), c.slot_of.data()); });
     for (int k = 0; k < 9; k++) c.class_count[k] = meta[k];

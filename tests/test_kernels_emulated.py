@@ -296,7 +296,7 @@ def test_emulated_device_order_is_the_stable_class_sort(emu, n):
     if n == 1000:
         free[:] = 0xFF                                  # one class only
     want = _host_order(free)
-    cap = (n + 9 * 32 + 256) // 128 * 128
+    cap = (n + 11 * 128) // 128 * 128
     order = np.empty(cap, dtype=np.int32)
     slot_of = np.empty(n, dtype=np.int32)
     cc = np.zeros(9, dtype=np.int64)
