@@ -683,6 +683,7 @@ def main():
                         s5.reduce_shards_device(dg.data_ptr(), world, N_PODS, df.data_ptr(), stream.cuda_stream)
                 for _ in range(3):
                     fn()
+                barrier()                              # ranks enter the timed steps together (their device-side rendezvous waits on the GPU)
                 reps = 5 if n_total <= 100_000 else 3
                 ms = timed(fn, reps) / reps
                 if rank == 0:
@@ -715,6 +716,7 @@ def main():
                     dist.all_gather_into_tensor(dg.view(-1), dl)
                     s3.reduce_shards_device(dg.data_ptr(), world, P3, df.data_ptr(), stream.cuda_stream)
             fn3()
+            barrier()
             ms3 = timed(fn3, 2) / 2
             k3 = df.cpu().numpy().view(np.uint64)
         if rank == 0:

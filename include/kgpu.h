@@ -203,7 +203,7 @@ int kgpu_reduce_shards_device(kgpu_t *h, const uint64_t *d_gathered, int G, int6
  *       other ranks at a flag barrier in peer memory and takes the per-pod minimum over the G slots.  *d_final (device
  *       memory owned by the handle, valid until the next-but-one call) then holds the global keys on every rank.
  *   kgpu_exchange_barrier(h, stream)                       the same kernel with P = 0: a device-side barrier of the ranks
- * All ranks must make the same sequence of exchange calls.  A rank that waits more than ~2 s for its peers raises an
+ * All ranks must make the same sequence of exchange calls.  A rank that waits more than ~10 s for its peers raises an
  * error (reported as KGPU_ERR_COMM by a later call) instead of hanging the GPU.  Single-device handles only. */
 #define KGPU_IPC_HANDLE_BYTES 64
 int kgpu_exchange_init(kgpu_t *h, int world, int rank, int64_t max_pods, unsigned char *out_handle);

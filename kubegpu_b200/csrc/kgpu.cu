@@ -1128,7 +1128,7 @@ int exchange_step(kgpu_ctx *h, const int32_t *d_pods, int64_t P, const uint64_t 
         int err = 0;
         KGPU_CUDA(h, cudaMemcpyAsync(&err, d_err, sizeof err, cudaMemcpyDeviceToHost, st));
         KGPU_CUDA(h, cudaStreamSynchronize(st));
-        if (err) return fail(h, KGPU_ERR_COMM, "key exchange: a rank waited more than ~2 s for its peers (ranks out of step or a peer died)");
+        if (err) return fail(h, KGPU_ERR_COMM, "key exchange: a rank waited more than ~10 s for its peers (ranks out of step or a peer died)");
     }
     const uint32_t epoch = ++h->xch.epoch;
     const int buf = (int)(epoch & 1u);

@@ -4,14 +4,18 @@
 // `if (S & ~free) continue`).  K1 (score_pairs.cuh) enumerates all C(8,k) subsets for every pair
 // because the 32 lanes of a warp (32 nodes) run in lockstep whatever their free masks are.  K1s
 // removes that waste without leaving the lane-per-node mapping:
-//   * the host keeps an ORDER of the nodes grouped by f = popcount(free_mask) (kgpu_upload_nodes:
-//     each class in increasing node id, padded to whole warps), so all lanes of a warp have the
-//     same f;
-//   * every lane permutes its node's GPUs so that the free ones sit at positions 0..f-1 (increasing
-//     GPU index, so subset order is preserved) and gathers its 28 pair costs in that order;
-//   * F = max f over the warp (REDUX.MAX on the CURRENT masks, so a stale order only costs speed,
+//   * the handle keeps an ORDER of the nodes grouped by f = popcount(free_mask) (a stable counting sort
+//     on the device, node_state.cuh: each class in increasing node id, padded to whole warps), so
+//     all lanes of a warp have the same f;
+//   * compact_nodes (below) permutes every node's GPUs so that the free ones sit at positions 0..f-1
+//     (increasing GPU index, so subset order is preserved) and stores its 28 pair costs in that order
+//     as a RECORD in slot order, tile-transposed: a block stages its 128 slots with seven fully
+//     coalesced 16-byte loads (120 B per node streamed: what bounds the kernel when pods are few);
+//   * F = max f over the warp (REDUX.MAX on the CURRENT records, so a stale order only costs speed,
 //     never correctness) selects generated code that enumerates the C(F,k) subsets of positions
-//     0..F-1 only (subset_dp_sparse_gen.cuh); F < k: the warp has nothing to do for those pods.
+//     0..F-1 only (subset_dp_sparse_gen.cuh); F < k: the warp has nothing to do for those pods;
+//   * the (tile, pod) plane is cut into work items of about equal work (sparse_work.h); with few pods
+//     an item is a run of tiles and the STREAM instantiation prefetches the next tile's record.
 // Per pair the enumeration is still done in full for the candidate subsets, with the same
 // per-pod multiplier device as K1 (see score_pairs.cuh); results are bit-identical.
 #pragma once
