@@ -407,6 +407,7 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
             // equal pod ranges leave a 13 % tail); KGPU_SP_WORKLIST=0 forces the plain grid.
             static const int worklist_mode = [] { const char *e = getenv("KGPU_SP_WORKLIST"); return e ? atoi(e) : -1; }();
             const bool use_work = worklist_mode != 0;
+            static const int tma_mode = [] { const char *e = getenv("KGPU_SP_TMA"); return e ? atoi(e) : 1; }();
             const int4 *d_work = nullptr;
             if (use_work) {
                 if (s.work_P != P) {
@@ -419,7 +420,9 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
                     if (env_tail >= 0) prm.tail_percent = env_tail;
                     if (env_waves > 0) prm.waves = env_waves;
                     if (env_floor > 0) prm.floor = env_floor;
-                    const int64_t res_list = P <= kgpu::kSparseChunk ? (int64_t)s.sm_count * KGPU_SP_STREAM_MINBLOCKS : resident;
+                    const int64_t res_list = (tma_mode != 0 && P <= kgpu::SP_TMA_PODS) ? (int64_t)s.sm_count * KGPU_SP_TMA_MINBLOCKS
+                                             : P <= kgpu::kSparseChunk               ? (int64_t)s.sm_count * KGPU_SP_STREAM_MINBLOCKS
+                                                                                     : resident;
                     kgpu::build_sparse_work(s.tile_class, P, res_list, s.h_work, prm);
                     if ((int64_t)s.h_work.size() > s.work_cap) {
                         if (s.d_work) cudaFree(s.d_work);
@@ -439,12 +442,18 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
 #define KGPU_LAUNCH_SPARSE(MEMF, BK, ST)                                                                      \
     kgpu::score_pairs_sparse<true, MEMF, BK, ST><<<grid, kgpu::SP_THREADS, 0, st>>>(                          \
         s.d_rec, s.d_meta, s.d_mem, s.d_order, s.d_flag, s.node_id_base, pods4, P, (int)per, d_work, PC, d_keys)
-            // few pods (the batch is one chunk): the work list holds runs of tiles -> the STREAM instantiation
-            // (next tile's record prefetched into registers while the current one is scored)
+#define KGPU_LAUNCH_SPARSE_TMA(BK)                                                                            \
+    kgpu::score_pairs_sparse<true, false, BK, true, true><<<grid, kgpu::SP_THREADS, kgpu::SP_TMA_DYN_SMEM, st>>>( \
+        s.d_rec, s.d_meta, s.d_mem, s.d_order, s.d_flag, s.node_id_base, pods4, P, (int)per, d_work, PC, d_keys)
+            // few pods (the batch is one chunk): the work list holds runs of tiles -> the STREAM instantiation (next
+            // tile's record prefetched into registers while the current one is scored); at most 64 pods: the TMA one
+            // (tiles staged by cp.async.bulk into a shared-memory ring, KGPU_SP_TMA=0 turns it off)
             const bool stream_build = use_work && P <= kgpu::kSparseChunk;
+            const bool tma_build = stream_build && tma_mode != 0 && P <= kgpu::SP_TMA_PODS;
             if (sparse_main) {
-                if (stream_build) { if (byte_keys) KGPU_LAUNCH_SPARSE(false, true, true); else KGPU_LAUNCH_SPARSE(false, false, true); }
-                else              { if (byte_keys) KGPU_LAUNCH_SPARSE(false, true, false); else KGPU_LAUNCH_SPARSE(false, false, false); }
+                if (tma_build)         { if (byte_keys) KGPU_LAUNCH_SPARSE_TMA(true); else KGPU_LAUNCH_SPARSE_TMA(false); }
+                else if (stream_build) { if (byte_keys) KGPU_LAUNCH_SPARSE(false, true, true); else KGPU_LAUNCH_SPARSE(false, false, true); }
+                else                   { if (byte_keys) KGPU_LAUNCH_SPARSE(false, true, false); else KGPU_LAUNCH_SPARSE(false, false, false); }
                 h->launches++;
             }
             if (has_mem != 0) {
@@ -452,6 +461,7 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
                 h->launches++;
             }
 #undef KGPU_LAUNCH_SPARSE
+#undef KGPU_LAUNCH_SPARSE_TMA
         } else if (has_mem != 0) {   // K1m: the memory-constrained pods (its blocks exit at once if the flag is 0)
             kgpu::score_pairs_lane_per_node<true, true><<<grid, kgpu::LPN_THREADS, 0, st>>>(
                 topo4, s.d_free, mem4, s.d_flag, s.n, s.node_id_base, pods4, P, (int)per, W, PC, d_keys);

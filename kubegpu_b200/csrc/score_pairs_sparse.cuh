@@ -311,6 +311,44 @@ compact_nodes(const int4 *__restrict__ topo4, int32_t *free_mask, int64_t n_item
         rec[sp_rec_index(slot, t)] = make_int4((int)wds[4 * t], (int)wds[4 * t + 1], (int)wds[4 * t + 2], (int)wds[4 * t + 3]);
 }
 
+// ---- TMA (cp.async.bulk) + mbarrier helpers of the TMA instantiation ------------------------------------------
+// One-dimensional bulk copies need no tensor map: [dst in shared], [src in global], bytes (multiples of 16, 16-byte
+// aligned), completion counted in bytes on an mbarrier.  The CPU emulation build copies synchronously.
+constexpr int SP_SLAB_REC = 7 * SP_THREADS * 16;                    // a tile's records
+constexpr int SP_SLAB = SP_SLAB_REC + SP_THREADS * 4 + SP_THREADS * 4;   // + meta + order: 15360 bytes at 128 threads
+constexpr int SP_TMA_STAGES = 2;
+constexpr size_t SP_TMA_DYN_SMEM = (size_t)SP_TMA_STAGES * SP_SLAB + 128;     // + alignment slack
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t sp_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sp_mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sp_smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void sp_mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void sp_mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sp_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sp_bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sp_smem_addr(dst)), "l"(src), "r"(bytes), "r"(sp_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ bool sp_mbar_wait(unsigned long long *bar, uint32_t parity) {     // false: gave up after ~2 s
+    const long long t0 = clock64();
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(sp_smem_addr(bar)), "r"(parity) : "memory");
+        if (!done && clock64() - t0 > 4000000000LL) return false;
+    }
+    return true;
+}
+#else
+inline void sp_mbar_init(unsigned long long *, uint32_t) {}
+inline void sp_mbar_fence_init() {}
+inline void sp_mbar_expect_tx(unsigned long long *, uint32_t) {}
+inline void sp_bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *) { std::memcpy(dst, src, bytes); }
+inline bool sp_mbar_wait(unsigned long long *, uint32_t) { return true; }
+#endif
+
 // grid = (work items) or (slot tiles, pod splits); block = SP_THREADS.  order[slot] = node index or -1 (padding).
 // STREAM (few pods, runs of tiles: the HBM-bound regime): the NEXT tile's record is loaded into a second register
 // set before the current tile's bucket loops, so every block always has a tile in flight from DRAM while it
@@ -319,21 +357,39 @@ compact_nodes(const int4 *__restrict__ topo4, int32_t *free_mask, int64_t n_item
 #ifndef KGPU_SP_STREAM_MINBLOCKS
 #define KGPU_SP_STREAM_MINBLOCKS 5
 #endif
-template <bool PER_PAIR, bool MEM, bool BYTE_KEYS, bool STREAM = false>
-__global__ void __launch_bounds__(SP_THREADS, STREAM ? KGPU_SP_STREAM_MINBLOCKS : MEM ? 4 : KGPU_SP_MINBLOCKS)
+// TMA (at most 64 pods, runs of tiles): the streaming path with the tiles staged by the TMA engine instead -- a
+// two-stage ring of 15 KB slabs (records + meta + order of a tile) in shared memory, filled by cp.async.bulk and
+// signalled on mbarriers; the pod tables shrink to 64 pods so that 6 blocks fit an SM, no prefetch registers.
+#ifndef KGPU_SP_TMA_MINBLOCKS
+#define KGPU_SP_TMA_MINBLOCKS 6
+#endif
+constexpr int SP_TMA_PODS = 64;
+template <bool PER_PAIR, bool MEM, bool BYTE_KEYS, bool STREAM = false, bool TMA = false>
+__global__ void __launch_bounds__(SP_THREADS, TMA ? KGPU_SP_TMA_MINBLOCKS : STREAM ? KGPU_SP_STREAM_MINBLOCKS : MEM ? 4 : KGPU_SP_MINBLOCKS)
 score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ meta,
                    const int32_t *__restrict__ gpu_mem, const int32_t *__restrict__ order,
                    const int *__restrict__ mem_flag, int64_t node_id_base, const int4 *__restrict__ pods4, int64_t P,
                    int pods_per_split, const int4 *__restrict__ work, PipeConsts pc, unsigned long long *__restrict__ keys) {
     if (MEM && *mem_flag == 0) return;
+    static_assert(!TMA || (STREAM && !MEM), "the TMA instantiation is a streaming one");
     constexpr int SUB = MEM ? SP_MEM_SUB : 1, NB = 9 * SUB + 1;     // sort buckets: (k, sub) for k = 0..8, then "not for this launch"
+    constexpr int CH = TMA ? SP_TMA_PODS : SP_CHUNK;                // pods per chunk of the block's pod sort
+    constexpr int POS = CH + 10 * (SP_GROUP - 1), TAB = (POS + SP_GROUP - 1) / SP_GROUP + 1;
     __shared__ int32_t sCnt[NB], sOff[11], sPad[9];
-    __shared__ uint8_t sK[SP_CHUNK];
-    __shared__ uint16_t sIdx[SP_POS];                  // bucket-order position -> chunk position (SP_DUMMY: padding)
-    __shared__ SpEnt sTab[SP_WARPS][SP_TAB];           // per warp, bucket order: multipliers | results
+    __shared__ uint8_t sK[CH];
+    __shared__ uint16_t sIdx[POS];                     // bucket-order position -> chunk position (SP_DUMMY: padding)
+    __shared__ SpEnt sTab[SP_WARPS][TAB];              // per warp, bucket order: multipliers | results
     __shared__ uint32_t sHotLo[SP_THREADS], sHotHi[SP_THREADS];   // position g -> byte (1 << GPU index), g = 0..3 | 4..7
     __shared__ int32_t sNode[SP_THREADS];              // slot -> node index (-1 = padding)
-    __shared__ unsigned long long sAcc[SP_POS];        // multi-tile items: running minimum per pod position across the tiles
+    __shared__ unsigned long long sAcc[POS];           // multi-tile items: running minimum per pod position across the tiles
+    __shared__ unsigned long long sBar[SP_TMA_STAGES]; // TMA: "slab of this stage has landed"
+#ifdef __CUDACC__
+    extern __shared__ __align__(128) unsigned char sDynRing[];      // TMA: SP_TMA_STAGES slabs
+    unsigned char *const ring = sDynRing;
+#else
+    __shared__ __attribute__((aligned(128))) unsigned char sRingEmu[SP_TMA_STAGES * SP_SLAB];
+    unsigned char *const ring = sRingEmu;
+#endif
 
     const int tid = threadIdx.x;
     SpEnt *const tab = sTab[tid >> 5];
@@ -362,7 +418,31 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
     int4 nx[7];
     int32_t nx_node = -1;
     uint32_t nx_pm = 0;
-    if (STREAM) load_tile(tile_first, nx, nx_node, nx_pm);
+    // TMA: thread 0 asks the TMA engine for a tile's slab (three bulk copies counted on the stage's mbarrier)
+    auto tma_fetch = [&](int64_t t, int stage) {
+        unsigned char *slab = ring + (size_t)stage * SP_SLAB;
+        sp_mbar_expect_tx(&sBar[stage], (uint32_t)SP_SLAB);
+        sp_bulk_g2s(slab, rec + t * (7 * SP_THREADS), (uint32_t)SP_SLAB_REC, &sBar[stage]);
+        sp_bulk_g2s(slab + SP_SLAB_REC, meta + t * SP_THREADS, (uint32_t)(SP_THREADS * 4), &sBar[stage]);
+        sp_bulk_g2s(slab + SP_SLAB_REC + SP_THREADS * 4, order + t * SP_THREADS, (uint32_t)(SP_THREADS * 4), &sBar[stage]);
+    };
+    if (TMA) {
+        if (tid == 0) {
+#pragma unroll
+            for (int st = 0; st < SP_TMA_STAGES; st++) sp_mbar_init(&sBar[st], 1);
+            sp_mbar_fence_init();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            tma_fetch(tile_first, 0);
+            if (ntiles > 1) tma_fetch(tile_first + 1, 1);
+        }
+#ifndef __CUDACC__
+        __syncthreads();                               // (emulation: the "TMA" is a memcpy by thread 0)
+#endif
+    } else if (STREAM) {
+        load_tile(tile_first, nx, nx_node, nx_pm);
+    }
 #pragma unroll 1
     for (int tt = 0; tt < ntiles; tt++) {
     const int64_t tile_index = tile_first + tt;
@@ -370,8 +450,17 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
     const int64_t slot = tile_index * SP_THREADS + tid;
     int4 rw[7];
     int32_t node;
-    uint32_t pm;                                       // eight 3-bit GPU indices | free count << 24
-    if (STREAM) {
+    uint32_t pm;                                       // eight 3-bit GPU indices | free count << 24 | tile ordered << 31
+    if (TMA) {
+        const int stage = tt % SP_TMA_STAGES;
+        const bool landed = sp_mbar_wait(&sBar[stage], (uint32_t)((tt / SP_TMA_STAGES) & 1));
+        const unsigned char *slab = ring + (size_t)stage * SP_SLAB;
+        const int4 *srec = reinterpret_cast<const int4 *>(slab);
+#pragma unroll
+        for (int q = 0; q < 7; q++) rw[q] = srec[q * SP_THREADS + tid];
+        pm = reinterpret_cast<const uint32_t *>(slab + SP_SLAB_REC)[tid];
+        node = landed ? reinterpret_cast<const int32_t *>(slab + SP_SLAB_REC + SP_THREADS * 4)[tid] : -1;   // a slab that never came scores nothing
+    } else if (STREAM) {
 #pragma unroll
         for (int q = 0; q < 7; q++) rw[q] = nx[q];
         node = nx_node;
@@ -401,7 +490,8 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
         // The streaming instantiation keeps the two block barriers the in-kernel check used to have: they hold the
         // block's four warps in step, so the next tile's 14 KB are requested together.  Measured on one box, 10M nodes:
         // 0.2007 / 0.2990 ms (1 / 32 pods) with them, 0.2294 / 0.3298 ms without.
-        __syncthreads();
+        __syncthreads();                               // (TMA: every thread has copied its part of the slab out)
+        if (TMA && tid == 0 && tt + SP_TMA_STAGES < ntiles) tma_fetch(tile_index + SP_TMA_STAGES, tt % SP_TMA_STAGES);
         ordered = __syncthreads_and(ordered) != 0;
     }
     PairCosts C;
@@ -417,8 +507,8 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
     }
     const int F = (int)__reduce_max_sync(0xFFFFFFFFu, nfree);    // warp-uniform bound on usable positions
 
-    for (int64_t c0 = p_begin; c0 < p_end; c0 += SP_CHUNK) {
-        const int cn = (int)min((int64_t)SP_CHUNK, p_end - c0);
+    for (int64_t c0 = p_begin; c0 < p_end; c0 += CH) {
+        const int cn = (int)min((int64_t)CH, p_end - c0);
         if (!multi || tt == 0) {                   // the chunk's pod sort (once per item when it walks several tiles)
         __syncthreads();
         if (tid < NB) sCnt[tid] = 0;
