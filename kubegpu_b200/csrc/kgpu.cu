@@ -420,7 +420,7 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
                     if (env_tail >= 0) prm.tail_percent = env_tail;
                     if (env_waves > 0) prm.waves = env_waves;
                     if (env_floor > 0) prm.floor = env_floor;
-                    const int64_t res_list = (tma_mode != 0 && P <= kgpu::SP_TMA_PODS) ? (int64_t)s.sm_count * KGPU_SP_TMA_MINBLOCKS
+                    const int64_t res_list = (tma_mode != 0 && P <= kgpu::SP_TMA_PODS) ? (int64_t)s.sm_count * kgpu::sp_tma_blocks(P)
                                              : P <= kgpu::kSparseChunk               ? (int64_t)s.sm_count * KGPU_SP_STREAM_MINBLOCKS
                                                                                      : resident;
                     kgpu::build_sparse_work(s.tile_class, P, res_list, s.h_work, prm);
@@ -442,16 +442,30 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
 #define KGPU_LAUNCH_SPARSE(MEMF, BK, ST)                                                                      \
     kgpu::score_pairs_sparse<true, MEMF, BK, ST><<<grid, kgpu::SP_THREADS, 0, st>>>(                          \
         s.d_rec, s.d_meta, s.d_mem, s.d_order, s.d_flag, s.node_id_base, pods4, P, (int)per, d_work, PC, d_keys)
-#define KGPU_LAUNCH_SPARSE_TMA(BK)                                                                            \
-    kgpu::score_pairs_sparse<true, false, BK, true, true><<<grid, kgpu::SP_THREADS, kgpu::SP_TMA_DYN_SMEM, st>>>( \
+#define KGPU_LAUNCH_SPARSE_TMA(BK, MB)                                                                        \
+    kgpu::score_pairs_sparse<true, false, BK, true, MB><<<grid, kgpu::SP_THREADS, kgpu::SP_TMA_DYN_SMEM, st>>>(   \
         s.d_rec, s.d_meta, s.d_mem, s.d_order, s.d_flag, s.node_id_base, pods4, P, (int)per, d_work, PC, d_keys)
             // few pods (the batch is one chunk): the work list holds runs of tiles -> the STREAM instantiation (next
             // tile's record prefetched into registers while the current one is scored); at most 64 pods: the TMA one
-            // (tiles staged by cp.async.bulk into a shared-memory ring, KGPU_SP_TMA=0 turns it off)
+            // (tiles staged by cp.async.bulk into shared memory, 7 or 8 blocks per SM; KGPU_SP_TMA=0 turns it off)
             const bool stream_build = use_work && P <= kgpu::kSparseChunk;
             const bool tma_build = stream_build && tma_mode != 0 && P <= kgpu::SP_TMA_PODS;
+            if (tma_build) {   // static + dynamic shared memory may pass 48 KB with more stages: opt in once
+                static const cudaError_t tma_attr = [] {
+                    const int bytes = (int)kgpu::SP_TMA_DYN_SMEM;
+                    cudaError_t e = cudaFuncSetAttribute(kgpu::score_pairs_sparse<true, false, true, true, KGPU_SP_TMA_MINBLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+                    if (e == cudaSuccess) e = cudaFuncSetAttribute(kgpu::score_pairs_sparse<true, false, false, true, KGPU_SP_TMA_MINBLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+                    if (e == cudaSuccess) e = cudaFuncSetAttribute(kgpu::score_pairs_sparse<true, false, true, true, KGPU_SP_TMA_MINBLOCKS_FEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+                    if (e == cudaSuccess) e = cudaFuncSetAttribute(kgpu::score_pairs_sparse<true, false, false, true, KGPU_SP_TMA_MINBLOCKS_FEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+                    return e;
+                }();
+                if (tma_attr != cudaSuccess) return fail(h, KGPU_ERR_CUDA, "cudaFuncSetAttribute(TMA K1s): %s", cudaGetErrorString(tma_attr));
+            }
             if (sparse_main) {
-                if (tma_build)         { if (byte_keys) KGPU_LAUNCH_SPARSE_TMA(true); else KGPU_LAUNCH_SPARSE_TMA(false); }
+                if (tma_build) {
+                    if (P <= kgpu::SP_TMA_FEW_PODS) { if (byte_keys) KGPU_LAUNCH_SPARSE_TMA(true, KGPU_SP_TMA_MINBLOCKS_FEW); else KGPU_LAUNCH_SPARSE_TMA(false, KGPU_SP_TMA_MINBLOCKS_FEW); }
+                    else                            { if (byte_keys) KGPU_LAUNCH_SPARSE_TMA(true, KGPU_SP_TMA_MINBLOCKS); else KGPU_LAUNCH_SPARSE_TMA(false, KGPU_SP_TMA_MINBLOCKS); }
+                }
                 else if (stream_build) { if (byte_keys) KGPU_LAUNCH_SPARSE(false, true, true); else KGPU_LAUNCH_SPARSE(false, false, true); }
                 else                   { if (byte_keys) KGPU_LAUNCH_SPARSE(false, true, false); else KGPU_LAUNCH_SPARSE(false, false, false); }
                 h->launches++;

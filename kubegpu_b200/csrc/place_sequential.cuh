@@ -419,6 +419,39 @@ place_sequential(const int32_t *__restrict__ topo, int32_t *__restrict__ free_ma
                     }
                 }
             }
+#ifndef KGPU_PLACE_HELPER
+#define KGPU_PLACE_HELPER 1        // a warp without a task (warp 9 with one view) prefetches the NEXT pod's candidate into L1: 10.94 ms against 11.43 on one box (C2, profiles/r02_k3_helper_ab.txt)
+#endif
+            else if (KGPU_PLACE_HELPER && pi + 1 < pn) {
+                // Off the chain: the next pod's winner under the state BEFORE this pod's update is its winner afterwards
+                // too unless it is this pod's node (a placement only RAISES the keys of one node).  While the other warps
+                // refresh, bring what they will load for that node into this SM's L1: its half tables and mask, and for
+                // every task the node-key row of its tile and the tile minima of its supertile.
+                const int4 rq = sPods[pi + 1];
+                const int k2 = rq.x;
+                if (k2 >= 1 && k2 <= 8) {
+                    int v2 = 0;
+                    for (int j = 1; j < V; j++)
+                        if (rq.w == sViewMin[j]) v2 = j;
+                    const unsigned long long *sp2 = sSuper[epoch & 1] + (v2 * 9 + k2) * ST;
+                    unsigned long long b2 = ~0ull;
+                    for (int s2 = lane; s2 < ST; s2 += 32) b2 = min(b2, sp2[s2]);
+                    b2 = warp_min_u64_redux(b2);
+                    const int64_t cand = (int64_t)((b2 >> 8) & 0xFFFFFFFFull) - node_id_base;
+                    if (b2 != ~0ull && cand != node) {
+                        const int64_t ctile = cand >> 7, cst = ctile >> st_shift;
+                        const int rows = ntask * 4, mins = ntask * 2;       // 128-byte lines: 4 per node-key row, 2 per 32 tile minima
+                        for (int e = lane; e < 4 + rows + mins; e += 32) {
+                            const void *q;
+                            if (e < 3) q = half_all + cand * PLACE_HALF + 32 * e;
+                            else if (e == 3) q = free_mask + cand;
+                            else if (e < 4 + rows) { const int t = (e - 4) >> 2, j = (e - 4) & 3; q = nodebest + (int64_t)t * Npad + ctile * PLACE_TILE + 32 * j; }
+                            else { const int t = (e - 4 - rows) >> 1, j = (e - 4 - rows) & 1; q = tilebest + (int64_t)t * T + min((int64_t)Ti - 1, (cst << st_shift) + 16 * j); }
+                            prefetch_l1(q);
+                        }
+                    }
+                }
+            }
             epoch++;
             __syncthreads();
         }

@@ -316,7 +316,11 @@ compact_nodes(const int4 *__restrict__ topo4, int32_t *free_mask, int64_t n_item
 // aligned), completion counted in bytes on an mbarrier.  The CPU emulation build copies synchronously.
 constexpr int SP_SLAB_REC = 7 * SP_THREADS * 16;                    // a tile's records
 constexpr int SP_SLAB = SP_SLAB_REC + SP_THREADS * 4 + SP_THREADS * 4;   // + meta + order: 15360 bytes at 128 threads
-constexpr int SP_TMA_STAGES = 2;
+#ifndef KGPU_SP_TMA_STAGES
+#define KGPU_SP_TMA_STAGES 1      // slabs per block.  Measured (10M nodes, one box, profiles/r02_stream_tma_ring.txt): blocks per SM matter,
+                                  // stages do not -- 1 x 8: 0.262 ms at 32 pods, 1 x 7: 0.270, 2 x 6: 0.289, 2 x 5: 0.315, 3 x 4: 0.365
+#endif
+constexpr int SP_TMA_STAGES = KGPU_SP_TMA_STAGES;
 constexpr size_t SP_TMA_DYN_SMEM = (size_t)SP_TMA_STAGES * SP_SLAB + 128;     // + alignment slack
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t sp_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -358,14 +362,22 @@ inline bool sp_mbar_wait(unsigned long long *, uint32_t) { return true; }
 #define KGPU_SP_STREAM_MINBLOCKS 5
 #endif
 // TMA (at most 64 pods, runs of tiles): the streaming path with the tiles staged by the TMA engine instead -- a
-// two-stage ring of 15 KB slabs (records + meta + order of a tile) in shared memory, filled by cp.async.bulk and
-// signalled on mbarriers; the pod tables shrink to 64 pods so that 6 blocks fit an SM, no prefetch registers.
+// slab (records + meta + order of a tile, 15 KB) per stage in shared memory, filled by cp.async.bulk and signalled on an
+// mbarrier; the threads copy their part out to registers and the slab is refilled at once, so the next tile is in
+// flight while this one is scored.  The pod tables shrink to 64 pods and there are no prefetch registers, so 7 or 8
+// blocks fit an SM: TMA = blocks per SM of the instantiation (0: not a TMA one).  8 blocks (64 registers, a 16-byte
+// spill) win from a handful of pods on, 7 (72 registers) with fewer: 0.1925 against 0.2007 ms for one pod.
 #ifndef KGPU_SP_TMA_MINBLOCKS
-#define KGPU_SP_TMA_MINBLOCKS 6
+#define KGPU_SP_TMA_MINBLOCKS 8
+#endif
+#ifndef KGPU_SP_TMA_MINBLOCKS_FEW
+#define KGPU_SP_TMA_MINBLOCKS_FEW 7
 #endif
 constexpr int SP_TMA_PODS = 64;
-template <bool PER_PAIR, bool MEM, bool BYTE_KEYS, bool STREAM = false, bool TMA = false>
-__global__ void __launch_bounds__(SP_THREADS, TMA ? KGPU_SP_TMA_MINBLOCKS : STREAM ? KGPU_SP_STREAM_MINBLOCKS : MEM ? 4 : KGPU_SP_MINBLOCKS)
+constexpr int SP_TMA_FEW_PODS = 4;          // at most this many pods: the KGPU_SP_TMA_MINBLOCKS_FEW instantiation
+constexpr int sp_tma_blocks(int64_t P) { return P <= SP_TMA_FEW_PODS ? KGPU_SP_TMA_MINBLOCKS_FEW : KGPU_SP_TMA_MINBLOCKS; }
+template <bool PER_PAIR, bool MEM, bool BYTE_KEYS, bool STREAM = false, int TMA = 0>
+__global__ void __launch_bounds__(SP_THREADS, TMA ? TMA : STREAM ? KGPU_SP_STREAM_MINBLOCKS : MEM ? 4 : KGPU_SP_MINBLOCKS)
 score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ meta,
                    const int32_t *__restrict__ gpu_mem, const int32_t *__restrict__ order,
                    const int *__restrict__ mem_flag, int64_t node_id_base, const int4 *__restrict__ pods4, int64_t P,
@@ -375,11 +387,13 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
     constexpr int SUB = MEM ? SP_MEM_SUB : 1, NB = 9 * SUB + 1;     // sort buckets: (k, sub) for k = 0..8, then "not for this launch"
     constexpr int CH = TMA ? SP_TMA_PODS : SP_CHUNK;                // pods per chunk of the block's pod sort
     constexpr int POS = CH + 10 * (SP_GROUP - 1), TAB = (POS + SP_GROUP - 1) / SP_GROUP + 1;
-    __shared__ int32_t sCnt[NB], sOff[11], sPad[9];
+    __shared__ int32_t sCnt[NB], sOff[12], sPad[9];  // sOff[11]: bit k set = bucket k has pods (STREAM builds test it per tile)
     __shared__ uint8_t sK[CH];
     __shared__ uint16_t sIdx[POS];                     // bucket-order position -> chunk position (SP_DUMMY: padding)
     __shared__ SpEnt sTab[SP_WARPS][TAB];              // per warp, bucket order: multipliers | results
-    __shared__ uint32_t sHotLo[SP_THREADS], sHotHi[SP_THREADS];   // position g -> byte (1 << GPU index), g = 0..3 | 4..7
+    // position g -> byte (1 << GPU index), g = 0..3 | 4..7.  STREAM builds (few pods per tile) keep the slot's
+    // permutation word in sHotLo instead and expand the winner's S' in the flush: per pod, not per node.
+    __shared__ uint32_t sHotLo[SP_THREADS], sHotHi[STREAM ? 1 : SP_THREADS];
     __shared__ int32_t sNode[SP_THREADS];              // slot -> node index (-1 = padding)
     __shared__ unsigned long long sAcc[POS];           // multi-tile items: running minimum per pod position across the tiles
     __shared__ unsigned long long sBar[SP_TMA_STAGES]; // TMA: "slab of this stage has landed"
@@ -434,8 +448,9 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
         }
         __syncthreads();
         if (tid == 0) {
-            tma_fetch(tile_first, 0);
-            if (ntiles > 1) tma_fetch(tile_first + 1, 1);
+#pragma unroll
+            for (int st = 0; st < SP_TMA_STAGES; st++)
+                if (st < ntiles) tma_fetch(tile_first + st, st);
         }
 #ifndef __CUDACC__
         __syncthreads();                               // (emulation: the "TMA" is a memcpy by thread 0)
@@ -447,7 +462,6 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
     for (int tt = 0; tt < ntiles; tt++) {
     const int64_t tile_index = tile_first + tt;
     if (tt > 0) __syncthreads();                       // the previous tile's flush has read sNode / sHot*
-    const int64_t slot = tile_index * SP_THREADS + tid;
     int4 rw[7];
     int32_t node;
     uint32_t pm;                                       // eight 3-bit GPU indices | free count << 24 | tile ordered << 31
@@ -472,7 +486,9 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
     const bool valid = node >= 0;
     sNode[tid] = node;
     const uint32_t nfree = (pm >> 24) & 0xFu;            // 0 for padding slots
-    {
+    if (STREAM) {
+        sHotLo[tid] = pm;
+    } else {
         uint32_t lo = 0, hi = 0;
 #pragma unroll
         for (int g = 0; g < 4; g++) {
@@ -533,6 +549,13 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
                 acc = (acc + SP_GROUP - 1) / SP_GROUP * SP_GROUP;
             }
             sOff[9] = acc;
+            {
+                int nonempty = 0;
+#pragma unroll 1
+                for (int k = 0; k < 9; k++)
+                    if (sOff[k + 1] > sOff[k]) nonempty |= 1 << k;
+                sOff[11] = nonempty;
+            }
             const int c9 = sCnt[9 * SUB];
             sCnt[9 * SUB] = acc;
             sOff[10] = acc + c9;
@@ -565,15 +588,13 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
         __syncthreads();
         }   // pod sort
 
-        sp_run_k<0, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[0], sOff[1]);
-        sp_run_k<1, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[1], sOff[2]);
-        sp_run_k<2, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[2], sOff[3]);
-        sp_run_k<3, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[3], sOff[4]);
-        sp_run_k<4, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[4], sOff[5]);
-        sp_run_k<5, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[5], sOff[6]);
-        sp_run_k<6, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[6], sOff[7]);
-        sp_run_k<7, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[7], sOff[8]);
-        sp_run_k<8, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[8], sOff[9]);
+        // few pods per tile: most buckets are empty and nine (two loads, compare, branch) prologues per tile show; one
+        // word says which buckets to enter
+        const uint32_t kmask = STREAM ? (uint32_t)sOff[11] : 0x1FFu;
+#define KGPU_SP_RUN(K) \
+        if (!STREAM || ((kmask >> K) & 1u)) sp_run_k<K, PER_PAIR, MEM, BYTE_KEYS>(F, C, pc, nfree, valid, mem, lane_field, tab, sOff[K], sOff[K + 1]);
+        KGPU_SP_RUN(0) KGPU_SP_RUN(1) KGPU_SP_RUN(2) KGPU_SP_RUN(3) KGPU_SP_RUN(4) KGPU_SP_RUN(5) KGPU_SP_RUN(6) KGPU_SP_RUN(7) KGPU_SP_RUN(8)
+#undef KGPU_SP_RUN
         __syncthreads();
 
         // block result per pod: min over the warps of (cost, node id), S' -> real GPU mask through the
@@ -602,11 +623,19 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
             }
             if (best_slot >= 0) {
                 // S' bit g set -> byte g of the one-hot words; OR the selected bytes together
-                const uint32_t sel_lo = (((best_m & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
-                const uint32_t sel_hi = ((((best_m >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
-                uint32_t t = (sHotLo[best_slot] & sel_lo) | (sHotHi[best_slot] & sel_hi);
-                t |= t >> 16;
-                const uint32_t S = (t | (t >> 8)) & 0xFFu;
+                uint32_t S;
+                if (STREAM) {                          // bit g of S' -> GPU index in the g-th 3-bit field of the permutation word
+                    const uint32_t perm = sHotLo[best_slot];
+                    S = 0;
+#pragma unroll
+                    for (int g = 0; g < 8; g++) S |= ((best_m >> g) & 1u) << ((perm >> (3 * g)) & 7u);
+                } else {
+                    const uint32_t sel_lo = (((best_m & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+                    const uint32_t sel_hi = ((((best_m >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+                    uint32_t t = (sHotLo[best_slot] & sel_lo) | (sHotHi[best_slot] & sel_hi);
+                    t |= t >> 16;
+                    S = (t | (t >> 8)) & 0xFFu;
+                }
                 const unsigned long long nid = (unsigned long long)(node_id_base + (long long)sNode[best_slot]);
                 const unsigned long long key = ((unsigned long long)cost << 40) | (nid << 8) | S;
                 if (multi) sAcc[i] = min(sAcc[i], key);      // position i belongs to this thread for the whole item

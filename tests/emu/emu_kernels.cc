@@ -104,8 +104,8 @@ void emu_launch_sparse(const EmuCache &c, const int32_t *free_mask, const int32_
     const bool stream_build = splits < 0 && P <= kgpu::kSparseChunk;      // kgpu.cu: runs of tiles -> the STREAM instantiation
     const bool tma_build = stream_build && P <= kgpu::SP_TMA_PODS;        //          at most 64 pods -> the TMA one
     if (tma_build) {
-        if (byte_keys) emu::launch(grid, dim3(kgpu::SP_THREADS), [&] { kgpu::score_pairs_sparse<true, false, true, true, true>(c.rec, c.meta, mem, c.order.data(), &flag, node_id_base, pods4, P, per, work, kPC, keys); });
-        else emu::launch(grid, dim3(kgpu::SP_THREADS), [&] { kgpu::score_pairs_sparse<true, false, false, true, true>(c.rec, c.meta, mem, c.order.data(), &flag, node_id_base, pods4, P, per, work, kPC, keys); });
+        if (byte_keys) emu::launch(grid, dim3(kgpu::SP_THREADS), [&] { kgpu::score_pairs_sparse<true, false, true, true, 8>(c.rec, c.meta, mem, c.order.data(), &flag, node_id_base, pods4, P, per, work, kPC, keys); });
+        else emu::launch(grid, dim3(kgpu::SP_THREADS), [&] { kgpu::score_pairs_sparse<true, false, false, true, 8>(c.rec, c.meta, mem, c.order.data(), &flag, node_id_base, pods4, P, per, work, kPC, keys); });
     } else if (stream_build) { if (byte_keys) EMU_SPARSE(false, true, true); else EMU_SPARSE(false, false, true); }
     else              { if (byte_keys) EMU_SPARSE(false, true, false); else EMU_SPARSE(false, false, false); }
     if (flag) { if (byte_keys) EMU_SPARSE(true, true, false); else EMU_SPARSE(true, false, false); }
