@@ -79,6 +79,7 @@ struct kgpu_shard {
     std::vector<kgpu::SparseWorkItem> h_work;   // K1s work list for work_P pods (sparse_work.h)
     int4 *d_work = nullptr;
     int64_t work_cap = 0, work_P = -1;
+    bool tma_attr_done = false;                 // cudaFuncSetAttribute of the TMA instantiations done on this device
     uint32_t *d_nodebest = nullptr;          // [views][9][Npad]  K3 tables
     int32_t *d_half = nullptr;               // [Npad][96]  K3: half tables of every node (place_half_tables)
     unsigned long long *d_tilebest = nullptr;   // [views][9][T]
@@ -450,16 +451,14 @@ int launch_score(kgpu_ctx *h, kgpu_shard &s, const int32_t *d_pods, int64_t P, u
             // (tiles staged by cp.async.bulk into shared memory, 7 or 8 blocks per SM; KGPU_SP_TMA=0 turns it off)
             const bool stream_build = use_work && P <= kgpu::kSparseChunk;
             const bool tma_build = stream_build && tma_mode != 0 && P <= kgpu::SP_TMA_PODS;
-            if (tma_build) {   // static + dynamic shared memory may pass 48 KB with more stages: opt in once
-                static const cudaError_t tma_attr = [] {
-                    const int bytes = (int)kgpu::SP_TMA_DYN_SMEM;
-                    cudaError_t e = cudaFuncSetAttribute(kgpu::score_pairs_sparse<true, false, true, true, KGPU_SP_TMA_MINBLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-                    if (e == cudaSuccess) e = cudaFuncSetAttribute(kgpu::score_pairs_sparse<true, false, false, true, KGPU_SP_TMA_MINBLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-                    if (e == cudaSuccess) e = cudaFuncSetAttribute(kgpu::score_pairs_sparse<true, false, true, true, KGPU_SP_TMA_MINBLOCKS_FEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-                    if (e == cudaSuccess) e = cudaFuncSetAttribute(kgpu::score_pairs_sparse<true, false, false, true, KGPU_SP_TMA_MINBLOCKS_FEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-                    return e;
-                }();
-                if (tma_attr != cudaSuccess) return fail(h, KGPU_ERR_CUDA, "cudaFuncSetAttribute(TMA K1s): %s", cudaGetErrorString(tma_attr));
+            if (tma_build && !s.tma_attr_done) {   // static + dynamic shared memory may pass 48 KB with more stages: opt in, once per device
+                const int bytes = (int)kgpu::SP_TMA_DYN_SMEM;
+                cudaError_t e = cudaFuncSetAttribute(kgpu::score_pairs_sparse<true, false, true, true, KGPU_SP_TMA_MINBLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(kgpu::score_pairs_sparse<true, false, false, true, KGPU_SP_TMA_MINBLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(kgpu::score_pairs_sparse<true, false, true, true, KGPU_SP_TMA_MINBLOCKS_FEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(kgpu::score_pairs_sparse<true, false, false, true, KGPU_SP_TMA_MINBLOCKS_FEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+                if (e != cudaSuccess) return fail(h, KGPU_ERR_CUDA, "cudaFuncSetAttribute(TMA K1s): %s", cudaGetErrorString(e));
+                s.tma_attr_done = true;
             }
             if (sparse_main) {
                 if (tma_build) {

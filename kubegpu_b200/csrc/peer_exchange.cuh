@@ -35,8 +35,9 @@ gather_and_min(unsigned long long *__restrict__ local_keys, int64_t P, int64_t m
     if (p < P) {
         const unsigned long long k = local_keys[p];
         local_keys[p] = ~0ull;                     // ready for the next step's K1
-#pragma unroll 1
-        for (int g = 0; g < world; g++) peers.slots[g][(int64_t)rank * max_pods + p] = k;
+#pragma unroll
+        for (int g = 0; g < PEER_MAX_WORLD; g++)
+            if (g < world) peers.slots[g][(int64_t)rank * max_pods + p] = k;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -62,10 +63,15 @@ gather_and_min(unsigned long long *__restrict__ local_keys, int64_t P, int64_t m
     __syncthreads();
     __threadfence_system();                        // acquire side: the flags were read before the slots are
     if (p < P) {
-        const volatile unsigned long long *mine = peers.slots[rank];
-        unsigned long long best = ~0ull;
-#pragma unroll 1
-        for (int g = 0; g < world; g++) best = min(best, mine[(int64_t)g * max_pods + p]);
+        // all G loads in flight together (they bypass L1: the slots were written by the peers into this device's memory;
+        // a loop of dependent volatile loads would pay G L2 round trips one after the other)
+        const unsigned long long *mine = peers.slots[rank];
+        unsigned long long v[PEER_MAX_WORLD];
+#pragma unroll
+        for (int g = 0; g < PEER_MAX_WORLD; g++) v[g] = g < world ? __ldcv(mine + (int64_t)g * max_pods + p) : ~0ull;
+        unsigned long long best = v[0];
+#pragma unroll
+        for (int g = 1; g < PEER_MAX_WORLD; g++) best = min(best, v[g]);
         final_keys[p] = best;
     }
 }

@@ -158,6 +158,8 @@ inline T __shfl_up_sync(unsigned, T v, int delta, int = 32) {      // lanes belo
 // ---- memory ------------------------------------------------------------------------------------------
 template <class T>
 inline T __ldg(const T *p) { return *p; }
+template <typename T>
+inline T __ldcv(const T *p) { return *reinterpret_cast<const volatile T *>(p); }
 template <class T>
 inline T __ldcg(const T *p) { return *p; }
 template <class T>
