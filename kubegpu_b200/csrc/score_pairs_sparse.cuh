@@ -461,7 +461,7 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
 #pragma unroll 1
     for (int tt = 0; tt < ntiles; tt++) {
     const int64_t tile_index = tile_first + tt;
-    if (tt > 0) __syncthreads();                       // the previous tile's flush has read sNode / sHot*
+    if (!TMA && tt > 0) __syncthreads();               // the previous tile's flush has read sNode / sHot* (TMA: the barrier below)
     int4 rw[7];
     int32_t node;
     uint32_t pm;                                       // eight 3-bit GPU indices | free count << 24 | tile ordered << 31
@@ -474,6 +474,10 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
         for (int q = 0; q < 7; q++) rw[q] = srec[q * SP_THREADS + tid];
         pm = reinterpret_cast<const uint32_t *>(slab + SP_SLAB_REC)[tid];
         node = landed ? reinterpret_cast<const int32_t *>(slab + SP_SLAB_REC + SP_THREADS * 4)[tid] : -1;   // a slab that never came scores nothing
+        // ONE barrier per tile before the loops: every thread has copied its part of the slab out (it can be refilled)
+        // and has finished the previous tile's flush (sNode / sHotLo / the pod table can be rewritten)
+        __syncthreads();
+        if (tid == 0 && tt + SP_TMA_STAGES < ntiles) tma_fetch(tile_index + SP_TMA_STAGES, tt % SP_TMA_STAGES);
     } else if (STREAM) {
 #pragma unroll
         for (int q = 0; q < 7; q++) rw[q] = nx[q];
@@ -502,12 +506,12 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
     // order IS (cost, node) order and the flush can min the four warp keys directly.  Decided when the records were
     // built (bit 31 of every meta word of the tile): no barrier, no neighbour load here.
     bool ordered = BYTE_KEYS && (pm >> 31) != 0;
-    if (STREAM) {
-        // The streaming instantiation keeps the two block barriers the in-kernel check used to have: they hold the
-        // block's four warps in step, so the next tile's 14 KB are requested together.  Measured on one box, 10M nodes:
-        // 0.2007 / 0.2990 ms (1 / 32 pods) with them, 0.2294 / 0.3298 ms without.
-        __syncthreads();                               // (TMA: every thread has copied its part of the slab out)
-        if (TMA && tid == 0 && tt + SP_TMA_STAGES < ntiles) tma_fetch(tile_index + SP_TMA_STAGES, tt % SP_TMA_STAGES);
+    if (STREAM && !TMA) {
+        // The register-prefetch instantiation keeps the two block barriers the in-kernel check used to have: they hold
+        // the block's four warps in step, so the next tile's 14 KB are requested together.  Measured on one box, 10M
+        // nodes: 0.2007 / 0.2990 ms (1 / 32 pods) with them, 0.2294 / 0.3298 ms without.  (The TMA instantiation has
+        // one thread request the slab: it runs on two barriers per tile, the one above and the one before the flush.)
+        __syncthreads();
         ordered = __syncthreads_and(ordered) != 0;
     }
     PairCosts C;
