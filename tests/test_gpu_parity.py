@@ -218,6 +218,23 @@ def test_ten_million_nodes_sweep_point(scorer, oracle_b):
     scorer.upload_nodes(topo[:1], free[:1])          # release the 2.5 GB before the next test
 
 
+def test_few_pod_instantiations_at_their_boundaries(scorer, oracle_b):
+    """The host picks the K1s instantiation by pod count: TMA-staged tiles with 7 blocks per SM up to 4 pods, with 8
+    blocks up to 64, the register-prefetch one up to 512, the plain one above.  Every boundary, on heterogeneous nodes
+    (runs of tiles across class boundaries, ragged permutations), with a k = 0 and an invalid pod riding along."""
+    topo, free, _ = synth.gen_c4(N=300_000, P=1)
+    scorer.set_variant(_lib.VARIANT_SPARSE)
+    scorer.upload_nodes(topo, free, node_id_base=5)
+    for P in (1, 2, 4, 5, 31, 32, 33, 63, 64, 65, 200, 512, 513):
+        pods = synth.make_pods((1 + synth.rand_below(77, P, P, 8)).astype(np.int32))
+        pods[0, 0] = 0
+        if P > 3:
+            pods[3, 0] = 9
+        want = oracle_b.score_batch(topo, free, pods, node_id_base=5, fast=True, nthreads=8)
+        assert (scorer.score_batch(pods) == want).all(), P
+    scorer.upload_nodes(topo[:1], free[:1])
+
+
 def test_agree_set_on_gpu_against_reference_greedy(golden_dir):
     """the chain GPU -> Oracle A -> reference goldens on hardware.  All 223 two-level
     8-GPU shapes x k = 1..8 (1784 cases) go through kgpu_score_pairs; the GPU's optimal cost is compared

@@ -378,3 +378,20 @@ def test_emulated_multi_tile_items_few_pods(emu, oracle_b, resident):
     assert (_run(emu.emu_score_sparse, topo, free, pods, W, mem=mem, splits=-resident) == want).all()
     p1 = synth.make_pods(np.array([3], dtype=np.int32))       # a single pod
     assert (_run(emu.emu_score_sparse, topo, free, p1, W, splits=-resident) == oracle_b.score_batch(topo, free, p1, W)).all()
+
+
+@pytest.mark.parametrize("P", [2, 4, 5, 63, 64, 65, 130])
+@pytest.mark.parametrize("wmax", [6, 2341])
+def test_emulated_few_pod_instantiations_at_their_boundaries(emu, oracle_b, P, wmax):
+    """The three few-pod instantiations and the pod counts where the host switches between them: at most 4 pods
+    (TMA, 7 blocks per SM), at most 64 (TMA, 8 blocks), at most 512 (next tile's record prefetched into registers);
+    byte-aligned and general warp keys; heterogeneous nodes so that tiles mix classes (the flush then compares node ids
+    explicitly) and S' has to be expanded through ragged permutations; an invalid k and a k = 0 pod ride along."""
+    topo, free, pods = synth.gen_c4(N=700, P=P, seed=1000 + P)
+    pods[0, 0] = 0
+    if P > 4:
+        pods[4, 0] = 9
+    W = np.array([max(1, wmax - 3 * i) for i in range(16)], dtype=np.int32)
+    want = oracle_b.score_batch(topo, free, pods, W, node_id_base=11)
+    for resident in (1, 2):                                   # runs of many tiles / of a few tiles per item
+        assert (_run(emu.emu_score_sparse, topo, free, pods, W, base=11, splits=-resident) == want).all(), resident
