@@ -395,7 +395,12 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
     // permutation word in sHotLo instead and expand the winner's S' in the flush: per pod, not per node.
     __shared__ uint32_t sHotLo[SP_THREADS], sHotHi[STREAM ? 1 : SP_THREADS];
     __shared__ int32_t sNode[SP_THREADS];              // slot -> node index (-1 = padding)
-    __shared__ unsigned long long sAcc[POS];           // multi-tile items: running minimum per pod position across the tiles
+    // multi-tile items: running minimum per pod position across the tiles as cost << 32 | node index (a node has ONE best
+    // subset, so this orders like the final key) and where it came from: tile of the run << 16 | slot << 8 | S'.  The final
+    // key -- S' expanded through the slot's permutation word, the node id -- is built once per item, not per tile.
+    constexpr bool CAN_MULTI = STREAM || MEM;          // the hosts hand runs of tiles to these instantiations only
+    __shared__ unsigned long long sAcc[CAN_MULTI ? POS : 1];
+    __shared__ uint32_t sWin[CAN_MULTI ? POS : 1];
     __shared__ unsigned long long sBar[SP_TMA_STAGES]; // TMA: "slab of this stage has landed"
 #ifdef __CUDACC__
     extern __shared__ __align__(128) unsigned char sDynRing[];      // TMA: SP_TMA_STAGES slabs
@@ -420,7 +425,7 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
     }
     // ntiles > 1 (few pods: p_end - p_begin <= SP_CHUNK, the host guarantees it): the block walks a run of tiles;
     // the pods are sorted once (first tile), the per-pod minimum is carried in sAcc and flushed once at the end.
-    const bool multi = ntiles > 1;
+    const bool multi = CAN_MULTI && ntiles > 1;        // (otherwise every tile of a run is flushed on its own: slower, still exact)
     // a slot's record: seven coalesced 16-byte loads + node index + permutation / free count
     auto load_tile = [&](int64_t t, int4 (&r)[7], int32_t &nd, uint32_t &m) {
         const int4 *src = rec + t * (7 * SP_THREADS) + tid;
@@ -491,7 +496,7 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
     sNode[tid] = node;
     const uint32_t nfree = (pm >> 24) & 0xFu;            // 0 for padding slots
     if (STREAM) {
-        sHotLo[tid] = pm;
+        if (!multi) sHotLo[tid] = pm;
     } else {
         uint32_t lo = 0, hi = 0;
 #pragma unroll
@@ -625,7 +630,13 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
                     if (cand < best) { best = cand; best_slot = s; best_m = m; cost = (uint32_t)(best >> 32); }
                 }
             }
-            if (best_slot >= 0) {
+            if (best_slot >= 0 && multi) {
+                const unsigned long long cand = ((unsigned long long)cost << 32) | (uint32_t)sNode[best_slot];
+                if (cand < sAcc[i]) {                        // position i belongs to this thread for the whole item
+                    sAcc[i] = cand;
+                    sWin[i] = ((uint32_t)tt << 16) | ((uint32_t)best_slot << 8) | (best_m & 0xFFu);
+                }
+            } else if (best_slot >= 0) {
                 // S' bit g set -> byte g of the one-hot words; OR the selected bytes together
                 uint32_t S;
                 if (STREAM) {                          // bit g of S' -> GPU index in the g-th 3-bit field of the permutation word
@@ -642,8 +653,7 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
                 }
                 const unsigned long long nid = (unsigned long long)(node_id_base + (long long)sNode[best_slot]);
                 const unsigned long long key = ((unsigned long long)cost << 40) | (nid << 8) | S;
-                if (multi) sAcc[i] = min(sAcc[i], key);      // position i belongs to this thread for the whole item
-                else atomicMin(&keys[c0 + sIdx[i]], key);
+                atomicMin(&keys[c0 + sIdx[i]], key);
             }
             if (multi) {                                     // the next tile starts from "no result" again
 #pragma unroll
@@ -654,8 +664,17 @@ score_pairs_sparse(const int4 *__restrict__ rec, const uint32_t *__restrict__ me
     }   // tiles of the item
     if (multi) {
         const int served = sOff[9];
-        for (int i = tid; i < served; i += SP_THREADS)
-            if (sIdx[i] != SP_DUMMY && sAcc[i] != ~0ull) atomicMin(&keys[p_begin + sIdx[i]], sAcc[i]);
+        for (int i = tid; i < served; i += SP_THREADS) {
+            const unsigned long long a = sAcc[i];
+            if (sIdx[i] == SP_DUMMY || a == ~0ull) continue;
+            const uint32_t w = sWin[i];
+            const uint32_t perm = __ldg(meta + (tile_first + (int64_t)(w >> 16)) * SP_THREADS + ((w >> 8) & 0xFFu));
+            uint32_t S = 0;
+#pragma unroll
+            for (int g = 0; g < 8; g++) S |= ((w >> g) & 1u) << ((perm >> (3 * g)) & 7u);
+            const unsigned long long nid = (unsigned long long)(node_id_base + (long long)(int32_t)(uint32_t)a);
+            atomicMin(&keys[p_begin + sIdx[i]], ((a >> 32) << 40) | (nid << 8) | S);
+        }
     }
 }
 
