@@ -66,3 +66,23 @@ def test_product_does_not_touch_oracle():
                 text = open(os.path.join(dirpath, fn), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), fn
                 assert "oracle_b" not in text and "oracle_a" not in text and "oracle/" not in text, fn
+
+
+def test_few_pod_kernel_stages_tiles_with_tma():
+    """The few-pod instantiations of the headline kernel (score_pairs_sparse<..., STREAM, TMA = 7 | 8>) must carry the
+    bulk-copy and mbarrier instructions in their SASS (UBLKCP / SYNCS: B200_PROFILING.md's mnemonics for cp.async.bulk
+    and mbarrier): the TMA path is compiled in, not a fallback to plain loads."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    fn, counts = None, {}
+    for line in sass.splitlines():
+        if "Function :" in line:
+            fn = line.split("Function :")[1].strip()
+        elif fn and ("UBLKCP" in line or "SYNCS.PHASECHK" in line):
+            counts[fn] = counts.get(fn, 0) + 1
+    tma = [f for f in counts if "score_pairs_sparse" in f and ("ELi7E" in f or "ELi8E" in f)]
+    assert len(tma) == 4, sorted(counts)          # byte / general keys x 7 / 8 blocks per SM
+    assert all(counts[f] >= 4 for f in tma)       # three bulk copies per slab + the phase wait, at least
