@@ -18,7 +18,7 @@ Prints ONE JSON line on rank 0.  Beyond the base contract:
                   instructions/s (ncu count of this build, profiles/k1s_counts.json) against SMs x 4 schedulers x
                   the SM clock sampled under load.  The algorithmic-bytes figure (260 B per pair)
                   is kept as `hbm_algorithmic` with the measured DRAM traffic beside it.
-  hbm_regime      the same kernel where HBM IS the roof: millions of nodes, 1 / 32 pods (node records streamed
+  hbm_regime      the same kernel where HBM IS the roof: millions of nodes, 1 .. 64 pods (node records streamed
                   once, hardly reused): DRAM GB/s against the measured copy peak.
   c5, c3          BASELINE configs[4] / configs[2] on this run's GPUs.
   noncollapsible  batches whose per-pod work cannot be memoised by k (per-pod min_mem; every pod distinct), with
@@ -733,7 +733,7 @@ def main():
                           "parity": {"ok": ok3, "pods_checked": S3, "against": "oracle over all 1M nodes"}}
         del t3, f3
 
-    # ---- the regime where HBM is the roof: millions of nodes, 1 / 32 pods (N = 1) ---------------------------
+    # ---- the regime where HBM is the roof: millions of nodes, 1 .. 64 pods (N = 1) --------------------------
     if extras and world == 1:
         n_big = 10_485_760
         tb, fb, _ = synth.gen_c2(n_big, 0, seed=synth.SEED_C5)
@@ -743,7 +743,7 @@ def main():
             up_big = sb.last_upload_ms
             pts = []
             from oracle import oracle_b
-            for pcount in (1, 32):
+            for pcount in (1, 8, 16, 32, 64):
                 _, _, pb = synth.gen_c2(0, pcount, seed=synth.SEED_C5)
                 dp = torch.from_numpy(pb).to(dev)
                 dk = torch.empty(pcount, dtype=torch.int64, device=dev)
@@ -760,7 +760,7 @@ def main():
         line["hbm_regime"] = {"nodes": n_big, "points": pts, "peak_gbs": peak, "peak_source": peak_src, "upload_ms": up_big,
                               "bytes_per_node_streamed": RECORD_BYTES,
                               "note": "1.26 GB of node records (> 126 MB L2), L2 flushed before every launch: every record comes from DRAM once; "
-                                      "dram_gbs_min = 120 B x nodes / time is a lower bound of the DRAM rate (ncu: profiles/r02_k1s_stream_*). "
+                                      "dram_gbs_min = 120 B x nodes / time is a lower bound of the DRAM rate (ncu: profiles/r02_k1s_tma_p{1,32}_ncu_raw.txt: dram__bytes_read = 1.2002 GB for 10M nodes, no over-fetch). Up to 64 pods the tiles are staged by cp.async.bulk (TMA) into shared memory, 7 / 8 blocks per SM. "
                                       "The algorithmic figure counts 260 B per pair, i.e. the uncompacted matrix."}
 
     # ---- N > 1: the single-process multi-device handle (in-library NCCL all-gather), on rank 0 ---------------
